@@ -1,0 +1,630 @@
+// C-ABI entry points of libiwae_b200.so and the host-side drivers that sequence the kernels.
+// See include/iwae_b200.h for the contract and the reference interfaces each entry point replaces.
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void iwae_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* iwae_last_error(void) { return g_err; }
+extern "C" int iwae_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+// arena
+// ---------------------------------------------------------------------------------------------
+int Arena::alloc(void** out, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  for (auto& b : blks) {
+    if (b.cap - b.off >= bytes) {
+      *out = b.p + b.off;
+      b.off += bytes;
+      return 0;
+    }
+  }
+  const size_t cap = std::max(bytes, (size_t)64 << 20);
+  char* p = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&p, cap));
+  blks.push_back({p, cap, bytes});
+  *out = p;
+  return 0;
+}
+void Arena::release() {
+  for (auto& b : blks) cudaFree(b.p);
+  blks.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+// model layout (Keras trainable_weights order)
+// ---------------------------------------------------------------------------------------------
+static void add_dense(ModelP& m, DenseP& d, int n_in, int n_out) {
+  d.n_in = n_in; d.n_out = n_out;
+  d.w = m.n_params; m.t_off.push_back(d.w); m.t_rows.push_back(n_in); m.t_cols.push_back(n_out);
+  m.n_params += (int64_t)n_in * n_out;
+  d.b = m.n_params; m.t_off.push_back(d.b); m.t_rows.push_back(n_out); m.t_cols.push_back(0);
+  m.n_params += n_out;
+}
+static void add_block(ModelP& m, BlockP& b, int n_in, int h, int d) {
+  add_dense(m, b.l1, n_in, h); add_dense(m, b.l2, h, h); add_dense(m, b.lmu, h, d); add_dense(m, b.lstd, h, d);
+}
+static void add_mlp3(ModelP& m, Mlp3P& p, int n_in, int h, int n_out) {
+  add_dense(m, p.d0, n_in, h); add_dense(m, p.d1, h, h); add_dense(m, p.d2, h, n_out);
+}
+
+static int build_model(const iwae_config& c, ModelP& m) {
+  m = ModelP();
+  m.cfg = c;
+  IWAE_REQUIRE(c.n_x > 0 && c.h1 > 0 && c.d1 > 0, "iwae_create: n_x, h1, d1 must be positive");
+  switch (c.kind) {
+    case IWAE_KIND_IWAE1:
+      IWAE_REQUIRE(c.n_cond == 0, "iwae_create: IWAE1 takes n_cond == 0");
+      add_block(m, m.enc1, c.n_x, c.h1, c.d1);
+      add_mlp3(m, m.dec, c.d1, c.h1, c.n_x);
+      break;
+    case IWAE_KIND_IWAE2:
+      IWAE_REQUIRE(c.n_cond == 0 && c.h2 > 0 && c.d2 > 0, "iwae_create: IWAE2 needs h2, d2 > 0 and n_cond == 0");
+      add_block(m, m.enc1, c.n_x, c.h1, c.d1);
+      add_block(m, m.enc2, c.d1, c.h2, c.d2);
+      add_block(m, m.dec21, c.d2, c.h2, c.d1);
+      add_mlp3(m, m.dec, c.d1, c.h1, c.n_x);
+      break;
+    case IWAE_KIND_CIWAE:
+    case IWAE_KIND_CIWAE_STD:
+      IWAE_REQUIRE(c.n_cond > 0, "iwae_create: CIWAE needs n_cond > 0");
+      add_block(m, m.enc1, c.n_x + c.n_cond, c.h1, c.d1);
+      add_mlp3(m, m.dec, c.d1 + c.n_cond, c.h1, c.n_x);
+      if (c.kind == IWAE_KIND_CIWAE) add_block(m, m.prior, c.n_cond, c.h1, c.d1);
+      break;
+    default:
+      IWAE_REQUIRE(false, "iwae_create: unknown kind %d", c.kind);
+  }
+  return 0;
+}
+
+extern "C" int iwae_create(const iwae_config* cfg, iwae_ctx** out) {
+  IWAE_REQUIRE(cfg && out, "iwae_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    iwae_set_error("iwae_create: no CUDA device (%s); libiwae_b200 has no CPU fallback",
+                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return 3;
+  }
+  iwae_ctx* ctx = new iwae_ctx();
+  int r = build_model(*cfg, ctx->model);
+  if (r) { delete ctx; return r; }
+  CUDA_TRY(cudaGetDevice(&ctx->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int iwae_destroy(iwae_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaDeviceSynchronize();
+  tc_release(ctx);
+  ctx->arena.release();
+  if (ctx->per_buf) cudaFree(ctx->per_buf);
+  if (ctx->stage_x) cudaFree(ctx->stage_x);
+  if (ctx->stage_aux) cudaFree(ctx->stage_aux);
+  delete ctx;
+  return 0;
+}
+
+// iwae_param_count / iwae_param_layout work without a device: a NULL-device context is never built,
+// so they are also offered through a config-only helper used by the CPU tests.
+extern "C" int iwae_param_count(const iwae_ctx* ctx, int64_t* n_params, int32_t* n_tensors) {
+  IWAE_REQUIRE(ctx, "iwae_param_count: null ctx");
+  if (n_params) *n_params = ctx->model.n_params;
+  if (n_tensors) *n_tensors = (int32_t)ctx->model.t_off.size();
+  return 0;
+}
+extern "C" int iwae_param_layout(const iwae_ctx* ctx, int64_t* offsets, int32_t* rows, int32_t* cols) {
+  IWAE_REQUIRE(ctx, "iwae_param_layout: null ctx");
+  for (size_t i = 0; i < ctx->model.t_off.size(); ++i) {
+    if (offsets) offsets[i] = ctx->model.t_off[i];
+    if (rows) rows[i] = ctx->model.t_rows[i];
+    if (cols) cols[i] = ctx->model.t_cols[i];
+  }
+  return 0;
+}
+// Device-free variant (host logic only): layout for a config.  n_tensors in/out = capacity / count.
+extern "C" int iwae_layout_for_config(const iwae_config* cfg, int64_t* n_params, int32_t* n_tensors,
+                                      int64_t* offsets, int32_t* rows, int32_t* cols) {
+  IWAE_REQUIRE(cfg, "iwae_layout_for_config: null cfg");
+  ModelP m;
+  IWAE_TRY(build_model(*cfg, m));
+  const int cap = n_tensors ? *n_tensors : 0;
+  if (n_params) *n_params = m.n_params;
+  if (n_tensors) *n_tensors = (int32_t)m.t_off.size();
+  for (size_t i = 0; i < m.t_off.size() && (int)i < cap; ++i) {
+    if (offsets) offsets[i] = m.t_off[i];
+    if (rows) rows[i] = m.t_rows[i];
+    if (cols) cols[i] = m.t_cols[i];
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward (fp32 path)
+// ---------------------------------------------------------------------------------------------
+struct Fwd {
+  int B = 0, k = 0; int64_t R = 0;
+  const float* x = nullptr; const float* y = nullptr;
+  const float* xin = nullptr; int64_t ld_xin = 0;      // encoder input [B, enc_in]
+  float *h1 = nullptr, *h2 = nullptr, *mu1 = nullptr, *std1 = nullptr;
+  float *eps1 = nullptr, *z1 = nullptr;
+  const float* zin = nullptr; int64_t ld_zin = 0;      // decoder input [R, dec_in]
+  float *a1 = nullptr, *a2 = nullptr, *logits = nullptr, *bpart = nullptr;
+  float *g1 = nullptr, *g2 = nullptr, *mu2 = nullptr, *std2 = nullptr, *eps2 = nullptr, *z2 = nullptr;
+  float *p1 = nullptr, *p2 = nullptr, *pmu = nullptr, *pstd = nullptr;   // IWAE2: [R,.]; CIWAE prior: [B,.]
+  float *yoh = nullptr;
+  float *lpxz = nullptr, *lpz = nullptr, *lq1 = nullptr, *lq2 = nullptr, *lp12 = nullptr, *lqst = nullptr;
+  float *log_w = nullptr, *al = nullptr, *iwae = nullptr, *vae = nullptr, *eq14 = nullptr, *kl = nullptr,
+        *dreg = nullptr, *snis1 = nullptr, *snis2 = nullptr;
+};
+
+struct FwdOpts {
+  bool keep_for_bwd = false;   // materialise logits, eps, al
+  bool want_dreg = false;
+};
+
+static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ldx, int64_t M, int act, float* Y,
+                     cudaStream_t st) {
+  GemmArgs g;
+  g.A = X; g.sa_m = ldx; g.sa_k = 1;
+  g.B = P + L.w; g.sb_k = L.n_out; g.sb_n = 1;
+  g.C = Y; g.ldc = L.n_out;
+  g.M = (int)M; g.N = L.n_out; g.K = L.n_in;
+  g.bias = P + L.b; g.act = act;
+  return gemm_f32(g, st);
+}
+
+static int block_fwd(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
+                     float* mu, float* sd, cudaStream_t st) {
+  IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st));
+  IWAE_TRY(dense_fwd(P, blk.l2, h1, blk.l1.n_out, M, ACT_TANH, h2, st));
+  IWAE_TRY(dense_fwd(P, blk.lmu, h2, blk.l2.n_out, M, ACT_NONE, mu, st));
+  IWAE_TRY(dense_fwd(P, blk.lstd, h2, blk.l2.n_out, M, ACT_EXP_EPS, sd, st));   // exp(a) + 1e-6 (iwae1.py:34,42)
+  return 0;
+}
+
+template <class T>
+static int pick(Arena& ar, T* user, size_t n, T** out) {
+  if (user) { *out = user; return 0; }
+  return ar.get(out, n);
+}
+
+static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const float* y, int B, int k, float beta,
+                            const float* eps1_in, const float* eps2_in, uint64_t seed, int64_t img_offset,
+                            const iwae_outputs* o, const FwdOpts& opt, Fwd& f, cudaStream_t st) {
+  const ModelP& m = ctx->model;
+  const iwae_config& c = m.cfg;
+  Arena& ar = ctx->arena;
+  static const iwae_outputs none = {};
+  if (!o) o = &none;
+  IWAE_REQUIRE(B > 0 && k > 0, "forward: B and k must be positive (B=%d k=%d)", B, k);
+  IWAE_REQUIRE(P && x, "forward: null params or x");
+  IWAE_REQUIRE(!m.cond() || y, "forward: CIWAE needs labels y");
+  const int64_t R = (int64_t)B * k;
+  IWAE_REQUIRE(R < ((int64_t)1 << 31) / 8, "forward: k*B too large for one call (%lld rows); chunk the batch", (long long)R);
+  f.B = B; f.k = k; f.R = R; f.x = x; f.y = y;
+  const int d1 = c.d1, d2 = c.d2, h1 = c.h1, h2 = c.h2, nx = c.n_x, nc = m.cond() ? c.n_cond : 0;
+
+  // ---- encoder on x (per image): q(z1|x)                                   iwae1.py:56-57
+  if (nc) {
+    float* xin; IWAE_TRY(ar.get(&xin, (size_t)B * (nx + nc)));
+    IWAE_TRY(concat_onehot(x, nx, nx, y, B, B, nc, xin, st));                 // task04.py:112-115
+    f.xin = xin; f.ld_xin = nx + nc;
+  } else { f.xin = x; f.ld_xin = nx; }
+  IWAE_TRY(ar.get(&f.h1, (size_t)B * h1)); IWAE_TRY(ar.get(&f.h2, (size_t)B * h1));
+  IWAE_TRY(pick(ar, o->q_mu, (size_t)B * d1, &f.mu1)); IWAE_TRY(pick(ar, o->q_std, (size_t)B * d1, &f.std1));
+  IWAE_TRY(block_fwd(P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, f.mu1, f.std1, st));
+
+  // ---- z1 = mu + std*eps, k samples                                        iwae1.py:59
+  IWAE_TRY(pick(ar, o->z1, (size_t)R * d1, &f.z1));
+  if (opt.keep_for_bwd) IWAE_TRY(ar.get(&f.eps1, (size_t)R * d1));
+  IWAE_TRY(sample_latent(f.mu1, f.std1, 1, eps1_in, f.eps1, f.z1, B, k, d1, seed, 1, img_offset, st));
+
+  // ---- IWAE2: q(z2|z1), z2, p(z1|z2)                                       iwae2.py:63-65,90
+  if (m.two_layer()) {
+    IWAE_TRY(ar.get(&f.g1, (size_t)R * h2)); IWAE_TRY(ar.get(&f.g2, (size_t)R * h2));
+    IWAE_TRY(ar.get(&f.mu2, (size_t)R * d2)); IWAE_TRY(ar.get(&f.std2, (size_t)R * d2));
+    IWAE_TRY(block_fwd(P, m.enc2, f.z1, d1, R, f.g1, f.g2, f.mu2, f.std2, st));
+    IWAE_TRY(pick(ar, o->z2, (size_t)R * d2, &f.z2));
+    if (opt.keep_for_bwd) IWAE_TRY(ar.get(&f.eps2, (size_t)R * d2));
+    IWAE_TRY(sample_latent(f.mu2, f.std2, 0, eps2_in, f.eps2, f.z2, B, k, d2, seed, 2, img_offset, st));
+    IWAE_TRY(ar.get(&f.p1, (size_t)R * h2)); IWAE_TRY(ar.get(&f.p2, (size_t)R * h2));
+    IWAE_TRY(ar.get(&f.pmu, (size_t)R * d1)); IWAE_TRY(ar.get(&f.pstd, (size_t)R * d1));
+    IWAE_TRY(block_fwd(P, m.dec21, f.z2, d2, R, f.p1, f.p2, f.pmu, f.pstd, st));
+  }
+  // ---- CIWAE learned prior p(z|y)                                          task04.py:123
+  if (m.learned_prior()) {
+    IWAE_TRY(ar.get(&f.yoh, (size_t)B * nc));
+    IWAE_TRY(onehot_f32(y, B, nc, f.yoh, st));
+    IWAE_TRY(ar.get(&f.p1, (size_t)B * h1)); IWAE_TRY(ar.get(&f.p2, (size_t)B * h1));
+    IWAE_TRY(ar.get(&f.pmu, (size_t)B * d1)); IWAE_TRY(ar.get(&f.pstd, (size_t)B * d1));
+    IWAE_TRY(block_fwd(P, m.prior, f.yoh, nc, B, f.p1, f.p2, f.pmu, f.pstd, st));
+  }
+
+  // ---- decoder p(x|z1)                                                     iwae1.py:79-85
+  if (nc) {
+    float* zin; IWAE_TRY(ar.get(&zin, (size_t)R * (d1 + nc)));
+    IWAE_TRY(concat_onehot(f.z1, d1, d1, y, B, (int)R, nc, zin, st));         // task04.py:119
+    f.zin = zin; f.ld_zin = d1 + nc;
+  } else { f.zin = f.z1; f.ld_zin = d1; }
+  IWAE_TRY(ar.get(&f.a1, (size_t)R * h1)); IWAE_TRY(ar.get(&f.a2, (size_t)R * h1));
+  IWAE_TRY(dense_fwd(P, m.dec.d0, f.zin, f.ld_zin, R, ACT_TANH, f.a1, st));
+  IWAE_TRY(dense_fwd(P, m.dec.d1, f.a1, h1, R, ACT_TANH, f.a2, st));
+  {
+    const bool mat = opt.keep_for_bwd || o->logits;
+    if (mat) IWAE_TRY(pick(ar, o->logits, (size_t)R * nx, &f.logits));
+    const int nt = gemm_f32_ntiles_n(nx, 0);
+    IWAE_TRY(ar.get(&f.bpart, (size_t)R * nt));
+    GemmArgs g;
+    g.A = f.a2; g.sa_m = h1; g.sa_k = 1;
+    g.B = P + m.dec.d2.w; g.sb_k = nx; g.sb_n = 1;
+    g.C = f.logits; g.ldc = nx;
+    g.M = (int)R; g.N = nx; g.K = h1; g.bias = P + m.dec.d2.b;
+    g.bern_x = x; g.bern_B = B; g.bern_partial = f.bpart;      // fused Bernoulli log-lik (iwae1.py:111)
+    IWAE_TRY(gemm_f32(g, st));
+    IWAE_TRY(pick(ar, o->lpxz, (size_t)R, &f.lpxz));
+    IWAE_TRY(bern_reduce_partials(f.bpart, (int)R, nt, f.lpxz, st));
+  }
+
+  // ---- Gaussian terms                                                      iwae1.py:107-109, iwae2.py:116-122
+  IWAE_TRY(pick(ar, o->lpz, (size_t)R, &f.lpz));
+  IWAE_TRY(pick(ar, o->lq1, (size_t)R, &f.lq1));
+  IWAE_TRY(normal_logp_rows(f.z1, f.mu1, f.std1, 1, 0.f, B, k, d1, f.lq1, st));
+  if (m.two_layer()) {
+    IWAE_TRY(pick(ar, o->lq2, (size_t)R, &f.lq2));
+    IWAE_TRY(pick(ar, o->lp12, (size_t)R, &f.lp12));
+    IWAE_TRY(normal_logp_rows(f.z2, nullptr, nullptr, 0, 0.f, B, k, d2, f.lpz, st));        // lpz2
+    IWAE_TRY(normal_logp_rows(f.z2, f.mu2, f.std2, 0, 0.f, B, k, d2, f.lq2, st));           // lqz2z1
+    IWAE_TRY(normal_logp_rows(f.z1, f.pmu, f.pstd, 0, 0.f, B, k, d1, f.lp12, st));          // lpz1z2
+  } else if (m.learned_prior()) {
+    IWAE_TRY(normal_logp_rows(f.z1, f.pmu, f.pstd, 1, 0.f, B, k, d1, f.lpz, st));           // lpzy
+  } else {
+    IWAE_TRY(normal_logp_rows(f.z1, nullptr, nullptr, 0, 0.f, B, k, d1, f.lpz, st));        // lpz
+  }
+  if (opt.want_dreg || o->dreg) {
+    IWAE_TRY(ar.get(&f.lqst, (size_t)R));
+    IWAE_TRY(normal_logp_rows(f.z1, f.mu1, f.std1, 1, 1e-6f, B, k, d1, f.lqst, st));        // task02.py:61-65
+  }
+  if (o->kl && !m.two_layer()) {
+    f.kl = o->kl;
+    IWAE_TRY(kl_rows(f.mu1, f.std1, B, d1, f.kl, st));                                      // iwae1.py:116
+  }
+
+  // ---- log-weights and reductions over k                                   iwae1.py:113-139
+  LogwArgs la;
+  la.B = B; la.k = k; la.beta = beta; la.two_layer = m.two_layer() ? 1 : 0;
+  la.lpxz = f.lpxz; la.lpz = f.lpz; la.lq1 = f.lq1; la.lq2 = f.lq2; la.lp12 = f.lp12; la.lq_stopped = f.lqst;
+  la.z1 = f.z1; la.z2 = f.z2; la.d1 = d1; la.d2 = d2;
+  f.log_w = o->log_w; f.al = o->al; f.iwae = o->iwae; f.vae = o->vae; f.eq14 = o->eq14;
+  f.snis1 = o->snis_z1; f.snis2 = m.two_layer() ? o->snis_z2 : nullptr;
+  if (opt.keep_for_bwd && !f.al) IWAE_TRY(ar.get(&f.al, (size_t)R));
+  if (f.lqst) IWAE_TRY(pick(ar, o->dreg, (size_t)B, &f.dreg));
+  la.log_w = f.log_w; la.al = f.al; la.iwae = f.iwae; la.vae = f.vae; la.eq14 = f.eq14; la.dreg = f.dreg;
+  la.snis1 = f.snis1; la.snis2 = f.snis2;
+  IWAE_TRY(logw_reduce(la, st));
+  return 0;
+}
+
+extern "C" int iwae_forward(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,
+                            float beta, const float* eps1, const float* eps2, uint64_t seed, int64_t img_offset,
+                            const iwae_outputs* outs, void* stream) {
+  IWAE_REQUIRE(ctx, "iwae_forward: null ctx");
+  ctx->arena.reset();
+  Fwd f; FwdOpts opt;
+  return forward_internal(ctx, params, x, y, B, k, beta, eps1, eps2, seed, img_offset, outs, opt, f,
+                          (cudaStream_t)stream);
+}
+
+static int grow_dev(float** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) CUDA_TRY(cudaFree(*p));
+  *p = nullptr; *cap = 0;
+  CUDA_TRY(cudaMalloc((void**)p, bytes));
+  *cap = bytes;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-sample log-likelihood evaluation (main.py:170-184)
+// ---------------------------------------------------------------------------------------------
+extern "C" int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
+                             uint64_t seed, int64_t img_offset, int32_t precision, float* out_per_example,
+                             double* out_sum, void* stream) {
+  IWAE_REQUIRE(ctx && params && x, "iwae_llh_eval: null argument");
+  IWAE_REQUIRE(N >= 0 && k > 0, "iwae_llh_eval: bad N=%lld k=%d", (long long)N, k);
+  cudaStream_t st = (cudaStream_t)stream;
+  const ModelP& m = ctx->model;
+  ctx->arena.reset();
+  float* per = out_per_example;
+  if (!per) {
+    IWAE_TRY(grow_dev(&ctx->per_buf, &ctx->per_cap, (size_t)std::max<int64_t>(N, 1) * sizeof(float)));
+    per = ctx->per_buf;
+  }
+  if (N == 0) {
+    if (out_sum) CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
+    return 0;
+  }
+  if (precision == IWAE_PREC_TC_F16) {
+    IWAE_TRY(tc_llh_eval(ctx, params, x, y, N, k, seed, img_offset, per, st));
+  } else {
+    IWAE_REQUIRE(precision == IWAE_PREC_FP32, "iwae_llh_eval: unknown precision %d", precision);
+    // chunk the images so that one chunk's activations stay around 256k rows
+    int64_t Bc = std::max<int64_t>(1, (int64_t)262144 / k);
+    Bc = std::min(Bc, N);
+    for (int64_t i0 = 0; i0 < N; i0 += Bc) {
+      const int Bi = (int)std::min<int64_t>(Bc, N - i0);
+      ctx->arena.reset();
+      iwae_outputs o = {};
+      o.iwae = per + i0;
+      Fwd f; FwdOpts opt;
+      IWAE_TRY(forward_internal(ctx, params, x + i0 * m.cfg.n_x, y ? y + i0 : nullptr, Bi, k, 1.0f, nullptr, nullptr,
+                                seed, img_offset + i0, &o, opt, f, st));
+    }
+  }
+  if (out_sum) IWAE_TRY(sum_to_double(per, N, out_sum, 0, st));
+  return 0;
+}
+
+extern "C" int iwae_llh_eval_host(iwae_ctx* ctx, const float* params, const float* x_host, const float* y_host,
+                                  int64_t N, int32_t k, uint64_t seed, int64_t img_offset, int32_t precision,
+                                  float* out_per_example_host, double* out_sum_host, void* stream) {
+  IWAE_REQUIRE(ctx && params && x_host, "iwae_llh_eval_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nx = ctx->model.cfg.n_x;
+  // persistent device staging (not the arena: iwae_llh_eval resets it)
+  const size_t xb = (size_t)N * nx * sizeof(float);
+  IWAE_TRY(grow_dev(&ctx->stage_x, &ctx->stage_x_cap, std::max(xb, (size_t)256)));
+  IWAE_TRY(grow_dev(&ctx->stage_aux, &ctx->stage_aux_cap, (size_t)N * 2 * sizeof(float) + 64));
+  float* d_x = ctx->stage_x;
+  float* d_aux = ctx->stage_aux;
+  double* d_sum = reinterpret_cast<double*>(d_aux);
+  float* d_per = d_aux + 16;
+  float* d_y = d_per + N;
+  CUDA_TRY(cudaMemcpyAsync(d_x, x_host, xb, cudaMemcpyHostToDevice, st));
+  if (y_host) CUDA_TRY(cudaMemcpyAsync(d_y, y_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, st));
+  IWAE_TRY(iwae_llh_eval(ctx, params, d_x, y_host ? d_y : nullptr, N, k, seed, img_offset, precision, d_per, d_sum, st));
+  if (out_per_example_host)
+    CUDA_TRY(cudaMemcpyAsync(out_per_example_host, d_per, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (out_sum_host) CUDA_TRY(cudaMemcpyAsync(out_sum_host, d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (fp32 path)
+// ---------------------------------------------------------------------------------------------
+// dW = X^T dY, db = colsum(dY)
+static int dense_bwd_w(const DenseP& L, const float* X, int64_t ldx, int64_t M, const float* dY, float* grads,
+                       cudaStream_t st) {
+  GemmArgs g;
+  g.A = X; g.sa_m = 1; g.sa_k = ldx;                 // A(i_in, row)
+  g.B = dY; g.sb_k = L.n_out; g.sb_n = 1;            // B(row, o)
+  g.C = grads + L.w; g.ldc = L.n_out;
+  g.M = L.n_in; g.N = L.n_out; g.K = (int)M;
+  g.small_tile = 1;
+  IWAE_TRY(gemm_f32(g, st));
+  return colsum_f32(dY, L.n_out, (int)M, L.n_out, grads + L.b, st);
+}
+// dX = dY W^T, optionally accumulated into dX and/or multiplied by tanh'(H) = 1 - H^2
+static int dense_bwd_x(const float* P, const DenseP& L, const float* dY, int64_t M, float* dX, int64_t ld_dx,
+                       int accumulate, const float* H, int64_t ld_h, cudaStream_t st) {
+  GemmArgs g;
+  g.A = dY; g.sa_m = L.n_out; g.sa_k = 1;
+  g.B = P + L.w; g.sb_k = 1; g.sb_n = L.n_out;       // B(o, i) = W[i, o]
+  g.C = dX; g.ldc = ld_dx;
+  g.M = (int)M; g.N = L.n_in; g.K = L.n_out;
+  g.accumulate = accumulate; g.mul_h = H; g.ld_h = ld_h;
+  return gemm_f32(g, st);
+}
+
+// BasicBlock backward from (dmu, da) where a is the std pre-activation.  dX may be null.
+static int block_bwd(iwae_ctx* ctx, const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M,
+                     const float* h1, const float* h2, const float* dmu, const float* da, float* grads, float* dX,
+                     cudaStream_t st) {
+  const int h = blk.l1.n_out;
+  float *dh2, *dh1;
+  IWAE_TRY(ctx->arena.get(&dh2, (size_t)M * h)); IWAE_TRY(ctx->arena.get(&dh1, (size_t)M * h));
+  IWAE_TRY(dense_bwd_w(blk.lmu, h2, h, M, dmu, grads, st));
+  IWAE_TRY(dense_bwd_w(blk.lstd, h2, h, M, da, grads, st));
+  IWAE_TRY(dense_bwd_x(P, blk.lmu, dmu, M, dh2, h, 0, nullptr, 0, st));
+  IWAE_TRY(dense_bwd_x(P, blk.lstd, da, M, dh2, h, 1, h2, h, st));            // (.. + ..) * (1 - h2^2)
+  IWAE_TRY(dense_bwd_w(blk.l2, h1, h, M, dh2, grads, st));
+  IWAE_TRY(dense_bwd_x(P, blk.l2, dh2, M, dh1, h, 0, h1, h, st));
+  IWAE_TRY(dense_bwd_w(blk.l1, X, ldx, M, dh1, grads, st));
+  if (dX) IWAE_TRY(dense_bwd_x(P, blk.l1, dh1, M, dX, blk.l1.n_in, 0, nullptr, 0, st));
+  return 0;
+}
+
+static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float beta, int objective, int B_norm,
+                             float* grads, cudaStream_t st) {
+  const ModelP& m = ctx->model;
+  const iwae_config& c = m.cfg;
+  Arena& ar = ctx->arena;
+  const int B = f.B, k = f.k; const int64_t R = f.R;
+  const int d1 = c.d1, d2 = c.d2, h1 = c.h1, nx = c.n_x;
+  // DReG's decoder part is the IWAE-ELBO gradient (task02.py:96)
+  const int dec_obj = (objective == IWAE_OBJ_DREG) ? IWAE_OBJ_IWAE_ELBO : objective;
+
+  float *g, *dl, *da2, *da1, *dzin;
+  IWAE_TRY(ar.get(&g, (size_t)R));
+  IWAE_TRY(row_coef(f.al, B, k, dec_obj, B_norm, g, st));
+  IWAE_TRY(ar.get(&dl, (size_t)R * nx));
+  IWAE_TRY(dlogits_f32(f.logits, f.x, g, (int)R, B, nx, dl, st));
+  // decoder MLP
+  IWAE_TRY(ar.get(&da2, (size_t)R * h1)); IWAE_TRY(ar.get(&da1, (size_t)R * h1));
+  IWAE_TRY(ar.get(&dzin, (size_t)R * m.dec_in()));
+  IWAE_TRY(dense_bwd_w(m.dec.d2, f.a2, h1, R, dl, grads, st));
+  IWAE_TRY(dense_bwd_x(P, m.dec.d2, dl, R, da2, h1, 0, f.a2, h1, st));
+  IWAE_TRY(dense_bwd_w(m.dec.d1, f.a1, h1, R, da2, grads, st));
+  IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, st));
+  IWAE_TRY(dense_bwd_w(m.dec.d0, f.zin, f.ld_zin, R, da1, grads, st));
+  IWAE_TRY(dense_bwd_x(P, m.dec.d0, da1, R, dzin, m.dec_in(), 0, nullptr, 0, st));
+
+  float* dz1_q = nullptr;
+  if (m.two_layer()) {
+    // lpz1z2 -> parameters of p(z1|z2)                                        iwae2.py:120
+    float *dpmu, *dpa, *dz2_p, *dmu2, *da_2;
+    IWAE_TRY(ar.get(&dpmu, (size_t)R * d1)); IWAE_TRY(ar.get(&dpa, (size_t)R * d1));
+    IWAE_TRY(gauss_rows_bwd(g, f.z1, f.pmu, f.pstd, R, d1, dpmu, dpa, st));
+    IWAE_TRY(ar.get(&dz2_p, (size_t)R * d2));
+    IWAE_TRY(block_bwd(ctx, P, m.dec21, f.z2, d2, R, f.p1, f.p2, dpmu, dpa, grads, dz2_p, st));
+    // z2 = mu2 + std2 eps2 ; lpz2 ; -lqz2z1                                   iwae2.py:65,116-118
+    IWAE_TRY(ar.get(&dmu2, (size_t)R * d2)); IWAE_TRY(ar.get(&da_2, (size_t)R * d2));
+    Latent2BwdArgs l2;
+    l2.R = (int)R; l2.d = d2; l2.g = g; l2.dz_p = dz2_p; l2.z = f.z2; l2.eps = f.eps2; l2.std = f.std2;
+    l2.dmu = dmu2; l2.da = da_2;
+    IWAE_TRY(latent2_bwd(l2, st));
+    IWAE_TRY(ar.get(&dz1_q, (size_t)R * d1));
+    IWAE_TRY(block_bwd(ctx, P, m.enc2, f.z1, d1, R, f.g1, f.g2, dmu2, da_2, grads, dz1_q, st));
+  }
+
+  // first stochastic layer
+  float *dmu1, *da_1, *dpmu_b = nullptr, *dpa_b = nullptr;
+  IWAE_TRY(ar.get(&dmu1, (size_t)B * d1)); IWAE_TRY(ar.get(&da_1, (size_t)B * d1));
+  Latent1BwdArgs l1;
+  l1.B = B; l1.k = k; l1.d = d1; l1.beta = beta; l1.objective = objective; l1.B_norm = B_norm;
+  l1.g = g; l1.al = f.al; l1.dz_dec = dzin; l1.ld_dz = m.dec_in(); l1.dz_q2 = dz1_q;
+  l1.z = f.z1; l1.eps = f.eps1; l1.mu = f.mu1; l1.std = f.std1;
+  if (m.two_layer()) { l1.prior_rows = 2; l1.pmu = f.pmu; l1.pstd = f.pstd; }
+  else if (m.learned_prior()) {
+    l1.prior_rows = 1; l1.pmu = f.pmu; l1.pstd = f.pstd;
+    IWAE_TRY(ar.get(&dpmu_b, (size_t)B * d1)); IWAE_TRY(ar.get(&dpa_b, (size_t)B * d1));
+    l1.dpmu = dpmu_b; l1.dpa = dpa_b;
+  }
+  l1.dmu = dmu1; l1.da = da_1;
+  IWAE_TRY(latent1_bwd(l1, st));
+  IWAE_TRY(block_bwd(ctx, P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, dmu1, da_1, grads, nullptr, st));
+  if (m.learned_prior())
+    IWAE_TRY(block_bwd(ctx, P, m.prior, f.yoh, c.n_cond, B, f.p1, f.p2, dpmu_b, dpa_b, grads, nullptr, st));
+  return 0;
+}
+
+static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, const float* y, int B, int k, float beta,
+                          int objective, int B_norm, const float* eps1, const float* eps2, uint64_t seed,
+                          int64_t img_offset, float* grads, const iwae_outputs* outs, cudaStream_t st) {
+  const ModelP& m = ctx->model;
+  IWAE_REQUIRE(grads, "iwae_grads: null grads");
+  IWAE_REQUIRE(objective >= IWAE_OBJ_VAE_ELBO && objective <= IWAE_OBJ_DREG, "unknown objective %d", objective);
+  // iwae2.IWAE.call has no 'vae_elbo_kl' key -> KeyError in the reference (iwae2.py:154-167,173)
+  IWAE_REQUIRE(!(m.two_layer() && objective == IWAE_OBJ_VAE_ELBO_KL), "KeyError: 'vae_elbo_kl' (two stochastic layers)");
+  IWAE_REQUIRE(!(objective == IWAE_OBJ_DREG && m.cfg.kind != IWAE_KIND_IWAE1), "DReG is defined for IWAE1 only (task02.py)");
+  if (B_norm <= 0) B_norm = B;
+  Fwd f; FwdOpts opt;
+  opt.keep_for_bwd = true;
+  opt.want_dreg = (objective == IWAE_OBJ_DREG);
+  IWAE_TRY(forward_internal(ctx, params, x, y, B, k, beta, eps1, eps2, seed, img_offset, outs, opt, f, st));
+  return backward_internal(ctx, params, f, beta, objective, B_norm, grads, st);
+}
+
+extern "C" int iwae_grads(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,
+                          float beta, int32_t objective, int32_t B_norm, const float* eps1, const float* eps2,
+                          uint64_t seed, int64_t img_offset, float* grads, const iwae_outputs* outs, void* stream) {
+  IWAE_REQUIRE(ctx, "iwae_grads: null ctx");
+  ctx->arena.reset();
+  return grads_internal(ctx, params, x, y, B, k, beta, objective, B_norm, eps1, eps2, seed, img_offset, grads, outs,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int iwae_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                              float beta2, float eps, int64_t t, void* stream) {
+  IWAE_REQUIRE(params && grads && m && v, "iwae_adam_step: null argument");
+  IWAE_REQUIRE(t >= 1, "iwae_adam_step: t is the step count after increment (>= 1)");
+  return adam_f32(params, grads, m, v, n, lr, beta1, beta2, eps, t, (cudaStream_t)stream);
+}
+
+extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x,
+                               const float* y, int32_t B, int32_t k, float beta, int32_t objective, const float* eps1,
+                               const float* eps2, uint64_t seed, int64_t img_offset, float lr, float beta1, float beta2,
+                               float adam_eps, int64_t t, const iwae_outputs* outs, void* stream) {
+  IWAE_REQUIRE(ctx && params && adam_m && adam_v, "iwae_train_step: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->arena.reset();
+  float* grads;
+  IWAE_TRY(ctx->arena.get(&grads, (size_t)ctx->model.n_params));
+  IWAE_TRY(grads_internal(ctx, params, x, y, B, k, beta, objective, B, eps1, eps2, seed, img_offset, grads, outs, st));
+  return adam_f32(params, grads, adam_m, adam_v, ctx->model.n_params, lr, beta1, beta2, adam_eps, t, st);
+}
+
+extern "C" int iwae_philox_normal(uint64_t seed, int32_t stream_id, int64_t img_offset, int32_t B, int32_t k, int32_t d,
+                                  float* out, void* stream) {
+  IWAE_REQUIRE(out && B > 0 && k > 0 && d > 0, "iwae_philox_normal: bad argument");
+  return philox_fill(seed, stream_id, img_offset, B, k, d, out, (cudaStream_t)stream);
+}
+
+extern "C" int iwae_decode(iwae_ctx* ctx, const float* params, const float* z, const float* x, const float* y,
+                           int32_t R, int32_t B, float* logits, float* lpxz, void* stream) {
+  IWAE_REQUIRE(ctx && params && z, "iwae_decode: null argument");
+  IWAE_REQUIRE(R > 0 && B > 0, "iwae_decode: R and B must be positive");
+  IWAE_REQUIRE(!lpxz || x, "iwae_decode: lpxz needs x");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ModelP& m = ctx->model;
+  const iwae_config& c = m.cfg;
+  Arena& ar = ctx->arena;
+  ar.reset();
+  const int nc = m.cond() ? c.n_cond : 0;
+  IWAE_REQUIRE(!nc || y, "iwae_decode: CIWAE needs labels y");
+  const float* zin = z; int64_t ld = c.d1;
+  if (nc) {
+    float* t; IWAE_TRY(ar.get(&t, (size_t)R * (c.d1 + nc)));
+    IWAE_TRY(concat_onehot(z, c.d1, c.d1, y, B, R, nc, t, st));
+    zin = t; ld = c.d1 + nc;
+  }
+  float *a1, *a2, *bpart = nullptr;
+  IWAE_TRY(ar.get(&a1, (size_t)R * c.h1)); IWAE_TRY(ar.get(&a2, (size_t)R * c.h1));
+  IWAE_TRY(dense_fwd(params, m.dec.d0, zin, ld, R, ACT_TANH, a1, st));
+  IWAE_TRY(dense_fwd(params, m.dec.d1, a1, c.h1, R, ACT_TANH, a2, st));
+  GemmArgs g;
+  g.A = a2; g.sa_m = c.h1; g.sa_k = 1;
+  g.B = params + m.dec.d2.w; g.sb_k = c.n_x; g.sb_n = 1;
+  g.C = logits; g.ldc = c.n_x; g.M = R; g.N = c.n_x; g.K = c.h1; g.bias = params + m.dec.d2.b;
+  const int nt = gemm_f32_ntiles_n(c.n_x, 0);
+  if (lpxz) {
+    IWAE_TRY(ar.get(&bpart, (size_t)R * nt));
+    g.bern_x = x; g.bern_B = B; g.bern_partial = bpart;
+  }
+  IWAE_REQUIRE(logits || lpxz, "iwae_decode: nothing to compute");
+  IWAE_TRY(gemm_f32(g, st));
+  if (lpxz) IWAE_TRY(bern_reduce_partials(bpart, R, nt, lpxz, st));
+  return 0;
+}
+
+extern "C" int iwae_sir(const float* al, int32_t L, const double* uniforms, int32_t n_uniforms, int32_t size,
+                        int64_t* out_idx, int32_t* out_consumed, void* stream) {
+  IWAE_REQUIRE(al && uniforms && out_idx && out_consumed, "iwae_sir: null argument");
+  IWAE_REQUIRE(L > 0 && size > 0, "iwae_sir: L and size must be positive");
+  return sir_launch(al, L, uniforms, n_uniforms, size, out_idx, out_consumed, (cudaStream_t)stream);
+}
+
+extern "C" int iwae_softmax_f32(const float* log_w, int32_t L, float* out, void* stream) {
+  IWAE_REQUIRE(log_w && out && L > 0, "iwae_softmax_f32: bad argument");
+  return softmax_vec_f32(log_w, L, out, (cudaStream_t)stream);
+}
+
+extern "C" int iwae_bernoulli_sample(const float* p, int64_t n, uint64_t seed, uint64_t epoch, float* out,
+                                     void* stream) {
+  IWAE_REQUIRE(p && out && n >= 0, "iwae_bernoulli_sample: bad argument");
+  return bernoulli_sample_f32(p, n, seed, epoch, out, (cudaStream_t)stream);
+}
+
+extern "C" int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, float* D, void* stream) {
+  IWAE_REQUIRE(A && B && D, "iwae_umma_selftest: null argument");
+  return umma_selftest(A, B, N, K, D, (cudaStream_t)stream);
+}

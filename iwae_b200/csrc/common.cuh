@@ -1,0 +1,170 @@
+// Internal declarations shared by the translation units of libiwae_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include "../../include/iwae_b200.h"
+
+void iwae_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      iwae_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));    \
+      return 1;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+#define IWAE_REQUIRE(cond, ...)                                                                 \
+  do {                                                                                          \
+    if (!(cond)) {                                                                              \
+      iwae_set_error(__VA_ARGS__);                                                              \
+      return 2;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+#define IWAE_TRY(expr)                                                                          \
+  do {                                                                                          \
+    int r__ = (expr);                                                                           \
+    if (r__ != 0) return r__;                                                                   \
+  } while (0)
+
+// ---- model description: offsets into the flat parameter buffer (Keras order) ----
+struct DenseP {
+  int64_t w = 0, b = 0;   // offsets (floats)
+  int n_in = 0, n_out = 0;
+};
+struct BlockP { DenseP l1, l2, lmu, lstd; };   // BasicBlock (iwae1.py:24-44)
+struct Mlp3P { DenseP d0, d1, d2; };           // decoder Sequential (iwae1.py:70-77)
+
+struct ModelP {
+  iwae_config cfg{};
+  BlockP enc1;    // encoder.encode_x_to_z / encode_x_to_z1
+  BlockP enc2;    // encoder.encode_z1_to_z2        (IWAE2)
+  BlockP dec21;   // decoder.decode_z2_to_z1        (IWAE2)
+  Mlp3P dec;      // decoder.decode_z_to_x / decode_z1_to_x
+  BlockP prior;   // conditional_prior_network      (CIWAE)
+  int64_t n_params = 0;
+  std::vector<int64_t> t_off;
+  std::vector<int32_t> t_rows, t_cols;
+  bool two_layer() const { return cfg.kind == IWAE_KIND_IWAE2; }
+  bool cond() const { return cfg.kind == IWAE_KIND_CIWAE || cfg.kind == IWAE_KIND_CIWAE_STD; }
+  bool learned_prior() const { return cfg.kind == IWAE_KIND_CIWAE; }
+  int enc_in() const { return cfg.n_x + (cond() ? cfg.n_cond : 0); }
+  int dec_in() const { return cfg.d1 + (cond() ? cfg.n_cond : 0); }
+};
+
+// ---- grow-only scratch arena (device memory owned by the context) ----
+struct Arena {
+  struct Blk { char* p; size_t cap; size_t off; };
+  std::vector<Blk> blks;
+  int alloc(void** out, size_t bytes);
+  void reset() { for (auto& b : blks) b.off = 0; }
+  void release();
+  template <class T> int get(T** out, size_t n) { return alloc((void**)out, n * sizeof(T)); }
+};
+
+struct TcPack;   // packed fp16 weights + program for the fused tcgen05 evaluation (eval_tc.cu)
+
+struct iwae_ctx {
+  ModelP model;
+  Arena arena;
+  int device = 0;
+  int sm_count = 148;
+  TcPack* tc = nullptr;
+  // persistent device staging for iwae_llh_eval / iwae_llh_eval_host (outlives arena resets)
+  float* per_buf = nullptr; size_t per_cap = 0;       // per-example results
+  float* stage_x = nullptr; size_t stage_x_cap = 0;   // x (and y) copied from the host
+  float* stage_aux = nullptr; size_t stage_aux_cap = 0;
+};
+
+// ---- fp32 kernels (kernels_f32.cu) ----
+enum { ACT_NONE = 0, ACT_TANH = 1, ACT_EXP_EPS = 2 };
+
+struct GemmArgs {
+  const float* A = nullptr; int64_t sa_m = 0, sa_k = 0;   // A(m,k) = A[m*sa_m + k*sa_k]
+  const float* B = nullptr; int64_t sb_k = 0, sb_n = 0;   // B(k,n) = B[k*sb_k + n*sb_n]
+  float* C = nullptr; int64_t ldc = 0;                    // C(m,n) row-major (may be null with bern)
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;                            // [N]
+  int act = ACT_NONE;
+  int accumulate = 0;                                     // v += C_old before mul_h
+  const float* mul_h = nullptr; int64_t ld_h = 0;         // v *= (1 - H(m,n)^2)   (tanh backward)
+  const float* bern_x = nullptr; int bern_B = 0;          // fused Bernoulli log-lik: x[(m % B), n]
+  float* bern_partial = nullptr;                          // [M, n_tiles_n] partial row sums
+  int small_tile = 0;                                     // 32x32 tiles (more CTAs for skinny outputs)
+};
+int gemm_f32(const GemmArgs& a, cudaStream_t st);
+int gemm_f32_ntiles_n(int N, int small_tile);
+
+int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st);
+int concat_onehot(const float* x, int64_t ldx, int n, const float* y, int B, int rows, int nc,
+                  float* out, cudaStream_t st);   // out[r] = [x[r, :n] | onehot(y[r % B])]
+int onehot_f32(const float* y, int B, int nc, float* out, cudaStream_t st);
+
+// z = mu + std*eps.  bcast: mu/std are [B,d] shared by all k samples, else [R,d].
+// eps_in null -> Philox (seed, stream_id, img_offset); eps_out (optional) receives the noise used.
+int sample_latent(const float* mu, const float* std, int bcast, const float* eps_in, float* eps_out,
+                  float* z, int B, int k, int d, uint64_t seed, int stream_id, int64_t img_offset,
+                  cudaStream_t st);
+int philox_fill(uint64_t seed, int stream_id, int64_t img_offset, int B, int k, int d, float* out,
+                cudaStream_t st);
+
+// out[r] = sum_j log N(z[r,j]; mu, std) in TFP's op order; mu==null -> standard normal.
+// std_extra is added to std (DReG's second +1e-6, task02.py:61-63).
+int normal_logp_rows(const float* z, const float* mu, const float* std, int bcast, float std_extra,
+                     int B, int k, int d, float* out, cudaStream_t st);
+int kl_rows(const float* mu, const float* std, int B, int d, float* out, cudaStream_t st);
+int bern_reduce_partials(const float* partial, int R, int nt, float* lpxz, cudaStream_t st);
+int bern_logp_rows(const float* logits, const float* x, int R, int B, int n, float* lpxz, cudaStream_t st);
+
+struct LogwArgs {
+  int B = 0, k = 0; float beta = 1.f; int two_layer = 0;
+  const float *lpxz = nullptr, *lpz = nullptr, *lq1 = nullptr, *lq2 = nullptr, *lp12 = nullptr;
+  const float* lq_stopped = nullptr;        // DReG
+  const float *z1 = nullptr, *z2 = nullptr; int d1 = 0, d2 = 0;
+  float *log_w = nullptr, *al = nullptr, *iwae = nullptr, *vae = nullptr, *eq14 = nullptr, *dreg = nullptr;
+  float *snis1 = nullptr, *snis2 = nullptr;
+};
+int logw_reduce(const LogwArgs& a, cudaStream_t st);
+int sum_to_double(const float* v, int64_t n, double* acc, int accumulate, cudaStream_t st);
+
+// backward helpers
+int row_coef(const float* al, int B, int k, int objective, int B_norm, float* g, cudaStream_t st);
+int dlogits_f32(const float* logits, const float* x, const float* g, int R, int B, int n, float* dl,
+                cudaStream_t st);
+struct Latent1BwdArgs {   // first stochastic layer: mu/std broadcast over k
+  int B = 0, k = 0, d = 0; float beta = 1.f; int objective = 0; int B_norm = 1;
+  const float *g = nullptr, *al = nullptr;
+  const float* dz_dec = nullptr; int64_t ld_dz = 0;    // [R, ld] gradient reaching z through the decoder
+  const float* dz_q2 = nullptr;                        // [R, d] through q(z2|z1) (IWAE2) or null
+  const float *z = nullptr, *eps = nullptr, *mu = nullptr, *std = nullptr;
+  const float *pmu = nullptr, *pstd = nullptr; int prior_rows = 0;  // 0: N(0,1); 1: [B,d] (CIWAE); 2: [R,d] (IWAE2 p(z1|z2))
+  float *dmu = nullptr, *da = nullptr;                 // [B,d] grads wrt mu and the std pre-activation
+  float *dpmu = nullptr, *dpa = nullptr;               // prior block grads: [B,d] (CIWAE) or [R,d] (IWAE2)
+};
+int latent1_bwd(const Latent1BwdArgs& a, cudaStream_t st);
+struct Latent2BwdArgs {   // second stochastic layer of IWAE2: everything per row
+  int R = 0, d = 0; const float* g = nullptr;
+  const float *dz_p = nullptr, *z = nullptr, *eps = nullptr, *std = nullptr;
+  float *dmu = nullptr, *da = nullptr;
+};
+int latent2_bwd(const Latent2BwdArgs& a, cudaStream_t st);
+int gauss_rows_bwd(const float* g, const float* z, const float* pmu, const float* pstd, int64_t R, int d,
+                   float* dpmu, float* dpa, cudaStream_t st);
+
+int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+             float eps, int64_t t, cudaStream_t st);
+int bernoulli_sample_f32(const float* p, int64_t n, uint64_t seed, uint64_t epoch, float* out, cudaStream_t st);
+int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64_t* out_idx,
+               int32_t* out_consumed, cudaStream_t st);
+int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st);
+
+// ---- fused tcgen05 evaluation (eval_tc.cu) ----
+int tc_pack_weights(iwae_ctx* ctx, const float* params, cudaStream_t st);
+int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k,
+                uint64_t seed, int64_t img_offset, float* out_per_example, cudaStream_t st);
+void tc_release(iwae_ctx* ctx);
+int umma_selftest(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);

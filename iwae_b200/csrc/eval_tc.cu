@@ -1,0 +1,843 @@
+// Fused tcgen05 evaluation kernel: the k-sample importance-weighted log-likelihood of main.py:170-184
+// in ONE pass per 128-row tile, with every activation and all 784 logits staying on chip.
+//
+// One CTA owns one tile (<=128 samples of ONE image) at a time and walks a static layer "program":
+//   z1 = mu1(x) + std1(x)*eps   (Philox in registers)              -> fp16 A operand in smem
+//   [IWAE2]  q(z2|z1): tanh,tanh,(mu2|log-std2) -> z2 ; p(z1|z2): tanh,tanh,(mu|log-std) -> log p(z1|z2)
+//   p(x|z1): tanh, tanh, 784 logits -> Bernoulli log-lik reduced in the epilogue (logits never leave TMEM)
+// Roles (192 threads): warp 0 = weight producer (cp.async.bulk slabs through an mbarrier ring; weights are
+// fp16, pre-packed in the exact smem image, ~0.55 MB/tile from L2), warp 1 = MMA issuer (tcgen05.mma,
+// kind::f16, M=128, fp32 accumulators in TMEM, two 128-column accumulator buffers), warps 2-5 = epilogue
+// (tcgen05.ld -> bias is already folded into the GEMM through a constant-1 column -> tanh / exp / softplus
+// -> fp16 back to smem for the next layer, log-density terms accumulated per row in registers).
+// Two CTAs are resident per SM (<=113 KB smem, 256 TMEM columns each) so one CTA's epilogue overlaps the
+// other CTA's MMAs.  Operand layout: no-swizzle K-major core matrices, element (row,k) at
+// (k/8)*rows*16 + row*16 + (k%8)*2 bytes, i.e. LBO = rows*16 (K direction), SBO = 128 (M/N direction).
+#include "common.cuh"
+#include "rng.cuh"
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdio.h>
+#include <algorithm>
+
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("iwae_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate, M=128
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=0.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (bit4), a=b=f16 (0), K-major both,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test GEMM: D[128,N] = A[128,K] B[N,K]^T through exactly the staging the fused kernel uses.
+// variant 0: LBO = K-direction stride, SBO = M/N-direction stride (CUTLASS canonical); 1: swapped.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int N,
+                                                            int K, float* __restrict__ D, int variant) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int Kp = (K + 15) & ~15;
+  uint8_t* sA = smem;                          // [Kp/8][128][8] halves
+  uint8_t* sB = smem + (size_t)Kp * 128 * 2;   // [Kp/8][N][8] halves
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * Kp; i += 128) {
+    const int r = i / Kp, k = i % Kp;
+    const float v = (k < K) ? A[(size_t)r * K + k] : 0.f;
+    *reinterpret_cast<__half*>(sA + (size_t)(k >> 3) * 128 * 16 + r * 16 + (k & 7) * 2) = __float2half_rn(v);
+  }
+  for (int i = tid; i < N * Kp; i += 128) {
+    const int n = i / Kp, k = i % Kp;
+    const float v = (k < K) ? B[(size_t)n * K + k] : 0.f;
+    *reinterpret_cast<__half*>(sB + (size_t)(k >> 3) * N * 16 + n * 16 + (k & 7) * 2) = __float2half_rn(v);
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, ncols); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc((uint32_t)N);
+    const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16, sbo = 128;
+    for (int ks = 0; ks < Kp / 16; ++ks) {
+      const uint32_t a_addr = smem_u32(sA) + ks * 2 * lboA;
+      const uint32_t b_addr = smem_u32(sB) + ks * 2 * lboB;
+      const uint64_t ad = variant ? make_smem_desc(a_addr, sbo, lboA) : make_smem_desc(a_addr, lboA, sbo);
+      const uint64_t bd = variant ? make_smem_desc(b_addr, sbo, lboB) : make_smem_desc(b_addr, lboB, sbo);
+      umma_f16(tmem_base, ad, bd, idesc, ks > 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0, 900);
+  tc_fence_after();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) D[(size_t)row * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused evaluation kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_M = 128;
+constexpr int MAX_LAYERS = 9;
+constexpr int MAX_CHUNKS = 7;
+constexpr int CHUNK_N_MAX = 112;
+constexpr int NSTAGES = 4;
+constexpr int SLAB_K = 32;
+constexpr int SLAB_BYTES = CHUNK_N_MAX * SLAB_K * 2;   // 7168
+constexpr int KZ_MAX = 112;                            // K capacity of the z1 buffer
+constexpr int KP_MAX = 208;                            // K capacity of the activation buffer
+constexpr int BUFZ_BYTES = TILE_M * KZ_MAX * 2;        // 28672
+constexpr int BUFP_BYTES = TILE_M * KP_MAX * 2;        // 53248
+constexpr int NX_MAX = 784;
+constexpr int D_MAX = 104;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 256;
+
+enum { EPI_TANH = 0, EPI_GSAMPLE = 1, EPI_GLOGP = 2, EPI_BERN = 3 };
+
+struct Layer {
+  int kind, src, dst;          // src/dst: 0 = z1 buffer, 1 = activation buffer
+  int k_pad;                   // multiple of 16 (includes the constant-1 bias column)
+  int n_real;                  // TANH: units, GSAMPLE/GLOGP: latent dims, BERN: pixels
+  int next_kpad;               // K of the consumer of this layer's output (0 = none)
+  int nchunks;
+  int chunk_n[MAX_CHUNKS];     // MMA N of the chunk (multiple of 16, <= 112)
+  int chunk_cnt[MAX_CHUNKS];   // real units / dims / pixels in the chunk
+  int chunk_off[MAX_CHUNKS];   // first unit / dim / pixel of the chunk
+  int wait_act, signal_act, inplace;
+};
+struct Program {
+  int nlayers, two_layer, cond, learned_prior;
+  int d1, d2, nc, nx, kz_pad;  // kz_pad: K of the layers that read z1
+  Layer L[MAX_LAYERS];
+};
+
+struct EvalArgs {
+  const uint8_t* wpack;        // packed fp16 weight slabs, program order
+  const float* x;              // [N, nx]
+  const float* y;              // [N] or null
+  const float* mu1;            // [N, d1]
+  const float* std1;           // [N, d1]
+  const float* pmu;            // [N, d1] learned prior (CIWAE) or null
+  const float* pstd;
+  float2* partial;             // [N * tiles_per_img] (max, sum exp)
+  int64_t n_tiles;
+  int tiles_per_img, rows_per_tile, k;
+  uint64_t seed; int64_t img_offset;
+};
+
+__constant__ Program c_prog;
+
+struct __align__(16) SmemLayout {
+  uint8_t bufZ[BUFZ_BYTES];
+  uint8_t bufP[BUFP_BYTES];
+  uint8_t ring[NSTAGES][SLAB_BYTES];
+  float sgn[NX_MAX];           // 1 - 2x per pixel of the current image
+  float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX];
+  float red[8];
+  uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready;
+  uint32_t tmem_base;
+  int label;
+};
+
+#define LOG2PI_HALF_F 0.91893853320467274178f
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <bool FAST>
+__device__ __forceinline__ float act_tanh(float v) {
+  if (FAST) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+  return tanhf(v);
+}
+template <bool FAST>
+__device__ __forceinline__ float act_exp(float v) { return FAST ? __expf(v) : expf(v); }
+template <bool FAST>
+__device__ __forceinline__ float act_log(float v) { return FAST ? __logf(v) : logf(v); }
+
+// store 16 consecutive k values (two 16-byte vectors) of one row into an A-operand buffer
+__device__ __forceinline__ void store16(uint8_t* buf, int row, int k0, const float (&v)[16]) {
+  uint4 a = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+  uint4 b = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+  *reinterpret_cast<uint4*>(buf + (size_t)(k0 >> 3) * (TILE_M * 16) + row * 16) = a;
+  *reinterpret_cast<uint4*>(buf + (size_t)((k0 >> 3) + 1) * (TILE_M * 16) + row * 16) = b;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs args) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
+  const Program& P = c_prog;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], 4); }
+    mbar_init(&S.act_ready, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&S.tmem_base, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_base;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+        const uint8_t* src = args.wpack;
+        for (int l = 0; l < P.nlayers; ++l) {
+          const Layer& Ly = P.L[l];
+          for (int c = 0; c < Ly.nchunks; ++c) {
+            for (int k0 = 0; k0 < Ly.k_pad; k0 += SLAB_K) {
+              const uint32_t bytes = (uint32_t)Ly.chunk_n[c] * (uint32_t)min(SLAB_K, Ly.k_pad - k0) * 2u;
+              mbar_wait(&S.empty[stage], phase ^ 1, 100);
+              mbar_expect_tx(&S.full[stage], bytes);
+              bulk_g2s(S.ring[stage], src, bytes, &S.full[stage]);
+              src += bytes;
+              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, act_phase = 0, cc = 0;
+      uint32_t empty_phase[2] = {0, 0};
+      const uint32_t zaddr = smem_u32(S.bufZ), paddr = smem_u32(S.bufP);
+      for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < P.nlayers; ++l) {
+          const Layer& Ly = P.L[l];
+          if (Ly.wait_act) { mbar_wait(&S.act_ready, act_phase, 200); act_phase ^= 1; tc_fence_after(); }
+          const uint32_t a_base = Ly.src ? paddr : zaddr;
+          for (int c = 0; c < Ly.nchunks; ++c) {
+            const uint32_t buf = cc & 1;
+            mbar_wait(&S.acc_empty[buf], empty_phase[buf] ^ 1, 201);
+            empty_phase[buf] ^= 1;
+            tc_fence_after();
+            const uint32_t n = (uint32_t)Ly.chunk_n[c];
+            const uint32_t idesc = make_idesc(n);
+            const uint32_t d_tmem = tmem_base + buf * 128;
+            for (int k0 = 0; k0 < Ly.k_pad; k0 += SLAB_K) {
+              mbar_wait(&S.full[stage], phase, 202);
+              tc_fence_after();
+              const int ksteps = min(SLAB_K, Ly.k_pad - k0) / 16;
+              const uint32_t b_base = smem_u32(S.ring[stage]);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t kk = (uint32_t)k0 + 16u * ks;
+                const uint64_t ad = make_smem_desc(a_base + (kk >> 3) * (TILE_M * 16), TILE_M * 16, 128);
+                const uint64_t bd = make_smem_desc(b_base + (uint32_t)ks * 2u * n * 16u, n * 16u, 128);
+                umma_f16(d_tmem, ad, bd, idesc, kk > 0);
+              }
+              umma_commit(&S.empty[stage]);     // slab consumed when these MMAs retire
+              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&S.acc_full[buf]);
+            ++cc;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (one row per thread) =====================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;   // 0..127 among epilogue threads
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t full_phase[2] = {0, 0};
+    uint32_t cc = 0;
+    const int d1 = P.d1, nx = P.nx;
+
+    for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+      const int64_t img = tile / args.tiles_per_img;
+      const int tin = (int)(tile % args.tiles_per_img);
+      const int s = tin * args.rows_per_tile + row;                 // sample index of this row
+      const bool valid = (row < args.rows_per_tile) && (s < args.k);
+
+      // ---- per-image constants into smem
+      epi_bar_sync();
+      for (int j = et; j < nx; j += 128) S.sgn[j] = 1.f - 2.f * __ldg(args.x + img * nx + j);
+      for (int j = et; j < d1; j += 128) {
+        const float sd = __ldg(args.std1 + img * d1 + j);
+        S.mu[j] = __ldg(args.mu1 + img * d1 + j); S.sd[j] = sd; S.lsd[j] = logf(sd);
+        if (P.learned_prior) {
+          const float ps = __ldg(args.pstd + img * d1 + j);
+          S.pmu[j] = __ldg(args.pmu + img * d1 + j); S.psd[j] = ps; S.lpsd[j] = logf(ps);
+        }
+      }
+      if (et == 0 && P.cond) S.label = (int)(unsigned char)(int)__ldg(args.y + img);
+      epi_bar_sync();
+
+      // ---- stage 0: z1 = mu + std*eps (A.2), lq1, lpz; fp16 z1 | onehot(y) | 1 | 0.. into bufZ
+      float lq1 = 0.f, lpz = 0.f, lq2 = 0.f, lp12 = 0.f, lpxz = 0.f;
+      {
+        const uint32_t gimg = (uint32_t)(args.img_offset + img);
+        const int one_col = d1 + P.nc;
+        for (int k0 = 0; k0 < P.kz_pad; k0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int j0 = k0 + 4 * qq;
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            if (j0 < d1) {
+              const float4 n4 = philox_normal4(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
+              e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = j0 + i;
+              float val = 0.f;
+              if (j < d1) {
+                const float sd = S.sd[j], m = S.mu[j];
+                const float z = e[i] * sd + m;
+                const float t = z / sd - m / sd;                         // TFP op order
+                lq1 += -0.5f * t * t - (LOG2PI_HALF_F + S.lsd[j]);
+                if (!P.two_layer) {
+                  if (P.learned_prior) {
+                    const float ps = S.psd[j];
+                    const float tp = z / ps - S.pmu[j] / ps;
+                    lpz += -0.5f * tp * tp - (LOG2PI_HALF_F + S.lpsd[j]);
+                  } else {
+                    lpz += -0.5f * z * z - LOG2PI_HALF_F;
+                  }
+                }
+                val = z;
+              } else if (j < one_col) {
+                val = (S.label == j - d1) ? 1.f : 0.f;
+              } else if (j == one_col) {
+                val = 1.f;
+              }
+              v[4 * qq + i] = val;
+            }
+          }
+          store16(S.bufZ, row, k0, v);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.act_ready);
+
+      // ---- layers
+      for (int l = 0; l < P.nlayers; ++l) {
+        const Layer& Ly = P.L[l];
+        uint8_t* dst = Ly.dst ? S.bufP : S.bufZ;
+        if (Ly.inplace && Ly.nchunks > 1) {
+          // all chunks' MMAs must have retired before the input buffer is overwritten
+          for (int c = 0; c < Ly.nchunks; ++c) {
+            const uint32_t b = (cc + c) & 1;
+            mbar_wait(&S.acc_full[b], full_phase[b], 300);
+            full_phase[b] ^= 1;
+          }
+        }
+        for (int c = 0; c < Ly.nchunks; ++c) {
+          const uint32_t buf = cc & 1;
+          if (!(Ly.inplace && Ly.nchunks > 1)) {
+            mbar_wait(&S.acc_full[buf], full_phase[buf], 301);
+            full_phase[buf] ^= 1;
+          }
+          tc_fence_after();
+          const uint32_t tbase = tmem_base + lane_addr + buf * 128;
+          const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
+
+          if (Ly.kind == EPI_TANH) {
+            for (int g = 0; g < cn; g += 16) {
+              uint32_t r[16];
+              tmem_ld16(tbase + g, r);
+              tmem_ld_wait();
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int u = off + g + i;
+                float t = act_tanh<FAST>(__uint_as_float(r[i]));
+                if (u >= Ly.n_real) t = (u == Ly.n_real) ? 1.f : 0.f;      // constant-1 bias column, zero pad
+                v[i] = t;
+              }
+              if (off + g < Ly.next_kpad) store16(dst, row, off + g, v);
+            }
+          } else if (Ly.kind == EPI_GSAMPLE) {
+            // columns [0,cnt) = mu2, [cnt,2cnt) = log-std2 pre-activation; z2 = mu2 + std2*eps2 (iwae2.py:65)
+            const uint32_t gimg = (uint32_t)(args.img_offset + img);
+            for (int g = 0; g < Ly.next_kpad; g += 16) {
+              float v[16];
+              if (g < cnt) {
+                uint32_t rm[16], ra[16];
+                tmem_ld16(tbase + g, rm);
+                tmem_ld16(tbase + cnt + g, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                  const float4 n4 = philox_normal4(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g) >> 2) + qq);
+                  const float e[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const int j = g + 4 * qq + i;
+                    float val = 0.f;
+                    if (j < cnt) {
+                      const float m = __uint_as_float(rm[4 * qq + i]);
+                      const float sd = act_exp<FAST>(__uint_as_float(ra[4 * qq + i])) + 1e-6f;
+                      const float z = e[i] * sd + m;
+                      const float t = z / sd - m / sd;
+                      lq2 += -0.5f * t * t - (LOG2PI_HALF_F + act_log<FAST>(sd));      // iwae2.py:118
+                      lpz += -0.5f * z * z - LOG2PI_HALF_F;                             // iwae2.py:116
+                      val = z;
+                    } else if (j == cnt) {
+                      val = 1.f;
+                    }
+                    v[4 * qq + i] = val;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (g + i == cnt) ? 1.f : 0.f;
+              }
+              store16(dst, row, g, v);
+            }
+          } else if (Ly.kind == EPI_GLOGP) {
+            // columns [0,cnt) = mu, [cnt,2cnt) = log-std pre-activation of p(z1|z2) for dims off..off+cnt
+            for (int g = 0; g < cnt; g += 16) {
+              uint32_t rm[16], ra[16];
+              tmem_ld16(tbase + g, rm);
+              tmem_ld16(tbase + cnt + g, ra);
+              tmem_ld_wait();
+              const uint4 za = *reinterpret_cast<const uint4*>(S.bufZ + (size_t)((off + g) >> 3) * (TILE_M * 16) + row * 16);
+              const uint4 zb = *reinterpret_cast<const uint4*>(S.bufZ + (size_t)(((off + g) >> 3) + 1) * (TILE_M * 16) + row * 16);
+              const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (g + i < cnt) {
+                  const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
+                  const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                  const float m = __uint_as_float(rm[i]);
+                  const float sd = act_exp<FAST>(__uint_as_float(ra[i])) + 1e-6f;
+                  const float t = z / sd - m / sd;
+                  lp12 += -0.5f * t * t - (LOG2PI_HALF_F + act_log<FAST>(sd));          // iwae2.py:120
+                }
+              }
+            }
+          } else {   // EPI_BERN: log p(x|z) = -softplus((1-2x) l), product-of-(1+e^-|s|) batching of the logs
+            float relu_sum = 0.f, prod = 1.f;
+            for (int g = 0; g < cn; g += 16) {
+              uint32_t r[16];
+              tmem_ld16(tbase + g, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int pix = off + g + i;
+                if (g + i < cnt) {
+                  const float sv = __uint_as_float(r[i]) * S.sgn[pix];
+                  relu_sum += fmaxf(sv, 0.f);
+                  prod = fmaf(prod, act_exp<FAST>(-fabsf(sv)), prod);
+                }
+              }
+            }
+            lpxz -= relu_sum + act_log<FAST>(prod);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.acc_empty[buf]);
+          ++cc;
+        }
+        if (Ly.signal_act) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.act_ready);
+        }
+      }
+
+      // ---- log-weight of this row and the tile's (max, sum exp) partial
+      float lw = P.two_layer ? (lpxz + lp12 + lpz - lq1 - lq2) : (lpxz + (lpz - lq1));
+      if (!valid) lw = -INFINITY;
+      float mx = lw;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      epi_bar_sync();
+      if (lane == 0) S.red[warp - 2] = mx;
+      epi_bar_sync();
+      mx = fmaxf(fmaxf(S.red[0], S.red[1]), fmaxf(S.red[2], S.red[3]));
+      float se = valid ? expf(lw - mx) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      if (lane == 0) S.red[4 + warp - 2] = se;
+      epi_bar_sync();
+      if (et == 0) args.partial[tile] = make_float2(mx, S.red[4] + S.red[5] + S.red[6] + S.red[7]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// per image: logmeanexp over its tiles' partials (utils.logmeanexp, utils.py:6-8)
+__global__ void combine_partials_kernel(const float2* __restrict__ partial, int64_t N, int tiles_per_img, int k,
+                                        float* __restrict__ out) {
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float mx = -INFINITY;
+  for (int t = 0; t < tiles_per_img; ++t) mx = fmaxf(mx, partial[n * tiles_per_img + t].x);
+  float se = 0.f;
+  for (int t = 0; t < tiles_per_img; ++t) {
+    const float2 p = partial[n * tiles_per_img + t];
+    se += p.y * expf(p.x - mx);
+  }
+  out[n] = logf(se / (float)k) + mx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: fp32 [in,out] Keras kernels -> fp16 slabs in the exact smem image, bias folded in as
+// K-row `k_real`.  One launch per layer; one thread per packed half.
+// ------------------------------------------------------------------------------------------------
+struct PackLayer {
+  const float *W, *b;       // primary kernel [k_real, ldw] and bias
+  const float *W2, *b2;     // second head (log-std) for Gaussian layers, else null
+  int k_real, k_pad, ldw;
+  int nchunks, gauss;
+  int chunk_n[MAX_CHUNKS], chunk_cnt[MAX_CHUNKS], chunk_off[MAX_CHUNKS];
+  int64_t chunk_base[MAX_CHUNKS];   // half offset of the chunk's first slab inside the packed buffer
+};
+
+__global__ void pack_layer_kernel(PackLayer pl, __half* __restrict__ out) {
+  for (int c = 0; c < pl.nchunks; ++c) {
+    const int cn = pl.chunk_n[c], cnt = pl.chunk_cnt[c], off = pl.chunk_off[c];
+    const int total = cn * pl.k_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      // i enumerates (k, n); locate the slab and the position inside it
+      const int k = i / cn, n = i % cn;
+      const int slab = k / SLAB_K, kin = k % SLAB_K;
+      const int64_t slab_base = pl.chunk_base[c] + (int64_t)slab * cn * SLAB_K;   // full slabs precede
+      const int64_t pos = slab_base + ((int64_t)(kin >> 3) * cn + n) * 8 + (kin & 7);
+      float v = 0.f;
+      const float* W = pl.W; const float* b = pl.b; int col = -1;
+      if (!pl.gauss) { if (n < cnt) col = off + n; }
+      else {
+        if (n < cnt) col = off + n;
+        else if (n < 2 * cnt) { col = off + n - cnt; W = pl.W2; b = pl.b2; }
+      }
+      if (col >= 0) {
+        if (k < pl.k_real) v = W[(int64_t)k * pl.ldw + col];
+        else if (k == pl.k_real) v = b[col];
+      }
+      out[pos] = __float2half_rn(v);
+    }
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcPack {
+  tc::Program prog;
+  tc::PackLayer pl[tc::MAX_LAYERS];
+  uint8_t* wpack = nullptr;
+  size_t wpack_bytes = 0;
+  float2* partial = nullptr;
+  size_t partial_cap = 0;
+  bool attr_set = false;
+};
+
+static int round16(int v) { return (v + 15) & ~15; }
+
+static void split_chunks(int n_pad, tc::Layer& L) {
+  // N (multiple of 16) into chunks of <= 112 columns
+  L.nchunks = 0;
+  int off = 0;
+  while (off < n_pad) {
+    const int cn = std::min(tc::CHUNK_N_MAX, n_pad - off);
+    L.chunk_n[L.nchunks] = cn; L.chunk_off[L.nchunks] = off; L.chunk_cnt[L.nchunks] = cn;
+    ++L.nchunks; off += cn;
+  }
+}
+
+static int build_program(const ModelP& m, TcPack& tp, const float* P) {
+  using namespace tc;
+  const iwae_config& c = m.cfg;
+  Program& pr = tp.prog;
+  memset(&pr, 0, sizeof(pr));
+  memset(tp.pl, 0, sizeof(tp.pl));
+  pr.two_layer = m.two_layer(); pr.cond = m.cond(); pr.learned_prior = m.learned_prior();
+  pr.d1 = c.d1; pr.d2 = c.d2; pr.nc = m.cond() ? c.n_cond : 0; pr.nx = c.n_x;
+  const int kz = round16(m.dec_in() + 1);
+  pr.kz_pad = kz;
+  IWAE_REQUIRE(kz <= KZ_MAX, "tensor-core path: d1 + n_cond + 1 must be <= %d", KZ_MAX);
+  IWAE_REQUIRE(c.h1 + 1 <= KP_MAX && c.d1 <= D_MAX && c.n_x <= NX_MAX, "tensor-core path: needs h1 <= %d, d1 <= %d, n_x <= %d",
+               KP_MAX - 1, D_MAX, NX_MAX);
+  int nl = 0;
+  auto tanh_layer = [&](const DenseP& D, int src, int dst, int k_pad) {
+    Layer& L = pr.L[nl]; PackLayer& K = tp.pl[nl]; ++nl;
+    L.kind = EPI_TANH; L.src = src; L.dst = dst; L.k_pad = k_pad; L.n_real = D.n_out;
+    L.next_kpad = round16(D.n_out + 1);
+    split_chunks(L.next_kpad, L);
+    for (int i = 0; i < L.nchunks; ++i) L.chunk_cnt[i] = std::max(0, std::min(L.chunk_n[i], D.n_out - L.chunk_off[i]));
+    K.W = P + D.w; K.b = P + D.b; K.k_real = D.n_in; K.k_pad = k_pad; K.ldw = D.n_out; K.gauss = 0;
+  };
+  auto gauss_layer = [&](const BlockP& B, int kind, int src, int dst, int k_pad, int next_kpad, int per_chunk) {
+    Layer& L = pr.L[nl]; PackLayer& K = tp.pl[nl]; ++nl;
+    const int d = B.lmu.n_out;
+    L.kind = kind; L.src = src; L.dst = dst; L.k_pad = k_pad; L.n_real = d; L.next_kpad = next_kpad;
+    L.nchunks = 0;
+    for (int off = 0; off < d; off += per_chunk) {
+      const int cnt = std::min(per_chunk, d - off);
+      L.chunk_cnt[L.nchunks] = cnt; L.chunk_off[L.nchunks] = off; L.chunk_n[L.nchunks] = round16(2 * cnt);
+      ++L.nchunks;
+    }
+    K.W = P + B.lmu.w; K.b = P + B.lmu.b; K.W2 = P + B.lstd.w; K.b2 = P + B.lstd.b;
+    K.k_real = B.lmu.n_in; K.k_pad = k_pad; K.ldw = d; K.gauss = 1;
+  };
+  if (m.two_layer()) {
+    IWAE_REQUIRE(c.h2 + 1 <= KP_MAX && 2 * c.d2 <= CHUNK_N_MAX && c.d2 + 1 <= KP_MAX,
+                 "tensor-core path: needs h2 <= %d and d2 <= %d", KP_MAX - 1, CHUNK_N_MAX / 2);
+    const int kh2 = round16(c.h2 + 1), kd2 = round16(c.d2 + 1);
+    tanh_layer(m.enc2.l1, 0, 1, kz);                                  // q(z2|z1) l1
+    tanh_layer(m.enc2.l2, 1, 1, kh2);                                 //          l2
+    gauss_layer(m.enc2, EPI_GSAMPLE, 1, 1, kh2, kd2, 56);             //          (mu2|std2) -> z2
+    IWAE_REQUIRE(pr.L[nl - 1].nchunks == 1, "tensor-core path: d2 too large");
+    tanh_layer(m.dec21.l1, 1, 1, kd2);                                // p(z1|z2) l1
+    tanh_layer(m.dec21.l2, 1, 1, kh2);                                //          l2
+    gauss_layer(m.dec21, EPI_GLOGP, 1, 1, kh2, 0, 56);                //          (mu|std) -> log p(z1|z2)
+  }
+  const int kh1 = round16(c.h1 + 1);
+  tanh_layer(m.dec.d0, 0, 1, kz);                                     // p(x|z1) dense0
+  tanh_layer(m.dec.d1, 1, 1, kh1);                                    //         dense1
+  {                                                                   //         dense2 + Bernoulli
+    Layer& L = pr.L[nl]; PackLayer& K = tp.pl[nl]; ++nl;
+    L.kind = EPI_BERN; L.src = 1; L.dst = 1; L.k_pad = kh1; L.n_real = c.n_x; L.next_kpad = 0;
+    split_chunks(round16(c.n_x), L);
+    for (int i = 0; i < L.nchunks; ++i) L.chunk_cnt[i] = std::max(0, std::min(L.chunk_n[i], c.n_x - L.chunk_off[i]));
+    IWAE_REQUIRE(L.nchunks <= MAX_CHUNKS, "tensor-core path: n_x too large");
+    K.W = P + m.dec.d2.w; K.b = P + m.dec.d2.b; K.k_real = c.h1; K.k_pad = kh1; K.ldw = c.n_x; K.gauss = 0;
+  }
+  pr.nlayers = nl;
+  // synchronisation flags: a layer waits for act_ready iff its input was produced by the previous
+  // layer's epilogue (or by the sampling stage for the first layer); layers reading z1 later do not.
+  for (int l = 0; l < nl; ++l) {
+    Layer& L = pr.L[l];
+    L.wait_act = (l == 0) || (L.src == 1);
+    L.inplace = (L.kind != EPI_BERN && L.kind != EPI_GLOGP && L.src == L.dst) ? 1 : 0;
+  }
+  for (int l = 0; l < nl; ++l) pr.L[l].signal_act = (l + 1 < nl) ? pr.L[l + 1].wait_act : 0;
+  // packed offsets
+  int64_t off = 0;
+  for (int l = 0; l < nl; ++l) {
+    Layer& L = pr.L[l]; PackLayer& K = tp.pl[l];
+    K.nchunks = L.nchunks;
+    for (int i = 0; i < L.nchunks; ++i) {
+      K.chunk_n[i] = L.chunk_n[i]; K.chunk_cnt[i] = L.chunk_cnt[i]; K.chunk_off[i] = L.chunk_off[i];
+      K.chunk_base[i] = off;
+      off += (int64_t)L.chunk_n[i] * L.k_pad;
+    }
+  }
+  tp.wpack_bytes = (size_t)off * 2;
+  return 0;
+}
+
+int tc_pack_weights(iwae_ctx* ctx, const float* params, cudaStream_t st) {
+  if (!ctx->tc) ctx->tc = new TcPack();
+  TcPack& tp = *ctx->tc;
+  IWAE_TRY(build_program(ctx->model, tp, params));
+  if (!tp.wpack) CUDA_TRY(cudaMalloc((void**)&tp.wpack, tp.wpack_bytes));
+  for (int l = 0; l < tp.prog.nlayers; ++l) {
+    tc::pack_layer_kernel<<<64, 256, 0, st>>>(tp.pl[l], reinterpret_cast<__half*>(tp.wpack));
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaMemcpyToSymbolAsync(tc::c_prog, &tp.prog, sizeof(tc::Program), 0, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+void tc_release(iwae_ctx* ctx) {
+  if (!ctx->tc) return;
+  if (ctx->tc->wpack) cudaFree(ctx->tc->wpack);
+  if (ctx->tc->partial) cudaFree(ctx->tc->partial);
+  delete ctx->tc;
+  ctx->tc = nullptr;
+}
+
+int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
+                  float* mu, float* sd, cudaStream_t st);
+
+int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k, uint64_t seed,
+                int64_t img_offset, float* out_per_example, cudaStream_t st) {
+  const ModelP& m = ctx->model;
+  const iwae_config& c = m.cfg;
+  IWAE_REQUIRE(!m.cond() || y, "tensor-core path: CIWAE needs labels");
+  IWAE_TRY(tc_pack_weights(ctx, params, st));
+  TcPack& tp = *ctx->tc;
+  Arena& ar = ctx->arena;
+
+  // encoder pre-pass q(z1|x) (per image, k-independent): fp32 FFMA, ~1% of the FLOPs
+  float *h1, *h2, *mu1, *std1, *pmu = nullptr, *pstd = nullptr;
+  const float* xin = x; int64_t ldx = c.n_x;
+  const int nc = m.cond() ? c.n_cond : 0;
+  if (nc) {
+    float* t; IWAE_TRY(ar.get(&t, (size_t)N * (c.n_x + nc)));
+    IWAE_TRY(concat_onehot(x, c.n_x, c.n_x, y, (int)N, (int)N, nc, t, st));
+    xin = t; ldx = c.n_x + nc;
+  }
+  IWAE_TRY(ar.get(&h1, (size_t)N * c.h1)); IWAE_TRY(ar.get(&h2, (size_t)N * c.h1));
+  IWAE_TRY(ar.get(&mu1, (size_t)N * c.d1)); IWAE_TRY(ar.get(&std1, (size_t)N * c.d1));
+  IWAE_TRY(block_fwd_f32(params, m.enc1, xin, ldx, N, h1, h2, mu1, std1, st));
+  if (m.learned_prior()) {
+    float* yoh;
+    IWAE_TRY(ar.get(&yoh, (size_t)N * nc));
+    IWAE_TRY(onehot_f32(y, (int)N, nc, yoh, st));
+    IWAE_TRY(ar.get(&pmu, (size_t)N * c.d1)); IWAE_TRY(ar.get(&pstd, (size_t)N * c.d1));
+    IWAE_TRY(block_fwd_f32(params, m.prior, yoh, nc, N, h1, h2, pmu, pstd, st));
+  }
+
+  tc::EvalArgs a;
+  a.wpack = tp.wpack; a.x = x; a.y = y; a.mu1 = mu1; a.std1 = std1; a.pmu = pmu; a.pstd = pstd;
+  a.tiles_per_img = (k + tc::TILE_M - 1) / tc::TILE_M;
+  a.rows_per_tile = (k + a.tiles_per_img - 1) / a.tiles_per_img;
+  a.n_tiles = N * a.tiles_per_img;
+  a.k = k; a.seed = seed; a.img_offset = img_offset;
+  const size_t need = (size_t)a.n_tiles * sizeof(float2);
+  if (tp.partial_cap < need) {
+    if (tp.partial) CUDA_TRY(cudaFree(tp.partial));
+    tp.partial = nullptr; tp.partial_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&tp.partial, need));
+    tp.partial_cap = need;
+  }
+  a.partial = tp.partial;
+
+  const size_t smem = sizeof(tc::SmemLayout) + 128;
+  auto kern = tc::iwae_eval_tc_kernel<false>;
+  if (!tp.attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tp.attr_set = true;
+  }
+  int grid = (int)std::min<int64_t>(a.n_tiles, (int64_t)2 * ctx->sm_count);
+  kern<<<grid, tc::NUM_THREADS, smem, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  tc::combine_partials_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(tp.partial, N, a.tiles_per_img, k, out_per_example);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int umma_selftest(const float* A, const float* B, int N, int K, float* D, cudaStream_t st) {
+  IWAE_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "umma_selftest: N must be a multiple of 16 in [16,256]");
+  IWAE_REQUIRE(K >= 1 && K <= 256, "umma_selftest: K must be in [1,256]");
+  int variant = 0;
+  if (K < 0) variant = 1;
+  const int Kp = (K + 15) & ~15;
+  const size_t smem = (size_t)Kp * (128 + N) * 2;
+  CUDA_TRY(cudaFuncSetAttribute(tc::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::umma_selftest_kernel<<<1, 128, smem, st>>>(A, B, N, K, D, variant);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

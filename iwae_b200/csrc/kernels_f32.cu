@@ -1,0 +1,733 @@
+// fp32 (FFMA) kernels: the parity-mode forward, the backward pass, Adam, SIR and the data step.
+// Row index convention everywhere: r = s*B + b (sample-major, the reference's [k,B,.] layout).
+#include "common.cuh"
+#include "rng.cuh"
+#include <math.h>
+
+// =============================================================================================
+// Tiled SGEMM with fused epilogues.  C(m,n) = epi( sum_k A(m,k) B(k,n) ).
+// Generic strides cover x@W (NN), dY@W^T (NT) and X^T@dY (TN); the tile loaders pick the thread
+// mapping that walks the unit-stride dimension so global loads stay coalesced in all three.
+// =============================================================================================
+template <int BM, int BN, int TM, int TN>
+struct GemmCfg {
+  static constexpr int BK = 16;
+  static constexpr int THREADS = (BM / TM) * (BN / TN);
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_f32_kernel(GemmArgs a) {
+  constexpr int BK = 16;
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int TX = BN / TN;   // threads along n
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;   // M tiles on x (no 65535 limit)
+  const bool a_kcontig = (a.sa_k == 1);
+  const bool b_ncontig = (a.sb_n == 1);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < a.K; k0 += BK) {
+    // ---- A tile
+    for (int e = tid; e < BM * BK; e += NT) {
+      int mm, kk;
+      if (a_kcontig) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < a.M && gk < a.K) v = __ldg(a.A + (int64_t)gm * a.sa_m + (int64_t)gk * a.sa_k);
+      As[kk][mm] = v;
+    }
+    // ---- B tile
+    for (int e = tid; e < BN * BK; e += NT) {
+      int nn, kk;
+      if (b_ncontig) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < a.N && gk < a.K) v = __ldg(a.B + (int64_t)gk * a.sb_k + (int64_t)gn * a.sb_n);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    float bern = 0.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gm < a.M && gn < a.N) {
+        float v = acc[i][j];
+        if (a.bias) v += __ldg(a.bias + gn);
+        if (a.act == ACT_TANH) v = tanhf(v);
+        else if (a.act == ACT_EXP_EPS) v = expf(v) + 1e-6f;
+        if (a.accumulate) v += a.C[(int64_t)gm * a.ldc + gn];
+        if (a.mul_h) {
+          const float h = __ldg(a.mul_h + (int64_t)gm * a.ld_h + gn);
+          v *= (1.f - h * h);
+        }
+        if (a.C) a.C[(int64_t)gm * a.ldc + gn] = v;
+        if (a.bern_x) {
+          // tfd.Bernoulli(logits).log_prob(x) = -(1-x) softplus(l) - x softplus(-l)   (A.3)
+          const float xv = __ldg(a.bern_x + (int64_t)(gm % a.bern_B) * a.N + gn);
+          const float sp = fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));
+          bern += -(1.f - xv) * sp - xv * (sp - v);
+        }
+      }
+    }
+    if (a.bern_x) {
+      // reduce over the TX threads that share this row (TX is a power of two <= 32, lane-aligned)
+#pragma unroll
+      for (int o = TX / 2; o > 0; o >>= 1) bern += __shfl_xor_sync(0xffffffffu, bern, o);
+      if (tx == 0 && gm < a.M) a.bern_partial[(int64_t)gm * gridDim.y + blockIdx.y] = bern;
+    }
+  }
+}
+
+int gemm_f32_ntiles_n(int N, int small_tile) { return small_tile ? (N + 31) / 32 : (N + 63) / 64; }
+
+int gemm_f32(const GemmArgs& a, cudaStream_t st) {
+  if (a.M <= 0 || a.N <= 0) return 0;
+  if (a.small_tile) {
+    dim3 grid((a.M + 31) / 32, (a.N + 31) / 32);
+    gemm_f32_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid((a.M + 63) / 64, (a.N + 63) / 64);
+    gemm_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// Small elementwise / reduction kernels
+// =============================================================================================
+__global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, int N, float* __restrict__ out) {
+  // one warp-wide strip of 32 columns per block.x; blockDim = (32, 8): 8 row-lanes then smem reduce
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (n < N)
+    for (int m = threadIdx.y; m < M; m += 8) s += A[(int64_t)m * lda + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[n] = t;
+  }
+}
+int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st) {
+  colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(A, lda, M, N, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+__device__ __forceinline__ int label_of(const float* y, int b) {
+  // tf.cast(y, tf.uint8) then one_hot(depth) (task04.py:112): out-of-range labels give a zero row
+  return (int)(unsigned char)(int)y[b];
+}
+
+__global__ void concat_onehot_kernel(const float* __restrict__ x, int64_t ldx, int n, const float* __restrict__ y,
+                                     int B, int rows, int nc, float* __restrict__ out) {
+  const int64_t total = (int64_t)rows * (n + nc);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (n + nc);
+    const int c = (int)(i % (n + nc));
+    float v;
+    if (c < n) v = x[r * ldx + c];
+    else v = (label_of(y, (int)(r % B)) == c - n) ? 1.f : 0.f;
+    out[i] = v;
+  }
+}
+int concat_onehot(const float* x, int64_t ldx, int n, const float* y, int B, int rows, int nc, float* out,
+                  cudaStream_t st) {
+  const int64_t total = (int64_t)rows * (n + nc);
+  const int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
+  concat_onehot_kernel<<<blocks, 256, 0, st>>>(x, ldx, n, y, B, rows, nc, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int onehot_f32(const float* y, int B, int nc, float* out, cudaStream_t st) {
+  return concat_onehot(nullptr, 0, 0, y, B, B, nc, out, st);
+}
+
+// ---- reparameterised sampling: z = eps*std + mu (tfd.Normal.sample, A.2) ----
+__global__ void sample_latent_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int bcast,
+                                     const float* __restrict__ eps_in, float* __restrict__ eps_out,
+                                     float* __restrict__ z, int B, int k, int d, uint64_t seed, int stream_id,
+                                     int64_t img_offset) {
+  const int nq = (d + 3) / 4;
+  const int64_t total = (int64_t)k * B * nq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % nq);
+    const int64_t r = i / nq;
+    const int b = (int)(r % B);
+    const int s = (int)(r / B);
+    float e[4];
+    if (eps_in) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) e[j] = (4 * q + j < d) ? eps_in[r * d + 4 * q + j] : 0.f;
+    } else {
+      const float4 n4 = philox_normal4(seed, (uint32_t)stream_id, (uint32_t)(img_offset + b), (uint32_t)s, (uint32_t)q);
+      e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+    }
+    const int64_t prow = bcast ? b : r;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * q + j;
+      if (c < d) {
+        const float m = mu ? mu[prow * d + c] : 0.f;
+        const float sdev = sd ? sd[prow * d + c] : 1.f;
+        if (z) z[r * d + c] = e[j] * sdev + m;
+        if (eps_out) eps_out[r * d + c] = e[j];
+      }
+    }
+  }
+}
+int sample_latent(const float* mu, const float* sd, int bcast, const float* eps_in, float* eps_out, float* z,
+                  int B, int k, int d, uint64_t seed, int stream_id, int64_t img_offset, cudaStream_t st) {
+  const int64_t total = (int64_t)k * B * ((d + 3) / 4);
+  if (total == 0) return 0;
+  const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  sample_latent_kernel<<<blocks, 256, 0, st>>>(mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int philox_fill(uint64_t seed, int stream_id, int64_t img_offset, int B, int k, int d, float* out, cudaStream_t st) {
+  return sample_latent(nullptr, nullptr, 1, nullptr, out, nullptr, B, k, d, seed, stream_id, img_offset, st);
+}
+
+// ---- Gaussian log-density row sums: one warp per row ----
+#define LOG2PI_HALF 0.91893853320467274178f
+__global__ void normal_logp_rows_kernel(const float* __restrict__ z, const float* __restrict__ mu,
+                                        const float* __restrict__ sd, int bcast, float std_extra, int B, int64_t R, int d,
+                                        float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const int64_t prow = bcast ? (r % B) : r;
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      const float zz = z[r * d + j];
+      if (mu) {
+        const float sc = sd[prow * d + j] + std_extra;
+        const float t = zz / sc - mu[prow * d + j] / sc;            // TFP: both terms divided first
+        s += -0.5f * t * t - (LOG2PI_HALF + logf(sc));
+      } else {
+        s += -0.5f * zz * zz - LOG2PI_HALF;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[r] = s;
+  }
+}
+int normal_logp_rows(const float* z, const float* mu, const float* sd, int bcast, float std_extra, int B, int k,
+                     int d, float* out, cudaStream_t st) {
+  const int64_t R = (int64_t)B * k;
+  if (R == 0) return 0;
+  int64_t blocks = (R + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  normal_logp_rows_kernel<<<(int)blocks, 256, 0, st>>>(z, mu, sd, bcast, std_extra, B, R, d, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+__global__ void kl_rows_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int B, int d,
+                               float* __restrict__ out) {
+  // tfd.kl_divergence(N(mu,sd), N(0,1)) = 0.5 mu^2 + 0.5 expm1(2 log sd) - log sd   (A.2)
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float m = mu[b * d + j], ls = logf(sd[b * d + j]);
+    s += 0.5f * m * m + 0.5f * expm1f(2.f * ls) - ls;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[b] = s;
+}
+int kl_rows(const float* mu, const float* sd, int B, int d, float* out, cudaStream_t st) {
+  kl_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(mu, sd, B, d, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+__global__ void bern_reduce_partials_kernel(const float* __restrict__ p, int64_t R, int nt, float* __restrict__ out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < nt; ++t) s += p[r * nt + t];
+    out[r] = s;
+  }
+}
+int bern_reduce_partials(const float* partial, int R, int nt, float* lpxz, cudaStream_t st) {
+  if (R == 0) return 0;
+  int blocks = (R + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+  bern_reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, R, nt, lpxz);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+__global__ void bern_logp_rows_kernel(const float* __restrict__ logits, const float* __restrict__ x, int64_t R,
+                                      int B, int n, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const float* l = logits + r * n;
+    const float* xr = x + (r % B) * (int64_t)n;
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float v = l[j], xv = xr[j];
+      const float sp = fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));
+      s += -(1.f - xv) * sp - xv * (sp - v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[r] = s;
+  }
+}
+int bern_logp_rows(const float* logits, const float* x, int R, int B, int n, float* lpxz, cudaStream_t st) {
+  if (R == 0) return 0;
+  int64_t blocks = ((int64_t)R + 7) / 8; if (blocks > 148 * 32) blocks = 148 * 32;
+  bern_logp_rows_kernel<<<(int)blocks, 256, 0, st>>>(logits, x, R, B, n, lpxz);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- log-weights, log-mean-exp over k, softmax, SNIS: one CTA per image ----
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
+  __shared__ float red[8];
+  const int b = blockIdx.x, B = a.B, k = a.k;
+  // pass 1: log_w and its max
+  float mx = -INFINITY, sm = 0.f;
+  for (int s = threadIdx.x; s < k; s += blockDim.x) {
+    const int64_t r = (int64_t)s * B + b;
+    float lw;
+    if (a.two_layer) lw = a.lpxz[r] + a.lp12[r] + a.lpz[r] - a.lq1[r] - a.lq2[r];     // iwae2.py:126
+    else lw = a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);                              // iwae1.py:113
+    if (a.log_w) a.log_w[r] = lw;
+    mx = fmaxf(mx, lw);
+    sm += lw;
+  }
+  mx = block_reduce(mx, red, true);
+  sm = block_reduce(sm, red, false);
+  // pass 2: sum exp(lw - max)
+  float se = 0.f;
+  for (int s = threadIdx.x; s < k; s += blockDim.x) {
+    const int64_t r = (int64_t)s * B + b;
+    float lw = a.two_layer ? a.lpxz[r] + a.lp12[r] + a.lpz[r] - a.lq1[r] - a.lq2[r]
+                           : a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);
+    se += expf(lw - mx);
+  }
+  se = block_reduce(se, red, false);
+  if (threadIdx.x == 0) {
+    if (a.iwae) a.iwae[b] = logf(se / (float)k) + mx;       // utils.logmeanexp (utils.py:6-8)
+    if (a.vae) a.vae[b] = sm / (float)k;
+  }
+  const bool need_al = a.al || a.eq14 || a.dreg || a.snis1 || a.snis2;
+  if (!need_al) return;
+  // pass 3: normalised weights, eq14, DReG
+  float e14 = 0.f, dr = 0.f;
+  for (int s = threadIdx.x; s < k; s += blockDim.x) {
+    const int64_t r = (int64_t)s * B + b;
+    float lw = a.two_layer ? a.lpxz[r] + a.lp12[r] + a.lpz[r] - a.lq1[r] - a.lq2[r]
+                           : a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);
+    const float w = expf(lw - mx) / se;
+    if (a.al) a.al[r] = w;
+    e14 += w * lw;
+    if (a.dreg) dr += w * w * (a.lpz[r] + a.lpxz[r] - a.lq_stopped[r]);                // task02.py:70-73
+  }
+  if (a.eq14) { e14 = block_reduce(e14, red, false); if (threadIdx.x == 0) a.eq14[b] = e14; }
+  if (a.dreg) { dr = block_reduce(dr, red, false); if (threadIdx.x == 0) a.dreg[b] = dr; }
+  // pass 4: snis_z = sum_k al * z  (thread per latent dim, coalesced over the dim)
+  for (int which = 0; which < 2; ++which) {
+    float* out = which ? a.snis2 : a.snis1;
+    const float* z = which ? a.z2 : a.z1;
+    const int d = which ? a.d2 : a.d1;
+    if (!out) continue;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+      float acc = 0.f;
+      for (int s = 0; s < k; ++s) {
+        const int64_t r = (int64_t)s * B + b;
+        float lw = a.two_layer ? a.lpxz[r] + a.lp12[r] + a.lpz[r] - a.lq1[r] - a.lq2[r]
+                               : a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);
+        acc += (expf(lw - mx) / se) * z[r * d + j];
+      }
+      out[(int64_t)b * d + j] = acc;
+    }
+  }
+}
+int logw_reduce(const LogwArgs& a, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  logw_reduce_kernel<<<a.B, 256, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+__global__ void sum_to_double_kernel(const float* __restrict__ v, int64_t n, double* acc, int accumulate) {
+  // single CTA, fixed summation order -> deterministic
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)v[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *acc = (accumulate ? *acc : 0.0) + red[0];
+}
+int sum_to_double(const float* v, int64_t n, double* acc, int accumulate, cudaStream_t st) {
+  sum_to_double_kernel<<<1, 256, 0, st>>>(v, n, acc, accumulate);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// Backward
+// =============================================================================================
+// g[r] = d(-objective)/d(log_w[r])  (A.4): iwae_elbo / iwae_eq14 / DReG-decoder -> -al/B ; vae -> -1/(kB)
+__global__ void row_coef_kernel(const float* __restrict__ al, int64_t R, int k, int objective, int B_norm,
+                                float* __restrict__ g) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (objective == IWAE_OBJ_VAE_ELBO || objective == IWAE_OBJ_VAE_ELBO_KL) v = -1.f / ((float)k * (float)B_norm);
+    else v = -al[r] / (float)B_norm;
+    g[r] = v;
+  }
+}
+int row_coef(const float* al, int B, int k, int objective, int B_norm, float* g, cudaStream_t st) {
+  const int64_t R = (int64_t)B * k;
+  if (R == 0) return 0;
+  int blocks = (int)((R + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  row_coef_kernel<<<blocks, 256, 0, st>>>(al, R, k, objective, B_norm, g);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// dl[r,j] = g[r] * (x[b,j] - sigmoid(l[r,j]))
+__global__ void dlogits_kernel(const float* __restrict__ logits, const float* __restrict__ x,
+                               const float* __restrict__ g, int64_t R, int B, int n, float* __restrict__ dl) {
+  const int64_t total = R * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n;
+    const int j = (int)(i % n);
+    const float l = logits[i];
+    const float sg = 1.f / (1.f + expf(-l));
+    dl[i] = g[r] * (x[(r % B) * (int64_t)n + j] - sg);
+  }
+}
+int dlogits_f32(const float* logits, const float* x, const float* g, int R, int B, int n, float* dl, cudaStream_t st) {
+  const int64_t total = (int64_t)R * n;
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  dlogits_kernel<<<blocks, 256, 0, st>>>(logits, x, g, R, B, n, dl);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// First stochastic layer.  One thread per (b, j), looping over the k samples (fixed order).
+// Uses the total-derivative identities of A.4: d lq/d mu = 0, d lq/d std = -1/std.
+__global__ void latent1_bwd_kernel(Latent1BwdArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.B * a.d) return;
+  const int b = idx / a.d, j = idx % a.d;
+  const float mu = a.mu[idx], sd = a.std[idx];
+  const bool dreg = (a.objective == IWAE_OBJ_DREG);
+  const bool klobj = (a.objective == IWAE_OBJ_VAE_ELBO_KL);
+  float acc_mu = 0.f, acc_sd = 0.f, acc_pmu = 0.f, acc_psd = 0.f;
+  for (int s = 0; s < a.k; ++s) {
+    const int64_t r = (int64_t)s * a.B + b;
+    const float g = a.g[r];
+    const float z = a.z[r * a.d + j], e = a.eps[r * a.d + j];
+    float dz = a.dz_dec[r * a.ld_dz + j];
+    if (a.dz_q2) dz += a.dz_q2[r * a.d + j];
+    if (dreg) {
+      // task02.py:60-76: encoder signal = al * (decoder-path dz) - (al^2/B) * d(lpz - lq_stopped)/dz
+      const float al = a.al[r];
+      const float sd2 = sd + 1e-6f;
+      dz = al * dz - (al * al / (float)a.B_norm) * (-z + (z - mu) / (sd2 * sd2));
+      acc_mu += dz;
+      acc_sd += dz * e;
+      continue;
+    }
+    if (!klobj) {
+      if (a.prior_rows == 0) {
+        dz += g * a.beta * (-z);
+      } else {
+        const int64_t pr = (a.prior_rows == 1) ? (int64_t)b * a.d + j : r * a.d + j;
+        const float pm = a.pmu[pr], ps = a.pstd[pr];
+        const float bt = (a.prior_rows == 1) ? a.beta : 1.f;    // iwae2 ignores beta (iwae2.py:128)
+        const float t = (z - pm) / (ps * ps);
+        dz += g * bt * (-t);
+        const float dpm = g * bt * t;
+        const float dps = g * bt * ((z - pm) * t / ps - 1.f / ps);
+        if (a.prior_rows == 1) { acc_pmu += dpm; acc_psd += dps; }
+        else if (a.dpmu) { a.dpmu[pr] = dpm; a.dpa[pr] = dps * (ps - 1e-6f); }
+      }
+      const float bt = (a.prior_rows == 2) ? 1.f : a.beta;
+      acc_sd += g * bt / sd;                                     // -beta * d lq/d std (total) = +beta/std
+    }
+    acc_mu += dz;
+    acc_sd += dz * e;
+  }
+  if (klobj) {
+    // loss = -mean lpxz + beta * mean_b kl ; d kl/d mu = mu, d kl/d std = std - 1/std
+    acc_mu += a.beta / (float)a.B_norm * mu;
+    acc_sd += a.beta / (float)a.B_norm * (sd - 1.f / sd);
+  }
+  a.dmu[idx] = acc_mu;
+  a.da[idx] = acc_sd * (sd - 1e-6f);      // std = exp(a) + 1e-6
+  if (a.prior_rows == 1 && a.dpmu) {
+    a.dpmu[idx] = acc_pmu;
+    a.dpa[idx] = acc_psd * (a.pstd[idx] - 1e-6f);
+  }
+}
+int latent1_bwd(const Latent1BwdArgs& a, cudaStream_t st) {
+  const int n = a.B * a.d;
+  if (n == 0) return 0;
+  latent1_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Gradients reaching the parameters (pmu, pstd pre-activation) of a per-row Gaussian log p(z; pmu, pstd)
+// weighted by g[r] (IWAE2's lpz1z2, iwae2.py:120).
+__global__ void gauss_rows_bwd_kernel(const float* __restrict__ g, const float* __restrict__ z,
+                                      const float* __restrict__ pmu, const float* __restrict__ pstd, int64_t R, int d,
+                                      float* __restrict__ dpmu, float* __restrict__ dpa) {
+  const int64_t total = R * d;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gg = g[i / d];
+    const float pm = pmu[i], ps = pstd[i];
+    const float t = (z[i] - pm) / (ps * ps);
+    dpmu[i] = gg * t;
+    dpa[i] = gg * ((z[i] - pm) * t / ps - 1.f / ps) * (ps - 1e-6f);
+  }
+}
+int gauss_rows_bwd(const float* g, const float* z, const float* pmu, const float* pstd, int64_t R, int d,
+                   float* dpmu, float* dpa, cudaStream_t st) {
+  const int64_t total = R * d;
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  gauss_rows_bwd_kernel<<<blocks, 256, 0, st>>>(g, z, pmu, pstd, R, d, dpmu, dpa);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Second stochastic layer of IWAE2 (all per row): z2 = mu2 + std2*eps2, lpz2 = N(0,1), -lq2 total.
+__global__ void latent2_bwd_kernel(Latent2BwdArgs a) {
+  const int64_t total = (int64_t)a.R * a.d;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / a.d;
+    const float g = a.g[r];
+    const float sd = a.std[i];
+    const float dz = a.dz_p[i] + g * (-a.z[i]);
+    a.dmu[i] = dz;
+    a.da[i] = (dz * a.eps[i] + g / sd) * (sd - 1e-6f);
+  }
+}
+int latent2_bwd(const Latent2BwdArgs& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.R * a.d;
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  latent2_bwd_kernel<<<blocks, 256, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- Keras Adam (A.6), 128-bit vectorised with a scalar tail ----
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, int vec, float lr_t, float b1, float b2, float eps) {
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (int64_t i = tid; i < n4; i += stride) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+#define ADAM1(c)                                             \
+    mm.c = b1 * mm.c + (1.f - b1) * gg.c;                    \
+    vv.c = b2 * vv.c + (1.f - b2) * gg.c * gg.c;             \
+    pp.c = pp.c - lr_t * mm.c / (sqrtf(vv.c) + eps);
+    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
+    const float gg = g[i];
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    m[i] = mm; v[i] = vv;
+    p[i] = p[i] - lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+             int64_t t, cudaStream_t st) {
+  if (n == 0) return 0;
+  // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), computed in double on the host like Keras does in fp32 ops
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
+  const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  int blocks = (int)((n / 4 + 255) / 256); if (blocks > 148 * 4) blocks = 148 * 4; if (blocks < 1) blocks = 1;
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, aligned ? 1 : 0, (float)lr_t, b1, b2, eps);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- utils.bernoullisample on the device ----
+__global__ void bernoulli_sample_kernel(const float* __restrict__ p, int64_t n, uint64_t seed, uint64_t epoch,
+                                        float* __restrict__ out) {
+  const int64_t nq = (n + 3) / 4;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)epoch, 0x42u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = 4 * q + j;
+      if (i < n) {
+        const float u = (float)(rr[j] >> 8) * 5.9604644775390625e-8f;
+        out[i] = (u < p[i]) ? 1.f : 0.f;
+      }
+    }
+  }
+}
+int bernoulli_sample_f32(const float* p, int64_t n, uint64_t seed, uint64_t epoch, float* out, cudaStream_t st) {
+  if (n == 0) return 0;
+  int64_t blocks = ((n + 3) / 4 + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+  bernoulli_sample_kernel<<<(int)blocks, 256, 0, st>>>(p, n, seed, epoch, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- scipy.special.softmax on an fp32 vector: exp(x - logsumexp(x)) ----
+__global__ void __launch_bounds__(256) softmax_vec_kernel(const float* __restrict__ x, int L, float* __restrict__ out) {
+  __shared__ float red[8];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, x[i]);
+  mx = block_reduce(mx, red, true);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) se += expf(x[i] - mx);
+  se = block_reduce(se, red, false);
+  const float lse = logf(se) + mx;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) out[i] = expf(x[i] - lse);
+}
+int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st) {
+  softmax_vec_kernel<<<1, 256, 0, st>>>(x, L, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// SIR: numpy legacy RandomState.choice(L, size, replace=False, p) (A.7), bit-exact.
+// The cdf is a SEQUENTIAL fp64 inclusive scan (np.cumsum order) done by one thread; searchsorted and
+// the first-occurrence de-duplication run on the whole CTA.  L = 10,000: ~50 us per round.
+// =============================================================================================
+__global__ void __launch_bounds__(256) sir_kernel(const float* __restrict__ al, int L, const double* __restrict__ u,
+                                                  int n_u, int size, int64_t* __restrict__ out_idx,
+                                                  int32_t* __restrict__ out_consumed, double* __restrict__ p,
+                                                  double* __restrict__ cdf, int32_t* __restrict__ cand) {
+  __shared__ int s_nuniq, s_pos, s_fail;
+  __shared__ int s_keep[1024];
+  for (int i = threadIdx.x; i < L; i += blockDim.x) p[i] = (double)al[i];
+  if (threadIdx.x == 0) { s_nuniq = 0; s_pos = 0; s_fail = 0; }
+  __syncthreads();
+  while (true) {
+    const int n_uniq = s_nuniq, pos = s_pos;
+    if (n_uniq >= size || s_fail) break;
+    const int n = size - n_uniq;
+    if (pos + n > n_u) { if (threadIdx.x == 0) s_fail = 1; __syncthreads(); break; }
+    for (int i = threadIdx.x; i < n_uniq; i += blockDim.x) p[out_idx[i]] = 0.0;       // p[found] = 0
+    __syncthreads();
+    if (threadIdx.x == 0) {                                                           // cdf = cumsum(p)
+      double c = 0.0;
+      for (int i = 0; i < L; ++i) { c += p[i]; cdf[i] = c; }
+    }
+    __syncthreads();
+    const double tot = cdf[L - 1];
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += blockDim.x) cdf[i] = cdf[i] / tot;          // cdf /= cdf[-1]
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {                               // searchsorted(side='right')
+      const double x = u[pos + i];
+      int lo = 0, hi = L;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= x) lo = mid + 1; else hi = mid; }
+      cand[i] = lo;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {                               // first occurrences, draw order
+      int keep = 1;
+      const int c = cand[i];
+      for (int j = 0; j < i; ++j) if (cand[j] == c) { keep = 0; break; }
+      s_keep[i] = keep;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int w = n_uniq;
+      for (int i = 0; i < n; ++i) if (s_keep[i]) out_idx[w++] = (int64_t)cand[i];
+      s_nuniq = w;
+      s_pos = pos + n;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_consumed = s_fail ? -1 : s_pos;
+}
+
+int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64_t* out_idx, int32_t* out_consumed,
+               cudaStream_t st) {
+  IWAE_REQUIRE(size <= 1024 && size <= L, "iwae_sir: size must be <= min(L, 1024)");
+  // scratch: p[L], cdf[L] doubles + cand[size] ints, allocated stream-ordered
+  double* scratch = nullptr;
+  const size_t bytes = sizeof(double) * 2 * (size_t)L + sizeof(int32_t) * 1024;
+  CUDA_TRY(cudaMallocAsync((void**)&scratch, bytes, st));
+  sir_kernel<<<1, 256, 0, st>>>(al, L, u, n_u, size, out_idx, out_consumed, scratch, scratch + L,
+                               reinterpret_cast<int32_t*>(scratch + 2 * (size_t)L));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(scratch, st));
+  return 0;
+}
