@@ -1,7 +1,7 @@
 /* iwae_b200.h - C-ABI of libiwae_b200.so: the B200-native importance-weighted ELBO hot path.
  *
  * The reference (nbip/IWAE) has no FFI: its boundary is the Python class API that main.py and
- * tasks/*.py call.  This header is what the Python shim (iwae_b200/model.py, reached
+ * the tasks/ scripts call.  This header is what the Python shim (iwae_b200/model.py, reached
  * from src/iwae1.py, src/iwae2.py) binds through ctypes; every entry point names the reference
  * interface it replaces.
  *
@@ -40,9 +40,12 @@ enum {
 };
 
 /* Arithmetic of the k-sample evaluation (iwae_llh_eval).
- * FP32 : FFMA kernels, fp32 everywhere (parity mode, <=1e-4 rel on every per-row term).
- * TC   : fused tcgen05 kernel, fp16 operands / fp32 TMEM accumulation (throughput mode). */
-enum { IWAE_PREC_FP32 = 0, IWAE_PREC_TC_F16 = 1 };
+ * FP32        : FFMA kernels, fp32 everywhere (parity mode, <=1e-4 rel on every per-row term).
+ * TC_F16      : fused tcgen05 kernel, fp16 operands / fp32 TMEM accumulation, libm-accurate
+ *               tanh/exp/log in the epilogues.
+ * TC_F16_FAST : same kernel with MUFU approximations (tanh.approx, ex2.approx, lg2.approx); the
+ *               throughput mode the bench reports. */
+enum { IWAE_PREC_FP32 = 0, IWAE_PREC_TC_F16 = 1, IWAE_PREC_TC_F16_FAST = 2 };
 
 typedef struct {
   int32_t kind;      /* IWAE_KIND_* */
@@ -75,6 +78,10 @@ typedef struct {
   float* logits;    /* [k,B,n_x]  (materialised only when asked for)                 */
   float* q_mu;      /* [B,d1]  qzx.loc                                               */
   float* q_std;     /* [B,d1]  qzx.scale (= exp(a)+1e-6)                             */
+  float* scalars;   /* [8] batch-mean scalars of the result dict (src/iwae1.py:119-134):
+                       [0] vae_elbo  [1] vae_elbo_kl (IWAE1/CIWAE)  [2] iwae_elbo  [3] iwae_eq14
+                       [4] inference_loss = -mean_b dreg (tasks/task02.py:76, when dreg is computed)
+                       [5] mean lpxz  [6] mean lpz  [7] mean lq1 (the TensorBoard scalars)      */
 } iwae_outputs;
 
 const char* iwae_last_error(void);
@@ -106,6 +113,11 @@ int iwae_forward(iwae_ctx* ctx, const float* params, const float* x, const float
 int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y,
                   int64_t N, int32_t k, uint64_t seed, int64_t img_offset, int32_t precision,
                   float* out_per_example, double* out_sum, void* stream);
+
+/* Device time (ms) of the fused tensor-core evaluation kernel in the most recent iwae_llh_eval /
+ * iwae_llh_eval_host call with a TC precision on this context (CUDA events recorded around that one
+ * launch on the caller's stream); synchronises on the second event.  bench.py's roofline uses it. */
+int iwae_llh_kernel_ms(iwae_ctx* ctx, float* ms);
 
 /* Same, reference-facing with HOST buffers: copies x (and y) host->device, runs, copies the
  * per-example vector and the sum back and synchronises.  This is the call the e2e number times. */
@@ -164,8 +176,14 @@ int iwae_bernoulli_sample(const float* p, int64_t n, uint64_t seed, uint64_t epo
 
 /* Tensor-core unit test hook: D[128,N] = A[128,K] * B[N,K]^T with fp16 operands staged exactly like
  * the fused evaluation kernel stages them (no-swizzle K-major core matrices, one tcgen05.mma chain).
- * A, B fp32 on the device (rounded to fp16 inside); used by tests/test_umma_unit.py. */
-int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, float* D, void* stream);
+ * A, B fp32 on the device (rounded to fp16 inside).  variant 0 = the descriptor convention the fused
+ * kernel uses (LBO = K-direction core-matrix stride, SBO = M/N-direction); 1 = the two swapped
+ * (diagnostic only).  Used by tests/test_umma_unit.py. */
+int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, int32_t variant, float* D,
+                       void* stream);
+
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t iwae_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,8 @@ void iwae_set_error(const char* fmt, ...) {
 }
 extern "C" const char* iwae_last_error(void) { return g_err; }
 extern "C" int iwae_version(void) { return 100; }
+long long g_iwae_launches = 0;
+extern "C" int64_t iwae_launch_count(void) { return (int64_t)g_iwae_launches; }
 
 // ---------------------------------------------------------------------------------------------
 // arena
@@ -119,6 +121,8 @@ extern "C" int iwae_destroy(iwae_ctx* ctx) {
   if (ctx->per_buf) cudaFree(ctx->per_buf);
   if (ctx->stage_x) cudaFree(ctx->stage_x);
   if (ctx->stage_aux) cudaFree(ctx->stage_aux);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   delete ctx;
   return 0;
 }
@@ -192,7 +196,7 @@ static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ld
   return gemm_f32(g, st);
 }
 
-static int block_fwd(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
+int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
                      float* mu, float* sd, cudaStream_t st) {
   IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st));
   IWAE_TRY(dense_fwd(P, blk.l2, h1, blk.l1.n_out, M, ACT_TANH, h2, st));
@@ -231,7 +235,7 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   } else { f.xin = x; f.ld_xin = nx; }
   IWAE_TRY(ar.get(&f.h1, (size_t)B * h1)); IWAE_TRY(ar.get(&f.h2, (size_t)B * h1));
   IWAE_TRY(pick(ar, o->q_mu, (size_t)B * d1, &f.mu1)); IWAE_TRY(pick(ar, o->q_std, (size_t)B * d1, &f.std1));
-  IWAE_TRY(block_fwd(P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, f.mu1, f.std1, st));
+  IWAE_TRY(block_fwd_f32(P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, f.mu1, f.std1, st));
 
   // ---- z1 = mu + std*eps, k samples                                        iwae1.py:59
   IWAE_TRY(pick(ar, o->z1, (size_t)R * d1, &f.z1));
@@ -242,13 +246,13 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   if (m.two_layer()) {
     IWAE_TRY(ar.get(&f.g1, (size_t)R * h2)); IWAE_TRY(ar.get(&f.g2, (size_t)R * h2));
     IWAE_TRY(ar.get(&f.mu2, (size_t)R * d2)); IWAE_TRY(ar.get(&f.std2, (size_t)R * d2));
-    IWAE_TRY(block_fwd(P, m.enc2, f.z1, d1, R, f.g1, f.g2, f.mu2, f.std2, st));
+    IWAE_TRY(block_fwd_f32(P, m.enc2, f.z1, d1, R, f.g1, f.g2, f.mu2, f.std2, st));
     IWAE_TRY(pick(ar, o->z2, (size_t)R * d2, &f.z2));
     if (opt.keep_for_bwd) IWAE_TRY(ar.get(&f.eps2, (size_t)R * d2));
     IWAE_TRY(sample_latent(f.mu2, f.std2, 0, eps2_in, f.eps2, f.z2, B, k, d2, seed, 2, img_offset, st));
     IWAE_TRY(ar.get(&f.p1, (size_t)R * h2)); IWAE_TRY(ar.get(&f.p2, (size_t)R * h2));
     IWAE_TRY(ar.get(&f.pmu, (size_t)R * d1)); IWAE_TRY(ar.get(&f.pstd, (size_t)R * d1));
-    IWAE_TRY(block_fwd(P, m.dec21, f.z2, d2, R, f.p1, f.p2, f.pmu, f.pstd, st));
+    IWAE_TRY(block_fwd_f32(P, m.dec21, f.z2, d2, R, f.p1, f.p2, f.pmu, f.pstd, st));
   }
   // ---- CIWAE learned prior p(z|y)                                          task04.py:123
   if (m.learned_prior()) {
@@ -256,7 +260,7 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     IWAE_TRY(onehot_f32(y, B, nc, f.yoh, st));
     IWAE_TRY(ar.get(&f.p1, (size_t)B * h1)); IWAE_TRY(ar.get(&f.p2, (size_t)B * h1));
     IWAE_TRY(ar.get(&f.pmu, (size_t)B * d1)); IWAE_TRY(ar.get(&f.pstd, (size_t)B * d1));
-    IWAE_TRY(block_fwd(P, m.prior, f.yoh, nc, B, f.p1, f.p2, f.pmu, f.pstd, st));
+    IWAE_TRY(block_fwd_f32(P, m.prior, f.yoh, nc, B, f.p1, f.p2, f.pmu, f.pstd, st));
   }
 
   // ---- decoder p(x|z1)                                                     iwae1.py:79-85
@@ -303,8 +307,8 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     IWAE_TRY(ar.get(&f.lqst, (size_t)R));
     IWAE_TRY(normal_logp_rows(f.z1, f.mu1, f.std1, 1, 1e-6f, B, k, d1, f.lqst, st));        // task02.py:61-65
   }
-  if (o->kl && !m.two_layer()) {
-    f.kl = o->kl;
+  if ((o->kl || o->scalars) && !m.two_layer()) {
+    IWAE_TRY(pick(ar, o->kl, (size_t)B, &f.kl));
     IWAE_TRY(kl_rows(f.mu1, f.std1, B, d1, f.kl, st));                                      // iwae1.py:116
   }
 
@@ -316,10 +320,22 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   f.log_w = o->log_w; f.al = o->al; f.iwae = o->iwae; f.vae = o->vae; f.eq14 = o->eq14;
   f.snis1 = o->snis_z1; f.snis2 = m.two_layer() ? o->snis_z2 : nullptr;
   if (opt.keep_for_bwd && !f.al) IWAE_TRY(ar.get(&f.al, (size_t)R));
+  if (o->scalars) {
+    if (!f.iwae) IWAE_TRY(ar.get(&f.iwae, (size_t)B));
+    if (!f.vae) IWAE_TRY(ar.get(&f.vae, (size_t)B));
+    if (!f.eq14) IWAE_TRY(ar.get(&f.eq14, (size_t)B));
+  }
   if (f.lqst) IWAE_TRY(pick(ar, o->dreg, (size_t)B, &f.dreg));
   la.log_w = f.log_w; la.al = f.al; la.iwae = f.iwae; la.vae = f.vae; la.eq14 = f.eq14; la.dreg = f.dreg;
   la.snis1 = f.snis1; la.snis2 = f.snis2;
   IWAE_TRY(logw_reduce(la, st));
+  if (o->scalars) {
+    ScalarArgs sa;
+    sa.B = B; sa.R = R; sa.beta = beta;
+    sa.iwae = f.iwae; sa.vae = f.vae; sa.eq14 = f.eq14; sa.kl = f.kl; sa.dreg = f.dreg;
+    sa.lpxz = f.lpxz; sa.lpz = f.lpz; sa.lq1 = f.lq1; sa.out = o->scalars;
+    IWAE_TRY(finalize_scalars(sa, st));
+  }
   return 0;
 }
 
@@ -362,8 +378,8 @@ extern "C" int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x,
     if (out_sum) CUDA_TRY(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
     return 0;
   }
-  if (precision == IWAE_PREC_TC_F16) {
-    IWAE_TRY(tc_llh_eval(ctx, params, x, y, N, k, seed, img_offset, per, st));
+  if (precision == IWAE_PREC_TC_F16 || precision == IWAE_PREC_TC_F16_FAST) {
+    IWAE_TRY(tc_llh_eval(ctx, params, x, y, N, k, seed, img_offset, precision == IWAE_PREC_TC_F16_FAST, per, st));
   } else {
     IWAE_REQUIRE(precision == IWAE_PREC_FP32, "iwae_llh_eval: unknown precision %d", precision);
     // chunk the images so that one chunk's activations stay around 256k rows
@@ -380,6 +396,14 @@ extern "C" int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x,
     }
   }
   if (out_sum) IWAE_TRY(sum_to_double(per, N, out_sum, 0, st));
+  return 0;
+}
+
+extern "C" int iwae_llh_kernel_ms(iwae_ctx* ctx, float* ms) {
+  IWAE_REQUIRE(ctx && ms, "iwae_llh_kernel_ms: null argument");
+  IWAE_REQUIRE(ctx->ev_valid, "iwae_llh_kernel_ms: no tensor-core evaluation has run on this context");
+  CUDA_TRY(cudaEventSynchronize(ctx->ev_k1));
+  CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
   return 0;
 }
 
@@ -624,7 +648,8 @@ extern "C" int iwae_bernoulli_sample(const float* p, int64_t n, uint64_t seed, u
   return bernoulli_sample_f32(p, n, seed, epoch, out, (cudaStream_t)stream);
 }
 
-extern "C" int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, float* D, void* stream) {
+extern "C" int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, int32_t variant, float* D,
+                                  void* stream) {
   IWAE_REQUIRE(A && B && D, "iwae_umma_selftest: null argument");
-  return umma_selftest(A, B, N, K, D, (cudaStream_t)stream);
+  return umma_selftest(A, B, N, K, variant, D, (cudaStream_t)stream);
 }

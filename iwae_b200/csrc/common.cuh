@@ -17,6 +17,14 @@ void iwae_set_error(const char* fmt, ...);
     }                                                                                           \
   } while (0)
 
+extern long long g_iwae_launches;
+// after every kernel launch: count it and surface launch-configuration errors
+#define LAUNCH_CHECK()                                                                          \
+  do {                                                                                          \
+    ++g_iwae_launches;                                                                          \
+    CUDA_TRY(cudaGetLastError());                                                               \
+  } while (0)
+
 #define IWAE_REQUIRE(cond, ...)                                                                 \
   do {                                                                                          \
     if (!(cond)) {                                                                              \
@@ -78,6 +86,7 @@ struct iwae_ctx {
   float* per_buf = nullptr; size_t per_cap = 0;       // per-example results
   float* stage_x = nullptr; size_t stage_x_cap = 0;   // x (and y) copied from the host
   float* stage_aux = nullptr; size_t stage_aux_cap = 0;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr; bool ev_valid = false;   // around the fused eval kernel
 };
 
 // ---- fp32 kernels (kernels_f32.cu) ----
@@ -129,6 +138,13 @@ struct LogwArgs {
   float *snis1 = nullptr, *snis2 = nullptr;
 };
 int logw_reduce(const LogwArgs& a, cudaStream_t st);
+struct ScalarArgs {
+  int B = 0; int64_t R = 0; float beta = 1.f;
+  const float *iwae = nullptr, *vae = nullptr, *eq14 = nullptr, *kl = nullptr, *dreg = nullptr;
+  const float *lpxz = nullptr, *lpz = nullptr, *lq1 = nullptr;
+  float* out = nullptr;   // [8]
+};
+int finalize_scalars(const ScalarArgs& a, cudaStream_t st);
 int sum_to_double(const float* v, int64_t n, double* acc, int accumulate, cudaStream_t st);
 
 // backward helpers
@@ -165,6 +181,8 @@ int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st);
 // ---- fused tcgen05 evaluation (eval_tc.cu) ----
 int tc_pack_weights(iwae_ctx* ctx, const float* params, cudaStream_t st);
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k,
-                uint64_t seed, int64_t img_offset, float* out_per_example, cudaStream_t st);
+                uint64_t seed, int64_t img_offset, int fast, float* out_per_example, cudaStream_t st);
+int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
+                  float* mu, float* sd, cudaStream_t st);
 void tc_release(iwae_ctx* ctx);
-int umma_selftest(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);
+int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st);

@@ -193,7 +193,7 @@ constexpr int TILE_M = 128;
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_CHUNKS = 7;
 constexpr int CHUNK_N_MAX = 112;
-constexpr int NSTAGES = 4;
+constexpr int NSTAGES = 3;
 constexpr int SLAB_K = 32;
 constexpr int SLAB_BYTES = CHUNK_N_MAX * SLAB_K * 2;   // 7168
 constexpr int KZ_MAX = 112;                            // K capacity of the z1 buffer
@@ -252,6 +252,9 @@ struct __align__(16) SmemLayout {
   int label;
 };
 
+// two CTAs per SM: 2 * (dynamic smem + 1 KB reserved) must fit the 228 KB of an SM
+static_assert(2 * (sizeof(SmemLayout) + 128 + 1024) <= 228 * 1024, "fused eval kernel: two CTAs must fit one SM");
+
 #define LOG2PI_HALF_F 0.91893853320467274178f
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -272,6 +275,12 @@ __device__ __forceinline__ void store16(uint8_t* buf, int row, int k0, const flo
   uint4 b = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
   *reinterpret_cast<uint4*>(buf + (size_t)(k0 >> 3) * (TILE_M * 16) + row * 16) = a;
   *reinterpret_cast<uint4*>(buf + (size_t)((k0 >> 3) + 1) * (TILE_M * 16) + row * 16) = b;
+}
+
+// store 8 consecutive k values (one 16-byte core-matrix row) of one row
+__device__ __forceinline__ void store8(uint8_t* buf, int row, int k0, const float (&v)[8]) {
+  uint4 a = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+  *reinterpret_cast<uint4*>(buf + (size_t)(k0 >> 3) * (TILE_M * 16) + row * 16) = a;
 }
 
 template <bool FAST>
@@ -470,26 +479,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               if (off + g < Ly.next_kpad) store16(dst, row, off + g, v);
             }
           } else if (Ly.kind == EPI_GSAMPLE) {
-            // columns [0,cnt) = mu2, [cnt,2cnt) = log-std2 pre-activation; z2 = mu2 + std2*eps2 (iwae2.py:65)
+            // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8].
+            // z2 = mu2 + std2*eps2 (iwae2.py:65); one 16-byte A-operand row segment per group.
             const uint32_t gimg = (uint32_t)(args.img_offset + img);
-            for (int g = 0; g < Ly.next_kpad; g += 16) {
-              float v[16];
-              if (g < cnt) {
-                uint32_t rm[16], ra[16];
-                tmem_ld16(tbase + g, rm);
-                tmem_ld16(tbase + cnt + g, ra);
+            for (int g8 = 0; g8 < Ly.next_kpad; g8 += 8) {
+              float v[8];
+              if (g8 < cnt) {
+                uint32_t r[16];
+                tmem_ld16(tbase + 2 * g8, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                  const float4 n4 = philox_normal4(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g) >> 2) + qq);
+                for (int qq = 0; qq < 2; ++qq) {
+                  const float4 n4 = philox_normal4(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2) + qq);
                   const float e[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
-                    const int j = g + 4 * qq + i;
+                    const int j = g8 + 4 * qq + i;
                     float val = 0.f;
                     if (j < cnt) {
-                      const float m = __uint_as_float(rm[4 * qq + i]);
-                      const float sd = act_exp<FAST>(__uint_as_float(ra[4 * qq + i])) + 1e-6f;
+                      const float m = __uint_as_float(r[4 * qq + i]);
+                      const float sd = act_exp<FAST>(__uint_as_float(r[8 + 4 * qq + i])) + 1e-6f;
                       const float z = e[i] * sd + m;
                       const float t = z / sd - m / sd;
                       lq2 += -0.5f * t * t - (LOG2PI_HALF_F + act_log<FAST>(sd));      // iwae2.py:118
@@ -503,27 +512,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = (g + i == cnt) ? 1.f : 0.f;
+                for (int i = 0; i < 8; ++i) v[i] = (g8 + i == cnt) ? 1.f : 0.f;
               }
-              store16(dst, row, g, v);
+              store8(dst, row, g8, v);
             }
           } else if (Ly.kind == EPI_GLOGP) {
-            // columns [0,cnt) = mu, [cnt,2cnt) = log-std pre-activation of p(z1|z2) for dims off..off+cnt
-            for (int g = 0; g < cnt; g += 16) {
-              uint32_t rm[16], ra[16];
-              tmem_ld16(tbase + g, rm);
-              tmem_ld16(tbase + cnt + g, ra);
+            // same column layout; log p(z1|z2) over dims off..off+cnt (iwae2.py:120), z1 re-read from bufZ
+            for (int g8 = 0; g8 < cnt; g8 += 8) {
+              uint32_t r[16];
+              tmem_ld16(tbase + 2 * g8, r);
               tmem_ld_wait();
-              const uint4 za = *reinterpret_cast<const uint4*>(S.bufZ + (size_t)((off + g) >> 3) * (TILE_M * 16) + row * 16);
-              const uint4 zb = *reinterpret_cast<const uint4*>(S.bufZ + (size_t)(((off + g) >> 3) + 1) * (TILE_M * 16) + row * 16);
-              const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+              const uint4 za = *reinterpret_cast<const uint4*>(S.bufZ + (size_t)((off + g8) >> 3) * (TILE_M * 16) + row * 16);
+              const uint32_t zw[4] = {za.x, za.y, za.z, za.w};
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (g + i < cnt) {
+              for (int i = 0; i < 8; ++i) {
+                if (g8 + i < cnt) {
                   const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
                   const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
-                  const float m = __uint_as_float(rm[i]);
-                  const float sd = act_exp<FAST>(__uint_as_float(ra[i])) + 1e-6f;
+                  const float m = __uint_as_float(r[i]);
+                  const float sd = act_exp<FAST>(__uint_as_float(r[8 + i])) + 1e-6f;
                   const float t = z / sd - m / sd;
                   lp12 += -0.5f * t * t - (LOG2PI_HALF_F + act_log<FAST>(sd));          // iwae2.py:120
                 }
@@ -625,8 +632,9 @@ __global__ void pack_layer_kernel(PackLayer pl, __half* __restrict__ out) {
       const float* W = pl.W; const float* b = pl.b; int col = -1;
       if (!pl.gauss) { if (n < cnt) col = off + n; }
       else {
-        if (n < cnt) col = off + n;
-        else if (n < 2 * cnt) { col = off + n - cnt; W = pl.W2; b = pl.b2; }
+        // 16 columns per 8 latent dims: [mu x8 | log-std pre-activation x8]
+        const int dl = 8 * (n >> 4) + (n & 7);
+        if (dl < cnt) { col = off + dl; if (n & 8) { W = pl.W2; b = pl.b2; } }
       }
       if (col >= 0) {
         if (k < pl.k_real) v = W[(int64_t)k * pl.ldw + col];
@@ -694,15 +702,14 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P) {
     L.nchunks = 0;
     for (int off = 0; off < d; off += per_chunk) {
       const int cnt = std::min(per_chunk, d - off);
-      L.chunk_cnt[L.nchunks] = cnt; L.chunk_off[L.nchunks] = off; L.chunk_n[L.nchunks] = round16(2 * cnt);
+      L.chunk_cnt[L.nchunks] = cnt; L.chunk_off[L.nchunks] = off; L.chunk_n[L.nchunks] = 16 * ((cnt + 7) / 8);
       ++L.nchunks;
     }
     K.W = P + B.lmu.w; K.b = P + B.lmu.b; K.W2 = P + B.lstd.w; K.b2 = P + B.lstd.b;
     K.k_real = B.lmu.n_in; K.k_pad = k_pad; K.ldw = d; K.gauss = 1;
   };
   if (m.two_layer()) {
-    IWAE_REQUIRE(c.h2 + 1 <= KP_MAX && 2 * c.d2 <= CHUNK_N_MAX && c.d2 + 1 <= KP_MAX,
-                 "tensor-core path: needs h2 <= %d and d2 <= %d", KP_MAX - 1, CHUNK_N_MAX / 2);
+    IWAE_REQUIRE(c.h2 + 1 <= KP_MAX && c.d2 <= 56, "tensor-core path: needs h2 <= %d and d2 <= 56", KP_MAX - 1);
     const int kh2 = round16(c.h2 + 1), kd2 = round16(c.d2 + 1);
     tanh_layer(m.enc2.l1, 0, 1, kz);                                  // q(z2|z1) l1
     tanh_layer(m.enc2.l2, 1, 1, kh2);                                 //          l2
@@ -754,7 +761,7 @@ int tc_pack_weights(iwae_ctx* ctx, const float* params, cudaStream_t st) {
   if (!tp.wpack) CUDA_TRY(cudaMalloc((void**)&tp.wpack, tp.wpack_bytes));
   for (int l = 0; l < tp.prog.nlayers; ++l) {
     tc::pack_layer_kernel<<<64, 256, 0, st>>>(tp.pl[l], reinterpret_cast<__half*>(tp.wpack));
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH_CHECK();
   }
   CUDA_TRY(cudaMemcpyToSymbolAsync(tc::c_prog, &tp.prog, sizeof(tc::Program), 0, cudaMemcpyHostToDevice, st));
   return 0;
@@ -768,11 +775,8 @@ void tc_release(iwae_ctx* ctx) {
   ctx->tc = nullptr;
 }
 
-int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
-                  float* mu, float* sd, cudaStream_t st);
-
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k, uint64_t seed,
-                int64_t img_offset, float* out_per_example, cudaStream_t st) {
+                int64_t img_offset, int fast, float* out_per_example, cudaStream_t st) {
   const ModelP& m = ctx->model;
   const iwae_config& c = m.cfg;
   IWAE_REQUIRE(!m.cond() || y, "tensor-core path: CIWAE needs labels");
@@ -816,28 +820,31 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   a.partial = tp.partial;
 
   const size_t smem = sizeof(tc::SmemLayout) + 128;
-  auto kern = tc::iwae_eval_tc_kernel<false>;
+  auto kern = fast ? tc::iwae_eval_tc_kernel<true> : tc::iwae_eval_tc_kernel<false>;
   if (!tp.attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tp.attr_set = true;
   }
   int grid = (int)std::min<int64_t>(a.n_tiles, (int64_t)2 * ctx->sm_count);
+  if (!ctx->ev_k0) { CUDA_TRY(cudaEventCreate(&ctx->ev_k0)); CUDA_TRY(cudaEventCreate(&ctx->ev_k1)); }
+  CUDA_TRY(cudaEventRecord(ctx->ev_k0, st));
   kern<<<grid, tc::NUM_THREADS, smem, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaEventRecord(ctx->ev_k1, st));
+  ctx->ev_valid = true;
   tc::combine_partials_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(tp.partial, N, a.tiles_per_img, k, out_per_example);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
-int umma_selftest(const float* A, const float* B, int N, int K, float* D, cudaStream_t st) {
+int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st) {
   IWAE_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "umma_selftest: N must be a multiple of 16 in [16,256]");
   IWAE_REQUIRE(K >= 1 && K <= 256, "umma_selftest: K must be in [1,256]");
-  int variant = 0;
-  if (K < 0) variant = 1;
   const int Kp = (K + 15) & ~15;
   const size_t smem = (size_t)Kp * (128 + N) * 2;
   CUDA_TRY(cudaFuncSetAttribute(tc::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc::umma_selftest_kernel<<<1, 128, smem, st>>>(A, B, N, K, D, variant);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }

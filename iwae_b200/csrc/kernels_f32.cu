@@ -118,7 +118,7 @@ int gemm_f32(const GemmArgs& a, cudaStream_t st) {
     dim3 grid((a.M + 63) / 64, (a.N + 63) / 64);
     gemm_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);
   }
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -143,7 +143,7 @@ __global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, i
 }
 int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st) {
   colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(A, lda, M, N, out);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -169,7 +169,7 @@ int concat_onehot(const float* x, int64_t ldx, int n, const float* y, int B, int
   const int64_t total = (int64_t)rows * (n + nc);
   const int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
   concat_onehot_kernel<<<blocks, 256, 0, st>>>(x, ldx, n, y, B, rows, nc, out);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 int onehot_f32(const float* y, int B, int nc, float* out, cudaStream_t st) {
@@ -215,7 +215,7 @@ int sample_latent(const float* mu, const float* sd, int bcast, const float* eps_
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
   sample_latent_kernel<<<blocks, 256, 0, st>>>(mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 int philox_fill(uint64_t seed, int stream_id, int64_t img_offset, int B, int k, int d, float* out, cudaStream_t st) {
@@ -255,7 +255,7 @@ int normal_logp_rows(const float* z, const float* mu, const float* sd, int bcast
   int64_t blocks = (R + 7) / 8;
   if (blocks > 148 * 32) blocks = 148 * 32;
   normal_logp_rows_kernel<<<(int)blocks, 256, 0, st>>>(z, mu, sd, bcast, std_extra, B, R, d, out);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -276,7 +276,7 @@ __global__ void kl_rows_kernel(const float* __restrict__ mu, const float* __rest
 }
 int kl_rows(const float* mu, const float* sd, int B, int d, float* out, cudaStream_t st) {
   kl_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(mu, sd, B, d, out);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -291,7 +291,7 @@ int bern_reduce_partials(const float* partial, int R, int nt, float* lpxz, cudaS
   if (R == 0) return 0;
   int blocks = (R + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
   bern_reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, R, nt, lpxz);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -318,7 +318,7 @@ int bern_logp_rows(const float* logits, const float* x, int R, int B, int n, flo
   if (R == 0) return 0;
   int64_t blocks = ((int64_t)R + 7) / 8; if (blocks > 148 * 32) blocks = 148 * 32;
   bern_logp_rows_kernel<<<(int)blocks, 256, 0, st>>>(logits, x, R, B, n, lpxz);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -403,7 +403,34 @@ __global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
 int logw_reduce(const LogwArgs& a, cudaStream_t st) {
   if (a.B == 0) return 0;
   logw_reduce_kernel<<<a.B, 256, 0, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// Batch-mean scalars of the result dict (iwae1.py:119-134): one CTA, fixed order -> deterministic.
+__global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
+  __shared__ float red[8];
+  auto mean_of = [&](const float* v, int64_t n) -> float {
+    if (!v || n == 0) return 0.f;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    return block_reduce(s, red, false) / (float)n;
+  };
+  const float m_vae = mean_of(a.vae, a.B), m_iwae = mean_of(a.iwae, a.B), m_eq14 = mean_of(a.eq14, a.B);
+  const float m_kl = mean_of(a.kl, a.B), m_dreg = mean_of(a.dreg, a.B);
+  const float m_lpxz = mean_of(a.lpxz, a.R), m_lpz = mean_of(a.lpz, a.R), m_lq1 = mean_of(a.lq1, a.R);
+  if (threadIdx.x == 0) {
+    a.out[0] = m_vae;
+    a.out[1] = m_lpxz - a.beta * m_kl;      // vae_elbo_kl (iwae1.py:121)
+    a.out[2] = m_iwae;
+    a.out[3] = m_eq14;
+    a.out[4] = -m_dreg;                     // inference_loss (task02.py:76)
+    a.out[5] = m_lpxz; a.out[6] = m_lpz; a.out[7] = m_lq1;
+  }
+}
+int finalize_scalars(const ScalarArgs& a, cudaStream_t st) {
+  finalize_scalars_kernel<<<1, 256, 0, st>>>(a);
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -422,7 +449,7 @@ __global__ void sum_to_double_kernel(const float* __restrict__ v, int64_t n, dou
 }
 int sum_to_double(const float* v, int64_t n, double* acc, int accumulate, cudaStream_t st) {
   sum_to_double_kernel<<<1, 256, 0, st>>>(v, n, acc, accumulate);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -444,7 +471,7 @@ int row_coef(const float* al, int B, int k, int objective, int B_norm, float* g,
   if (R == 0) return 0;
   int blocks = (int)((R + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   row_coef_kernel<<<blocks, 256, 0, st>>>(al, R, k, objective, B_norm, g);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -465,7 +492,7 @@ int dlogits_f32(const float* logits, const float* x, const float* g, int R, int 
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
   dlogits_kernel<<<blocks, 256, 0, st>>>(logits, x, g, R, B, n, dl);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -530,7 +557,7 @@ int latent1_bwd(const Latent1BwdArgs& a, cudaStream_t st) {
   const int n = a.B * a.d;
   if (n == 0) return 0;
   latent1_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -554,7 +581,7 @@ int gauss_rows_bwd(const float* g, const float* z, const float* pmu, const float
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   gauss_rows_bwd_kernel<<<blocks, 256, 0, st>>>(g, z, pmu, pstd, R, d, dpmu, dpa);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -575,7 +602,7 @@ int latent2_bwd(const Latent2BwdArgs& a, cudaStream_t st) {
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   latent2_bwd_kernel<<<blocks, 256, 0, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -615,7 +642,7 @@ int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
   const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   int blocks = (int)((n / 4 + 255) / 256); if (blocks > 148 * 4) blocks = 148 * 4; if (blocks < 1) blocks = 1;
   adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, aligned ? 1 : 0, (float)lr_t, b1, b2, eps);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -641,7 +668,7 @@ int bernoulli_sample_f32(const float* p, int64_t n, uint64_t seed, uint64_t epoc
   if (n == 0) return 0;
   int64_t blocks = ((n + 3) / 4 + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
   bernoulli_sample_kernel<<<(int)blocks, 256, 0, st>>>(p, n, seed, epoch, out);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -659,7 +686,7 @@ __global__ void __launch_bounds__(256) softmax_vec_kernel(const float* __restric
 }
 int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st) {
   softmax_vec_kernel<<<1, 256, 0, st>>>(x, L, out);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return 0;
 }
 
@@ -727,7 +754,7 @@ int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64
   CUDA_TRY(cudaMallocAsync((void**)&scratch, bytes, st));
   sir_kernel<<<1, 256, 0, st>>>(al, L, u, n_u, size, out_idx, out_consumed, scratch, scratch + L,
                                reinterpret_cast<int32_t*>(scratch + 2 * (size_t)L));
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   CUDA_TRY(cudaFreeAsync(scratch, st));
   return 0;
 }

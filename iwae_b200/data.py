@@ -1,0 +1,65 @@
+"""Host-side data helpers mirroring `src/utils.py` of the reference, plus the synthetic stand-in for
+MNIST (no dataset is reachable from this image)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def get_bias(train_mean: np.ndarray) -> np.ndarray:
+    """utils.get_bias (src/utils.py:11-23): logit of the clipped mean train pixel.  The reference
+    reloads MNIST inside; here the caller passes the mean of whatever train set it has."""
+    return -np.log(1.0 / np.clip(np.asarray(train_mean, dtype=np.float64), 0.001, 0.999) - 1.0)
+
+
+def bernoullisample(x: np.ndarray) -> np.ndarray:
+    """utils.bernoullisample (src/utils.py:26-27), on the NumPy global RNG like the reference."""
+    return np.random.binomial(1, x, size=x.shape).astype("float32")
+
+
+def synthetic_mnist(n_train: int = 60000, n_test: int = 10000, seed: int = 123, n_x: int = 784):
+    """Intensities rand**4 (mean 0.2), labels uniform over 10 classes; returns
+    (Ptrain, ytrain), (Ptest, ytest) with P in [0,1] float64 like `Xtrain/255` (main.py:64-65)."""
+    rs = np.random.RandomState(seed)
+    Ptrain = rs.rand(n_train, n_x) ** 4
+    ytrain = rs.randint(0, 10, n_train)
+    Ptest = rs.rand(n_test, n_x) ** 4
+    ytest = rs.randint(0, 10, n_test)
+    return (Ptrain, ytrain), (Ptest, ytest)
+
+
+def synthetic_binarised(n: int, seed: int = 123, n_x: int = 784):
+    """(P, X, y): n images binarised exactly like utils.bernoullisample; same stream as the oracle's
+    `synthetic_data` so tests and bench share inputs."""
+    rs = np.random.RandomState(seed)
+    P = rs.rand(n, n_x) ** 4
+    X = rs.binomial(1, P, size=P.shape).astype("float32")
+    y = rs.randint(0, 10, n)
+    return P, X, y
+
+
+def lr_schedule():
+    """main.py:44-51: {first epoch: learning rate}, and the total number of epochs (3280)."""
+    epochs, d = 0, {}
+    for i in range(8):
+        d[epochs] = 0.001 * 10 ** (-i / 7)
+        epochs += 3 ** i
+    return d, epochs
+
+
+class MyMetric:
+    """utils.MyMetric (src/utils.py:30-45): running mean over appended batches of values."""
+
+    def __init__(self):
+        self.VALUES, self.N = [], []
+
+    def update_state(self, losses):
+        a = np.asarray(losses.numpy() if hasattr(losses, "numpy") else losses, dtype=np.float64)
+        a = a.reshape(a.shape[0], -1) if a.ndim else a.reshape(1, 1)
+        self.VALUES.append(a)
+        self.N.append(a.shape[0])
+
+    def result(self):
+        return np.float32(np.sum(np.concatenate(self.VALUES, axis=0)) / np.float32(np.sum(self.N)))
+
+    def reset_states(self):
+        self.VALUES, self.N = [], []

@@ -1,0 +1,710 @@
+"""Host-side mirror of the reference's model/objective API.
+
+Same names, argument meaning and error behaviour as `src/iwae1.py`, `src/iwae2.py`,
+`tasks/task02.py` (IWAEDReG) and `tasks/task04.py` / `tasks/task05.py` (CIWAE) of nbip/IWAE, so the
+reference's drivers can run on it unchanged; every number is produced by libiwae_b200.so
+(hand-written sm_100a kernels) through the ctypes C-ABI in `_abi.py`.  PyTorch tensors appear only as
+device-buffer handles.  There is no CPU path: constructing a model without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import Config, Outputs, check, lib
+
+_F32 = torch.float32
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+class DeviceValue:
+    """What the result dict holds: a device buffer that answers the few things the reference's drivers
+    ask of a tf.Tensor - `.numpy()`, indexing (`res['iwae_elbo'][None, None]`, main.py:177), `.shape`,
+    float() and `format(v, '.2f')` (main.py:161-162)."""
+
+    __slots__ = ("tensor",)
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+    def numpy(self) -> np.ndarray:
+        return self.tensor.detach().cpu().numpy()
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    @property
+    def dtype(self):
+        return self.tensor.dtype
+
+    def __getitem__(self, idx):
+        return DeviceValue(self.tensor[idx])
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __float__(self):
+        return float(self.tensor.item())
+
+    def __format__(self, spec):
+        return format(float(self), spec) if self.tensor.numel() == 1 else format(self.numpy(), spec)
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+    def __repr__(self):
+        return f"DeviceValue(shape={self.shape}, device={self.tensor.device})"
+
+
+class Result(dict):
+    """The dict `IWAE.call` returns.  The large entries (`logits` [k,B,784], `z`) are thunks resolved on
+    first access, so a training or monitoring step does not write GBs nobody reads (the reference
+    materialises them on every call, src/iwae1.py:141-151)."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if callable(v):
+            v = v()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
+class Variable:
+    """One entry of `model.trainable_weights`: a view into the model's flat parameter buffer with the
+    Keras layout (`kernel [in,out]`, `bias [out]`)."""
+
+    def __init__(self, name: str, view: torch.Tensor, offset: int):
+        self.name = name
+        self.value = view
+        self.offset = offset
+
+    @property
+    def shape(self):
+        return tuple(self.value.shape)
+
+    def numpy(self) -> np.ndarray:
+        return self.value.detach().cpu().numpy()
+
+    def assign(self, v):
+        self.value.copy_(torch.as_tensor(np.asarray(v), dtype=_F32).reshape(self.value.shape))
+        return self
+
+    def __repr__(self):
+        return f"<Variable {self.name} shape={self.shape}>"
+
+
+class Normal:
+    """Minimal stand-in for `tfd.Normal` as the reference reads it: `.loc`, `.scale`
+    (plot_task01.py:40-42, task02.py:61)."""
+
+    def __init__(self, loc: torch.Tensor, scale: torch.Tensor):
+        self.loc = DeviceValue(loc)
+        self.scale = DeviceValue(scale)
+
+
+class Bernoulli:
+    """Minimal stand-in for `tfd.Bernoulli(logits)`: `.logits`, `.log_prob(x)` (plot_task01.py:63)."""
+
+    def __init__(self, owner: "IWAE", z: torch.Tensor, y, logits: torch.Tensor):
+        self._owner, self._z, self._y = owner, z, y
+        self.logits = DeviceValue(logits)
+
+    def log_prob_sum(self, x) -> DeviceValue:
+        """sum_j log p(x_j | z): the reduction the reference applies right after log_prob
+        (iwae1.py:111), computed in the decoder kernel's fused epilogue."""
+        return self._owner._decode(self._z, self._y, x, want_logits=False)[1]
+
+
+def _block_names(prefix):
+    out = []
+    for lyr in ("l1", "l2", "lmu", "lstd"):
+        out += [f"{prefix}.{lyr}.kernel", f"{prefix}.{lyr}.bias"]
+    return out
+
+
+def _mlp3_names(prefix):
+    out = []
+    for i in range(3):
+        out += [f"{prefix}.dense{i}.kernel", f"{prefix}.dense{i}.bias"]
+    return out
+
+
+class _SubModel:
+    """`model.encoder` / `model.decoder` / `model.conditional_prior_network`: owns a contiguous range of
+    the flat parameter buffer (task02.py:95-99 reads `.trainable_weights` of each)."""
+
+    def __init__(self, owner: "IWAE", prefix: str):
+        self._owner, self._prefix = owner, prefix
+
+    @property
+    def trainable_weights(self) -> List[Variable]:
+        return [v for v in self._owner.trainable_weights if v.name.startswith(self._prefix + ".")]
+
+
+class _Encoder(_SubModel):
+    def __call__(self, x, n_samples, y=None):
+        """Encoder.call (iwae1.py:56-61): returns (z [k,B,d], qzx)."""
+        o = self._owner
+        res = o._forward(x, y, int(n_samples), 1.0, want=("z1", "q_mu", "q_std"))
+        return DeviceValue(res["z1"]), Normal(res["q_mu"], res["q_std"])
+
+
+class _Decoder(_SubModel):
+    def __call__(self, z, y=None):
+        """Decoder.call (iwae1.py:79-85): returns (logits, pxz)."""
+        logits, _ = self._owner._decode(z, y, None, want_logits=True)
+        zt = z.tensor if isinstance(z, DeviceValue) else z
+        return logits, Bernoulli(self._owner, zt, y, logits.tensor)
+
+    def decode_z_to_x(self, z, y=None):
+        return self._owner._decode(z, y, None, want_logits=True)[0]
+
+
+class IWAE:
+    """iwae1.IWAE (src/iwae1.py:88-166): one stochastic layer.
+
+    `IWAE(n_hidden, n_latent)`; `model(x, n_samples, beta=1.0)` -> dict with the reference's keys;
+    `train_step(x, n_samples, beta, optimizer, objective=...)`; `val_step(x, n_samples, beta)`.
+    Extras over the reference: `eps=` (inject the N(0,1) noise, [k,B,d]), `seed=`, and the per-example
+    vectors `iwae_elbo_per_example` / `vae_elbo_per_example` / `log_w` in the result.
+    """
+
+    KIND = _abi.KIND_IWAE1
+    # result-dict names of (lpxz, prior term, q term): src/iwae1.py:141-151
+    TERM_KEYS = ("lpxz", "lpz", "lqzx")
+
+    def __init__(self, n_hidden, n_latent, n_x: int = 784, n_cond: int = 0, seed: int = 123, device=None,
+                 out_bias: Optional[np.ndarray] = None, **kwargs):
+        if not torch.cuda.is_available():
+            raise RuntimeError("iwae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._cfg = self._make_config(n_hidden, n_latent, n_x, n_cond)
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.iwae_create(C.byref(self._cfg), C.byref(self._ctx)), "iwae_create")
+        n_params, layout = _abi.layout_for_config(self._cfg)
+        self.n_params = n_params
+        self.params = torch.zeros(n_params, dtype=_F32, device=self.device)
+        self._names = self._param_names()
+        assert len(self._names) == len(layout)
+        self.trainable_weights: List[Variable] = []
+        for name, (off, rows, cols) in zip(self._names, layout):
+            n = rows * cols if cols else rows
+            view = self.params[off:off + n].view(rows, cols) if cols else self.params[off:off + n]
+            self.trainable_weights.append(Variable(name, view, off))
+        self._seed = int(seed)
+        self._calls = 0
+        self._build_submodels()
+        self.init_weights(np.random.RandomState(seed), out_bias)
+
+    # ---- construction ---------------------------------------------------------------------------
+    def _make_config(self, n_hidden, n_latent, n_x, n_cond) -> Config:
+        return Config(self.KIND, int(n_x), 0, int(n_hidden), 0, int(n_latent), 0)
+
+    def _param_names(self) -> List[str]:
+        return _block_names("encoder.encode_x_to_z") + _mlp3_names("decoder.decode_z_to_x")
+
+    def _build_submodels(self):
+        self.encoder = _Encoder(self, "encoder")
+        self.decoder = _Decoder(self, "decoder")
+
+    def __del__(self):
+        ctx = getattr(self, "_ctx", None)
+        if ctx is not None and ctx.value:
+            try:
+                lib.iwae_destroy(ctx)
+            except Exception:
+                pass
+            self._ctx = C.c_void_p()
+
+    # ---- weights --------------------------------------------------------------------------------
+    def init_weights(self, rs: np.random.RandomState, out_bias: Optional[np.ndarray] = None, scale: float = 1.0):
+        """Keras defaults: kernels glorot_uniform, biases zero; the 784-way output bias is utils.get_bias()
+        (iwae1.py:74-75).  TF's seeded initialiser stream is not reproducible outside TF, so values
+        come from `rs`; only the order and shapes are the reference's."""
+        flat = np.zeros(self.n_params, dtype=np.float32)
+        for v in self.trainable_weights:
+            shp = v.shape
+            if len(shp) == 2:
+                lim = math.sqrt(6.0 / (shp[0] + shp[1])) * scale
+                flat[v.offset:v.offset + shp[0] * shp[1]] = rs.uniform(-lim, lim, size=shp).astype(np.float32).ravel()
+        if out_bias is not None:
+            last = [v for v in self.trainable_weights if v.name.endswith("dense2.bias")][-1]
+            flat[last.offset:last.offset + last.shape[0]] = np.asarray(out_bias, dtype=np.float64).astype(np.float32)
+        self.params.copy_(torch.from_numpy(flat))
+
+    def get_weights(self) -> "OrderedDict[str, np.ndarray]":
+        return OrderedDict((v.name, v.numpy()) for v in self.trainable_weights)
+
+    def set_weights(self, weights):
+        """dict name -> array, or a list in `trainable_weights` order."""
+        if isinstance(weights, dict):
+            for v in self.trainable_weights:
+                v.assign(weights[v.name])
+        else:
+            weights = list(weights)
+            assert len(weights) == len(self.trainable_weights)
+            for v, w in zip(self.trainable_weights, weights):
+                v.assign(w)
+
+    def save_weights(self, path: str):
+        """model.save_weights (main.py:165).  Own format (.npz keyed by the Keras-style names); the
+        TF checkpoint format cannot be written without TF."""
+        import os
+        os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
+        np.savez(path if path.endswith(".npz") else path + ".npz", **self.get_weights())
+
+    def load_weights(self, path: str):
+        with np.load(path if path.endswith(".npz") else path + ".npz") as f:
+            self.set_weights({k: f[k] for k in f.files})
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _dev(self, a, dtype=_F32) -> Optional[torch.Tensor]:
+        if a is None:
+            return None
+        if isinstance(a, DeviceValue):
+            a = a.tensor
+        if not isinstance(a, torch.Tensor):
+            a = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32 if dtype == _F32 else None)))
+        return a.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+
+    def _next_seed(self, seed=None) -> int:
+        if seed is not None:
+            return int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._calls += 1
+        return _splitmix64(self._seed * 0x100000001B3 + self._calls)
+
+    @property
+    def _d1(self):
+        return self._cfg.d1
+
+    @property
+    def _d2(self):
+        return self._cfg.d2
+
+    def _alloc(self, *shape):
+        return torch.empty(*shape, dtype=_F32, device=self.device)
+
+    def _outputs(self, B, k, want: Sequence[str]):
+        """Allocate the requested output buffers; returns (Outputs struct, dict name -> tensor)."""
+        cfg = self._cfg
+        shapes = {
+            "lpxz": (k, B), "lpz": (k, B), "lq1": (k, B), "lq2": (k, B), "lp12": (k, B), "log_w": (k, B),
+            "al": (k, B), "iwae": (B,), "vae": (B,), "eq14": (B,), "kl": (B,), "dreg": (B,),
+            "snis_z1": (B, cfg.d1), "snis_z2": (B, max(cfg.d2, 1)), "z1": (k, B, cfg.d1),
+            "z2": (k, B, max(cfg.d2, 1)), "logits": (k, B, cfg.n_x), "q_mu": (B, cfg.d1), "q_std": (B, cfg.d1),
+            "scalars": (8,),
+        }
+        bufs: Dict[str, torch.Tensor] = {}
+        o = Outputs()
+        for name in want:
+            t = self._alloc(*shapes[name])
+            bufs[name] = t
+            setattr(o, name, t.data_ptr())
+        return o, bufs
+
+    def _check_x(self, x, y):
+        x = self._dev(x)
+        if x.dim() == 1:
+            x = x[None, :]
+        if x.dim() != 2 or x.shape[1] != self._cfg.n_x:
+            raise ValueError(f"x must be [B, {self._cfg.n_x}], got {tuple(x.shape)}")
+        if self._cfg.n_cond:
+            if y is None:
+                raise TypeError("this model is label-conditioned: call(x, y, n_samples, beta)")
+            y = self._dev(np.asarray(y, dtype=np.float32) if not isinstance(y, (torch.Tensor, DeviceValue)) else y)
+            y = y.reshape(-1)
+            if y.shape[0] != x.shape[0]:
+                raise ValueError("x and y disagree on the batch size")
+        else:
+            y = None
+        return x, y
+
+    def _check_eps(self, eps, k, B, d, what):
+        if eps is None:
+            return None
+        eps = self._dev(eps)
+        if tuple(eps.shape) != (k, B, d):
+            raise ValueError(f"{what} must be [{k}, {B}, {d}], got {tuple(eps.shape)}")
+        return eps
+
+    def _forward(self, x, y, k, beta, want, eps1=None, eps2=None, seed=None, img_offset=0):
+        x, y = self._check_x(x, y)
+        B = x.shape[0]
+        if k <= 0:
+            raise ValueError("n_samples must be positive")
+        eps1 = self._check_eps(eps1, k, B, self._d1, "eps")
+        eps2 = self._check_eps(eps2, k, B, self._d2, "eps2") if self._d2 else None
+        o, bufs = self._outputs(B, k, want)
+        seed = self._next_seed(seed)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_forward(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), B, k, float(beta), _ptr(eps1),
+                                   _ptr(eps2), seed, int(img_offset), C.byref(o), _stream_ptr()), "iwae_forward")
+        bufs["_seed"] = seed
+        bufs["_x"], bufs["_y"], bufs["_eps1"], bufs["_eps2"] = x, y, eps1, eps2
+        return bufs
+
+    def _decode(self, z, y, x, want_logits: bool):
+        """decoder(z) and/or sum_j Bernoulli(logits).log_prob(x) for arbitrary z [..., d]
+        (plot_task01.py:57-63; model.sample, iwae1.py:168-178)."""
+        z = self._dev(z)
+        lead = tuple(z.shape[:-1])
+        if z.shape[-1] != self._d1:
+            raise ValueError(f"z must have last dim {self._d1}")
+        z2 = z.reshape(-1, self._d1)
+        R = z2.shape[0]
+        xd = self._dev(x) if x is not None else None
+        if xd is not None and xd.dim() == 1:
+            xd = xd[None, :]
+        if self._cfg.n_cond:
+            if y is None:
+                raise TypeError("this model is label-conditioned: pass y")
+            yd = self._dev(np.asarray(y, dtype=np.float32) if not isinstance(y, (torch.Tensor, DeviceValue)) else y).reshape(-1)
+            B = yd.shape[0]
+        else:
+            yd = None
+            B = xd.shape[0] if xd is not None else 1
+        if R % B:
+            raise ValueError("number of z rows must be a multiple of the batch size of x / y")
+        logits = self._alloc(R, self._cfg.n_x) if want_logits else None
+        lp = self._alloc(R) if xd is not None else None
+        with torch.cuda.device(self.device):
+            check(lib.iwae_decode(self._ctx, _ptr(self.params), _ptr(z2), _ptr(xd), _ptr(yd), R, B, _ptr(logits),
+                                  _ptr(lp), _stream_ptr()), "iwae_decode")
+        return (DeviceValue(logits.view(*lead, self._cfg.n_x)) if logits is not None else None,
+                DeviceValue(lp.view(*lead)) if lp is not None else None)
+
+    # ---- the reference API ----------------------------------------------------------------------
+    _WANT = ("lpxz", "lpz", "lq1", "log_w", "al", "iwae", "vae", "eq14", "snis_z1", "scalars")
+
+    def _lazy(self, bufs, k, beta, names):
+        """Thunk that re-runs the forward with the same noise and keeps only `names`."""
+        def run():
+            r = self._forward(bufs["_x"], bufs["_y"], k, beta, names, bufs["_eps1"], bufs["_eps2"], bufs["_seed"],
+                              bufs.get("_img_offset", 0))
+            return r
+        cache = {}
+
+        def get(name):
+            def thunk():
+                if not cache:
+                    cache.update(run())
+                return DeviceValue(cache[name])
+            return thunk
+        return get
+
+    def _result(self, bufs, k, beta) -> Result:
+        s = bufs["scalars"]
+        kx, kp, kq = self.TERM_KEYS
+        lazy = self._lazy(bufs, k, beta, ("z1", "logits"))
+        res = Result()
+        res["vae_elbo"] = DeviceValue(s[0])
+        res["vae_elbo_kl"] = DeviceValue(s[1])
+        res["iwae_elbo"] = DeviceValue(s[2])
+        res["iwae_eq14"] = DeviceValue(s[3])
+        res["z"] = lazy("z1")
+        res["snis_z"] = DeviceValue(bufs["snis_z1"])
+        res["al"] = DeviceValue(bufs["al"])
+        res["logits"] = lazy("logits")
+        res[kx] = DeviceValue(bufs["lpxz"])
+        res[kp] = DeviceValue(bufs["lpz"])
+        res[kq] = DeviceValue(bufs["lq1"])
+        self._extras(res, bufs)
+        return res
+
+    @staticmethod
+    def _extras(res, bufs):
+        res["iwae_elbo_per_example"] = DeviceValue(bufs["iwae"])
+        res["vae_elbo_per_example"] = DeviceValue(bufs["vae"])
+        res["log_w"] = DeviceValue(bufs["log_w"])
+
+    def call(self, x, n_samples, beta=1.0, eps=None, seed=None, img_offset=0):
+        """IWAE.call (src/iwae1.py:98-151)."""
+        k = int(n_samples)
+        bufs = self._forward(x, None, k, beta, self._WANT, eps, None, seed, img_offset)
+        bufs["_img_offset"] = img_offset
+        return self._result(bufs, k, beta)
+
+    __call__ = call
+
+    def val_step(self, x, n_samples, beta):
+        """IWAE.val_step (src/iwae1.py:164-166)."""
+        return self.call(x, n_samples, beta)
+
+    def _objective_id(self, objective: str, res_keys) -> int:
+        if objective not in res_keys or objective not in _abi.OBJ:
+            raise KeyError(objective)       # the reference's error for an unknown objective (iwae1.py:157)
+        return _abi.OBJ[objective]
+
+    _OBJECTIVES = ("vae_elbo", "iwae_elbo", "iwae_eq14", "vae_elbo_kl")
+
+    def _train(self, x, y, k, beta, optimizer, objective_id, eps1=None, eps2=None, seed=None, want=None):
+        x, y = self._check_x(x, y)
+        B = x.shape[0]
+        eps1 = self._check_eps(eps1, k, B, self._d1, "eps")
+        eps2 = self._check_eps(eps2, k, B, self._d2, "eps2") if self._d2 else None
+        o, bufs = self._outputs(B, k, want or self._WANT)
+        seed = self._next_seed(seed)
+        m, v = optimizer._state_for(self)
+        optimizer.iterations += 1
+        with torch.cuda.device(self.device):
+            check(lib.iwae_train_step(self._ctx, _ptr(self.params), _ptr(m), _ptr(v), _ptr(x), _ptr(y), B, k,
+                                      float(beta), objective_id, _ptr(eps1), _ptr(eps2), seed, 0,
+                                      float(optimizer.learning_rate.value), optimizer.beta_1, optimizer.beta_2,
+                                      optimizer.epsilon, optimizer.iterations, C.byref(o), _stream_ptr()),
+                  "iwae_train_step")
+        bufs["_seed"] = seed
+        bufs["_x"], bufs["_y"], bufs["_eps1"], bufs["_eps2"] = x, y, eps1, eps2
+        return bufs
+
+    def train_step(self, x, n_samples, beta, optimizer, objective="vae_elbo", eps=None, seed=None):
+        """IWAE.train_step (src/iwae1.py:153-162): forward, reverse pass of -res[objective], Keras-Adam
+        update.  The returned dict holds the PRE-update forward values, like the reference's tape."""
+        oid = self._objective_id(objective, self._OBJECTIVES)
+        k = int(n_samples)
+        bufs = self._train(x, None, k, beta, optimizer, oid, eps, None, seed)
+        return self._result(bufs, k, beta)
+
+    def grads(self, x, n_samples, beta=1.0, objective="iwae_elbo", eps=None, eps2=None, seed=None, y=None,
+              B_norm: int = 0, img_offset: int = 0) -> torch.Tensor:
+        """Flat gradient of -res[objective] in `trainable_weights` order (tape.gradient, iwae1.py:159)."""
+        oid = _abi.OBJ[objective] if objective == "dreg" else self._objective_id(objective, self._OBJECTIVES)
+        x, y = self._check_x(x, y)
+        B, k = x.shape[0], int(n_samples)
+        eps = self._check_eps(eps, k, B, self._d1, "eps")
+        eps2 = self._check_eps(eps2, k, B, self._d2, "eps2") if self._d2 else None
+        g = torch.empty_like(self.params)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_grads(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), B, k, float(beta), oid, int(B_norm),
+                                 _ptr(eps), _ptr(eps2), self._next_seed(seed), int(img_offset), _ptr(g), None,
+                                 _stream_ptr()), "iwae_grads")
+        return g
+
+    # ---- k-sample test log-likelihood (main.py:170-184) ------------------------------------------
+    def llh(self, x, n_samples=5000, y=None, precision="tc_f16_fast", seed=None, img_offset=0):
+        """Per-example log-mean-exp of `n_samples` importance weights for every row of x (device
+        resident), and their fp64 sum: returns (per_example [N] tensor, sum as 0-dim fp64 tensor)."""
+        x, y = self._check_x(x, y)
+        N = x.shape[0]
+        per = self._alloc(max(N, 1))[:N]
+        total = torch.zeros((), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_llh_eval(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), N, int(n_samples),
+                                    self._next_seed(seed), int(img_offset), _abi.PRECISIONS[precision], _ptr(per),
+                                    _ptr(total), _stream_ptr()), "iwae_llh_eval")
+        return per, total
+
+    def llh_host(self, x_host: np.ndarray, n_samples=5000, y_host=None, precision="tc_f16_fast", seed=None,
+                 img_offset=0):
+        """Same through the reference-facing HOST-buffer entry point (iwae_llh_eval_host): x (and y) are
+        host arrays, copied to the device, evaluated, results copied back; synchronous."""
+        x_host = np.ascontiguousarray(x_host, dtype=np.float32)
+        N = x_host.shape[0]
+        per = np.empty(N, dtype=np.float32)
+        total = C.c_double(0.0)
+        yh = None if y_host is None else np.ascontiguousarray(y_host, dtype=np.float32)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_llh_eval_host(self._ctx, _ptr(self.params), x_host.ctypes.data_as(C.c_void_p),
+                                         None if yh is None else yh.ctypes.data_as(C.c_void_p), N, int(n_samples),
+                                         self._next_seed(seed), int(img_offset), _abi.PRECISIONS[precision],
+                                         per.ctypes.data_as(C.c_void_p), C.byref(total), _stream_ptr()),
+                  "iwae_llh_eval_host")
+        return per, total.value
+
+    def last_eval_kernel_ms(self) -> float:
+        """Device time of the fused evaluation kernel of the most recent tensor-core `llh` call."""
+        ms = C.c_float(0.0)
+        check(lib.iwae_llh_kernel_ms(self._ctx, C.byref(ms)), "iwae_llh_kernel_ms")
+        return float(ms.value)
+
+    # ---- sampling (iwae1.py:168-178) ------------------------------------------------------------
+    def sample(self, z, y=None, seed=0):
+        """model.sample(z): decode prior samples to Bernoulli probabilities and binary draws."""
+        logits, _ = self._decode(z, y, None, want_logits=True)
+        probs = torch.sigmoid(logits.tensor)
+        n = probs.numel()
+        out = torch.empty_like(probs)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_bernoulli_sample(_ptr(probs), n, int(seed), 0, _ptr(out), _stream_ptr()),
+                  "iwae_bernoulli_sample")
+        return DeviceValue(probs), DeviceValue(out)
+
+    @staticmethod
+    def write_to_tensorboard(res, step, writer=None):
+        """iwae1.py:226-232: the five scalars the reference logs; returns them (and writes them if a
+        torch.utils.tensorboard SummaryWriter is given)."""
+        vals = {"Evaluation/vae_elbo": float(res["vae_elbo"]), "Evaluation/iwae_elbo": float(res["iwae_elbo"])}
+        for key in res.keys():
+            if key.startswith("lp") or key.startswith("lq"):
+                vals[f"Evaluation/{key}"] = float(res[key].numpy().mean())
+        if writer is not None:
+            for name, v in vals.items():
+                writer.add_scalar(name, v, step)
+        return vals
+
+
+class IWAE2(IWAE):
+    """iwae2.IWAE (src/iwae2.py:99-182): two stochastic layers; `beta` is accepted and ignored and there
+    is no `vae_elbo_kl` key (iwae2.py:128,154-167)."""
+
+    KIND = _abi.KIND_IWAE2
+    _OBJECTIVES = ("vae_elbo", "iwae_elbo", "iwae_eq14")
+    _WANT = ("lpxz", "lpz", "lq1", "lq2", "lp12", "log_w", "al", "iwae", "vae", "eq14", "snis_z1", "snis_z2",
+             "scalars")
+
+    def _make_config(self, n_hidden, n_latent, n_x, n_cond):
+        return Config(self.KIND, int(n_x), 0, int(n_hidden[0]), int(n_hidden[1]), int(n_latent[0]), int(n_latent[1]))
+
+    def _param_names(self):
+        return (_block_names("encoder.encode_x_to_z1") + _block_names("encoder.encode_z1_to_z2") +
+                _block_names("decoder.decode_z2_to_z1") + _mlp3_names("decoder.decode_z1_to_x"))
+
+    def _result(self, bufs, k, beta) -> Result:
+        s = bufs["scalars"]
+        lazy = self._lazy(bufs, k, beta, ("z1", "z2", "logits"))
+        res = Result()
+        res["vae_elbo"] = DeviceValue(s[0])
+        res["iwae_elbo"] = DeviceValue(s[2])
+        res["iwae_eq14"] = DeviceValue(s[3])
+        res["z1"] = lazy("z1")
+        res["z2"] = lazy("z2")
+        res["snis_z1"] = DeviceValue(bufs["snis_z1"])
+        res["snis_z2"] = DeviceValue(bufs["snis_z2"])
+        res["al"] = DeviceValue(bufs["al"])
+        res["logits"] = lazy("logits")
+        res["lpxz1"] = DeviceValue(bufs["lpxz"])
+        res["lpz1z2"] = DeviceValue(bufs["lp12"])
+        res["lpz2"] = DeviceValue(bufs["lpz"])
+        res["lqz1x"] = DeviceValue(bufs["lq1"])
+        res["lqz2z1"] = DeviceValue(bufs["lq2"])
+        self._extras(res, bufs)
+        return res
+
+    def call(self, x, n_samples, beta=1.0, eps=None, eps2=None, seed=None, img_offset=0):
+        """iwae2.IWAE.call (src/iwae2.py:109-167); eps [k,B,d1], eps2 [k,B,d2] inject the noise."""
+        k = int(n_samples)
+        bufs = self._forward(x, None, k, beta, self._WANT, eps, eps2, seed, img_offset)
+        bufs["_img_offset"] = img_offset
+        return self._result(bufs, k, beta)
+
+    __call__ = call
+
+    def train_step(self, x, n_samples, beta, optimizer, objective="vae_elbo", eps=None, eps2=None, seed=None):
+        oid = self._objective_id(objective, self._OBJECTIVES)
+        k = int(n_samples)
+        bufs = self._train(x, None, k, beta, optimizer, oid, eps, eps2, seed)
+        return self._result(bufs, k, beta)
+
+
+class IWAEDReG(IWAE):
+    """tasks/task02.py:27-101: the doubly-reparameterised gradient estimator.  `call` returns the
+    reference's keys (no `al`, no vae variants, plus `inference_loss`); `train_step` takes no objective:
+    encoder gradients come from `inference_loss`, decoder gradients from `-iwae_elbo`."""
+
+    _WANT = ("lpxz", "lpz", "lq1", "log_w", "al", "iwae", "vae", "eq14", "snis_z1", "dreg", "scalars")
+
+    def _result(self, bufs, k, beta) -> Result:
+        s = bufs["scalars"]
+        lazy = self._lazy(bufs, k, beta, ("z1", "logits"))
+        res = Result()
+        res["iwae_elbo"] = DeviceValue(s[2])
+        res["inference_loss"] = DeviceValue(s[4])
+        res["z"] = lazy("z1")
+        res["snis_z"] = DeviceValue(bufs["snis_z1"])
+        res["logits"] = lazy("logits")
+        res["lpxz"] = DeviceValue(bufs["lpxz"])
+        res["lpz"] = DeviceValue(bufs["lpz"])
+        res["lqzx"] = DeviceValue(bufs["lq1"])
+        res["iwae_elbo_per_example"] = DeviceValue(bufs["iwae"])
+        res["log_w"] = DeviceValue(bufs["log_w"])
+        return res
+
+    def train_step(self, x, n_samples, beta, optimizer, eps=None, seed=None):
+        k = int(n_samples)
+        bufs = self._train(x, None, k, beta, optimizer, _abi.OBJ["dreg"], eps, None, seed)
+        return self._result(bufs, k, beta)
+
+
+class CIWAE(IWAE):
+    """tasks/task04.py:101-188: label-conditioned IWAE with a learned prior p(z|y); `call(x, y, n_samples,
+    beta)`.  `learned_prior=False` gives tasks/task05.py (N(0,1) prior)."""
+
+    KIND = _abi.KIND_CIWAE
+    TERM_KEYS = ("lpxzy", "lpzy", "lqzxy")
+
+    def __init__(self, n_hidden, n_latent, learned_prior: bool = True, **kwargs):
+        self.KIND = _abi.KIND_CIWAE if learned_prior else _abi.KIND_CIWAE_STD
+        self._learned_prior = learned_prior
+        super().__init__(n_hidden, n_latent, **kwargs)
+
+    def _make_config(self, n_hidden, n_latent, n_x, n_cond):
+        return Config(self.KIND, int(n_x), int(n_cond or 10), int(n_hidden), 0, int(n_latent), 0)
+
+    def _param_names(self):
+        names = _block_names("encoder.encode_x_to_z") + _mlp3_names("decoder.decode_z_to_x")
+        if self._learned_prior:
+            names += _block_names("conditional_prior_network")
+        return names
+
+    def _build_submodels(self):
+        super()._build_submodels()
+        if self._learned_prior:
+            self.conditional_prior_network = _SubModel(self, "conditional_prior_network")
+
+    def call(self, x, y, n_samples, beta=1.0, eps=None, seed=None, img_offset=0):
+        k = int(n_samples)
+        bufs = self._forward(x, y, k, beta, self._WANT, eps, None, seed, img_offset)
+        bufs["_img_offset"] = img_offset
+        return self._result(bufs, k, beta)
+
+    __call__ = call
+
+    def val_step(self, x, y, n_samples, beta):
+        return self.call(x, y, n_samples, beta)
+
+    def train_step(self, x, y, n_samples, beta, optimizer, objective="vae_elbo", eps=None, seed=None):
+        oid = self._objective_id(objective, self._OBJECTIVES)
+        k = int(n_samples)
+        bufs = self._train(x, y, k, beta, optimizer, oid, eps, None, seed)
+        return self._result(bufs, k, beta)
+
+
+class BasicBlock:
+    """iwae1.BasicBlock(n_hidden, n_latent) as tasks/task04.py:108 constructs it directly.  In this
+    implementation blocks live inside a model's flat parameter buffer, so a free-standing block is only a
+    shape record; CIWAE creates its prior network itself."""
+
+    def __init__(self, n_hidden, n_latent, **kwargs):
+        self.n_hidden, self.n_latent = int(n_hidden), int(n_latent)

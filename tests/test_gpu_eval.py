@@ -1,0 +1,141 @@
+"""GPU: the k-sample test log-likelihood estimator (main.py:170-184) - fp32 parity mode and the fused
+tcgen05 kernel - against the oracle fed with the SAME Philox noise (oracle.philox_normal restates the
+device generator), plus size-independent properties at BASELINE.json's k=5000."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_case
+from test_gpu_parity import build, rel, RTOL, TC_RTOL
+
+pytestmark = pytest.mark.gpu
+SEED = 20251018
+
+
+def oracle_llh(oracle, kind, case, k, img_offset=0, dtype=torch.float64):
+    p = oracle.to_torch(case["params"], dtype)
+    x = torch.tensor(case["x"], dtype=dtype)
+    B = x.shape[0]
+    if kind == "iwae2":
+        d1, d2 = case["d"]
+        e1 = torch.tensor(oracle.philox_normal(SEED, 1, img_offset, B, k, d1), dtype=dtype)
+        e2 = torch.tensor(oracle.philox_normal(SEED, 2, img_offset, B, k, d2), dtype=dtype)
+        r = oracle.iwae2_call(p, x, k, 1.0, e1, e2)
+    elif kind == "iwae1":
+        e1 = torch.tensor(oracle.philox_normal(SEED, 1, img_offset, B, k, case["d"]), dtype=dtype)
+        r = oracle.iwae1_call(p, x, k, 1.0, e1)
+    else:
+        e1 = torch.tensor(oracle.philox_normal(SEED, 1, img_offset, B, k, case["d"]), dtype=dtype)
+        r = oracle.ciwae_call(p, x, case["y"], k, 1.0, e1, learned_prior=(kind == "ciwae"))
+    return r["iwae_elbo_per_example"].numpy()
+
+
+def _case(oracle, kind, B, scale=1.0, seed=51):
+    h, d = ([200, 100], [100, 50]) if kind == "iwae2" else (200, 100)
+    case = make_case(oracle, kind, h, d, B, 1, seed=seed, scale=scale, n_cond=10 if kind.startswith("ciwae") else 0)
+    case["d"] = d
+    case["h"] = h
+    return case
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (112, 112), (96, 208), (256, 64), (48, 100), (112, 7)])
+def test_umma_descriptor_selftest(N, K):
+    """One tcgen05.mma chain through the exact operand staging of the fused kernel."""
+    from iwae_b200._abi import lib, check
+    rs = np.random.RandomState(N * 1000 + K)
+    A = rs.randn(128, K).astype(np.float32)
+    Bm = rs.randn(N, K).astype(np.float32)
+    tA, tB = torch.tensor(A, device="cuda"), torch.tensor(Bm, device="cuda")
+    D = torch.zeros(128, N, device="cuda")
+    check(lib.iwae_umma_selftest(C.c_void_p(tA.data_ptr()), C.c_void_p(tB.data_ptr()), N, K, 0,
+                                 C.c_void_p(D.data_ptr()), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = A.astype(np.float16).astype(np.float64) @ Bm.astype(np.float16).astype(np.float64).T
+    assert np.max(np.abs(D.cpu().numpy() - ref)) < 2e-3 * np.sqrt(K)
+
+
+@pytest.mark.parametrize("kind", ["iwae1", "iwae2", "ciwae", "ciwae_std"])
+def test_llh_fp32_matches_oracle(oracle, kind):
+    N, k = 3, 300
+    case = _case(oracle, kind, N)
+    m = build(kind, case, case)
+    y = case["y"] if kind.startswith("ciwae") else None
+    per, total = m.llh(case["x"], k, y=y, precision="fp32", seed=SEED, img_offset=7)
+    ref = oracle_llh(oracle, kind, case, k, img_offset=7)
+    assert rel(per.cpu().numpy(), ref) < RTOL
+    assert abs(float(total) - ref.sum()) < RTOL * abs(ref.sum())
+
+
+@pytest.mark.parametrize("precision", ["tc_f16", "tc_f16_fast"])
+@pytest.mark.parametrize("kind,scale", [("iwae2", 1.0), ("iwae2", 0.5), ("iwae1", 1.0), ("iwae1", 0.5), ("ciwae", 1.0),
+                                        ("ciwae_std", 1.0)])
+def test_llh_tensor_core_matches_oracle(oracle, kind, scale, precision):
+    """Fused tcgen05 kernel (fp16 operands, fp32 accumulate).  Stated tolerance: TC_RTOL relative on
+    the per-example LLH."""
+    N, k = 5, 300       # 3 tiles of 100 rows per image: exercises ragged tiles and the cross-tile combine
+    case = _case(oracle, kind, N, scale=scale)
+    m = build(kind, case, case)
+    y = case["y"] if kind.startswith("ciwae") else None
+    per, total = m.llh(case["x"], k, y=y, precision=precision, seed=SEED, img_offset=3)
+    torch.cuda.synchronize()
+    ref = oracle_llh(oracle, kind, case, k, img_offset=3)
+    err = rel(per.cpu().numpy(), ref)
+    print(f"\n[tc parity] {kind} scale={scale} {precision}: max rel err {err:.3e}")
+    assert err < TC_RTOL
+    assert abs(float(total) - float(per.double().sum())) < 1e-6 * abs(float(total))
+
+
+@pytest.mark.parametrize("kind,d", [("iwae1", 2), ("iwae1", 50), ("iwae2", [4, 2]), ("iwae2", [2, 2])])
+@pytest.mark.parametrize("k", [1, 5, 129])
+def test_llh_tensor_core_small_latents(oracle, kind, d, k):
+    h = [200, 100] if kind == "iwae2" else 200
+    case = make_case(oracle, kind, h, d, 3, 1, seed=61)
+    case["d"], case["h"] = d, h
+    m = build(kind, case, case)
+    per, _ = m.llh(case["x"], k, precision="tc_f16", seed=SEED)
+    ref = oracle_llh(oracle, kind, case, k)
+    assert rel(per.cpu().numpy(), ref) < TC_RTOL
+
+
+def test_llh_edge_cases(oracle):
+    case = _case(oracle, "iwae2", 4)
+    m = build("iwae2", case, case)
+    for prec in ("fp32", "tc_f16_fast"):
+        per, total = m.llh(case["x"][:0], 50, precision=prec, seed=SEED)
+        assert per.numel() == 0 and float(total) == 0.0
+    # host-buffer entry point == device entry point
+    per_d, tot_d = m.llh(case["x"], 200, precision="tc_f16_fast", seed=SEED)
+    per_h, tot_h = m.llh_host(case["x"], 200, precision="tc_f16_fast", seed=SEED)
+    assert np.array_equal(per_d.cpu().numpy(), per_h) and float(tot_d) == tot_h
+
+
+def test_llh_sharding_invariance(oracle):
+    """Noise is keyed on the global image index: evaluating shards with img_offset reproduces the
+    single-pass per-example values bit for bit (what makes the 1/2/4/8-GPU runs identical)."""
+    case = _case(oracle, "iwae2", 12)
+    m = build("iwae2", case, case)
+    for prec in ("fp32", "tc_f16_fast"):
+        whole, tot = m.llh(case["x"], 150, precision=prec, seed=SEED)
+        parts = [m.llh(case["x"][a:b], 150, precision=prec, seed=SEED, img_offset=a)[0] for a, b in ((0, 5), (5, 6), (6, 12))]
+        assert torch.equal(whole, torch.cat(parts)), prec
+
+
+def test_llh_full_size_properties(oracle):
+    """BASELINE.json k=5000 on a bounded set of images: the tensor-core fast path agrees with the fp32
+    FFMA path per example (same Philox noise), LLH rises with k (Jensen), and the fp64 sum is the sum
+    of the per-example values."""
+    case = _case(oracle, "iwae2", 24, scale=0.5)
+    m = build("iwae2", case, case)
+    per_tc, tot = m.llh(case["x"], 5000, precision="tc_f16_fast", seed=SEED)
+    per_32, _ = m.llh(case["x"], 5000, precision="fp32", seed=SEED)
+    err = rel(per_tc.cpu().numpy(), per_32.cpu().numpy())
+    print(f"\n[k=5000] tc_f16_fast vs fp32: max rel err {err:.3e}")
+    assert err < TC_RTOL
+    assert abs(float(tot) - float(per_tc.double().sum())) < 1e-6 * abs(float(tot))
+    per_small, _ = m.llh(case["x"], 50, precision="tc_f16_fast", seed=SEED)
+    assert float(per_tc.mean()) > float(per_small.mean())
+    # one image against the fp64 oracle at the full k
+    ref = oracle_llh(oracle, "iwae2", {**case, "x": case["x"][:2]}, 5000)
+    assert rel(per_tc[:2].cpu().numpy(), ref) < TC_RTOL
