@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   uint32_t ncols = 32;
   while ((int)ncols < N) ncols <<= 1;
   if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  __syncwarp();
   if (warp == 0) { tmem_alloc(&tmem_base_s, ncols); tmem_relinquish(); }
   fence_proxy_async();
   tc_fence_before();
