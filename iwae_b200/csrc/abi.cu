@@ -364,7 +364,7 @@ static int grow_dev(float** p, size_t* cap, size_t bytes) {
 extern "C" int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
                              uint64_t seed, int64_t img_offset, int32_t precision, float* out_per_example,
                              double* out_sum, void* stream) {
-  IWAE_REQUIRE(ctx && params && x, "iwae_llh_eval: null argument");
+  IWAE_REQUIRE(ctx && params && (x || N == 0), "iwae_llh_eval: null argument");
   IWAE_REQUIRE(N >= 0 && k > 0, "iwae_llh_eval: bad N=%lld k=%d", (long long)N, k);
   cudaStream_t st = (cudaStream_t)stream;
   const ModelP& m = ctx->model;
@@ -410,7 +410,7 @@ extern "C" int iwae_llh_kernel_ms(iwae_ctx* ctx, float* ms) {
 extern "C" int iwae_llh_eval_host(iwae_ctx* ctx, const float* params, const float* x_host, const float* y_host,
                                   int64_t N, int32_t k, uint64_t seed, int64_t img_offset, int32_t precision,
                                   float* out_per_example_host, double* out_sum_host, void* stream) {
-  IWAE_REQUIRE(ctx && params && x_host, "iwae_llh_eval_host: null argument");
+  IWAE_REQUIRE(ctx && params && (x_host || N == 0), "iwae_llh_eval_host: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int nx = ctx->model.cfg.n_x;
   // persistent device staging (not the arena: iwae_llh_eval resets it)
