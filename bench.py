@@ -88,7 +88,7 @@ def cpu_llh_pass(params32, X, k, layers, torch, oracle, gen):
 def cpu_setup(args):
     import torch
     from oracle import iwae_oracle as oracle
-    P, X = synthetic(max(args.ref_images, 64))
+    P, X = synthetic(max(args.ref_images, 1000))
     rs = np.random.RandomState(123)
     if args.layers == 2:
         shapes = oracle.param_shapes("iwae2", [200, 100], [100, 50])
@@ -107,7 +107,7 @@ def cpu_baseline(args):
         t0 = time.perf_counter()
         cpu_llh_pass(p32, X[:2], args.k, args.layers, torch, oracle, gen)
         per_img = (time.perf_counter() - t0) / 2
-        n = int(min(max(args.cpu_seconds / max(per_img, 1e-4), 4), 64))
+        n = int(min(max(args.cpu_seconds / max(per_img, 1e-4), 4), 1000))
         t0 = time.perf_counter()
         cpu_llh_pass(p32, X[:n], args.k, args.layers, torch, oracle, gen)
         dt = time.perf_counter() - t0

@@ -38,12 +38,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the
+// hint (ns) expires, so a waiting role does not burn issue slots of the SM sub-partition it shares
+// with an epilogue warp (ncu on v1: 32 % of all executed instructions were this spin loop).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
@@ -53,16 +56,18 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 // Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+    if (globaltimer_ns() - t0 > 4000000000ull) {
       printf("iwae_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -245,8 +250,8 @@ struct __align__(16) SmemLayout {
   uint8_t bufZ[BUFZ_BYTES];
   uint8_t bufP[BUFP_BYTES];
   uint8_t ring[NSTAGES][SLAB_BYTES];
-  float sgn[NX_MAX];           // 1 - 2x per pixel of the current image
-  float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX];
+  float sgn[NX_MAX];           // 1 - 2x per pixel of the current image (0 for padded columns); 16-byte aligned
+  float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX], ipsd[D_MAX];
   float red[8];
   uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready;
   uint32_t tmem_base;
@@ -282,6 +287,59 @@ __device__ __forceinline__ void store16(uint8_t* buf, int row, int k0, const flo
 __device__ __forceinline__ void store8(uint8_t* buf, int row, int k0, const float (&v)[8]) {
   uint4 a = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
   *reinterpret_cast<uint4*>(buf + (size_t)(k0 >> 3) * (TILE_M * 16) + row * 16) = a;
+}
+
+// ---- math helpers ----
+__device__ __forceinline__ float ex2_approx(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float lg2_approx(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float rcp_approx(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float sin_approx(float v) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float cos_approx(float v) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+#define LN2_F 0.69314718055994530942f
+#define LOG2E_F 1.44269504088896340736f
+
+// Four N(0,1) for dims 4q..4q+3: Philox4x32-10 + Box-Muller (rng.cuh defines the mapping).  FAST uses the
+// MUFU approximations (lg2, sqrt, sin, cos on [-pi,pi)): same uniforms, normals equal to ~1e-6.
+template <bool FAST>
+__device__ __forceinline__ float4 normal4(uint64_t seed, uint32_t stream_id, uint32_t img, uint32_t s, uint32_t q) {
+  if (!FAST) return philox_normal4(seed, stream_id, img, s, q);
+  const uint4 r = philox4x32_10(make_uint4(s, q, img, stream_id), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  float o[4];
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = (float)((rr[2 * h] >> 8) + 1u) * 5.9604644775390625e-8f;
+    const float u2 = (float)(rr[2 * h + 1] >> 8) * 5.9604644775390625e-8f;
+    const float rad = sqrt_approx(-2.0f * LN2_F * lg2_approx(u1));
+    // cos(2 pi u) = -cos(2 pi u - pi), sin likewise: keeps the MUFU argument inside [-pi, pi)
+    const float th = fmaf(u2, 6.283185307179586f, -3.14159265358979f);
+    o[2 * h] = -rad * cos_approx(th);
+    o[2 * h + 1] = -rad * sin_approx(th);
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// TMEM -> registers, 16 columns at a time, software-pipelined: the load of group g+1 is in flight
+// while group g is processed (tcgen05.wait::ld waits for ALL outstanding loads, so the order is
+// wait(g) -> issue(g+1) -> process(g)).  f(regs, g) is called for g = 0, 16, ... < ncols.
+template <class F>
+__device__ __forceinline__ void for_each_16cols(uint32_t taddr, int ncols, F&& f) {
+  uint32_t ra[16], rb[16];
+  tmem_ld16(taddr, ra);
+  tmem_ld_wait();
+  for (int g = 0; g < ncols; g += 32) {
+    const bool has_b = g + 16 < ncols;
+    if (has_b) tmem_ld16(taddr + g + 16, rb);
+    f(ra, g);
+    if (has_b) {
+      tmem_ld_wait();
+      const bool has_a = g + 32 < ncols;
+      if (has_a) tmem_ld16(taddr + g + 32, ra);
+      f(rb, g + 16);
+      if (has_a) tmem_ld_wait();
+    }
+  }
 }
 
 template <bool FAST>
@@ -372,6 +430,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
     uint32_t full_phase[2] = {0, 0};
     uint32_t cc = 0;
     const int d1 = P.d1, nx = P.nx;
+    const int nx_pad = (nx + 15) & ~15;
 
     for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
       const int64_t img = tile / args.tiles_per_img;
@@ -381,31 +440,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
 
       // ---- per-image constants into smem
       epi_bar_sync();
-      for (int j = et; j < nx; j += 128) S.sgn[j] = 1.f - 2.f * __ldg(args.x + img * nx + j);
+      for (int j = et; j < nx_pad; j += 128) S.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
       for (int j = et; j < d1; j += 128) {
         const float sd = __ldg(args.std1 + img * d1 + j);
         S.mu[j] = __ldg(args.mu1 + img * d1 + j); S.sd[j] = sd; S.lsd[j] = logf(sd);
         if (P.learned_prior) {
           const float ps = __ldg(args.pstd + img * d1 + j);
-          S.pmu[j] = __ldg(args.pmu + img * d1 + j); S.psd[j] = ps; S.lpsd[j] = logf(ps);
+          S.pmu[j] = __ldg(args.pmu + img * d1 + j); S.psd[j] = ps; S.lpsd[j] = logf(ps); S.ipsd[j] = 1.f / ps;
         }
       }
       if (et == 0 && P.cond) S.label = (int)(unsigned char)(int)__ldg(args.y + img);
       epi_bar_sync();
 
-      // ---- stage 0: z1 = mu + std*eps (A.2), lq1, lpz; fp16 z1 | onehot(y) | 1 | 0.. into bufZ
+      // Accumulators of the row's log-density terms.  Precise mode adds log-probabilities term by
+      // term in TFP's op order; FAST mode accumulates sums of squares / logs and applies the
+      // constants once (algebraically identical: (z-mu)/sd == eps for a reparameterised sample).
       float lq1 = 0.f, lpz = 0.f, lq2 = 0.f, lp12 = 0.f, lpxz = 0.f;
+      float sum_lsd = 0.f, sum_lpsd = 0.f;
+      if (FAST) {
+        for (int j = lane; j < d1; j += 32) { sum_lsd += S.lsd[j]; if (P.learned_prior) sum_lpsd += S.lpsd[j]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sum_lsd += __shfl_xor_sync(0xffffffffu, sum_lsd, o);
+          sum_lpsd += __shfl_xor_sync(0xffffffffu, sum_lpsd, o);
+        }
+      }
+
+      // ---- stage 0: z1 = mu + std*eps (A.2), lq1, lpz; fp16 z1 | onehot(y) | 1 | 0.. into bufZ
       {
         const uint32_t gimg = (uint32_t)(args.img_offset + img);
         const int one_col = d1 + P.nc;
-        for (int k0 = 0; k0 < P.kz_pad; k0 += 16) {
-          float v[16];
+        for (int k0 = 0; k0 < P.kz_pad; k0 += 8) {
+          float v[8];
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
+          for (int qq = 0; qq < 2; ++qq) {
             const int j0 = k0 + 4 * qq;
             float e[4] = {0.f, 0.f, 0.f, 0.f};
             if (j0 < d1) {
-              const float4 n4 = philox_normal4(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
+              const float4 n4 = normal4<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
               e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
             }
 #pragma unroll
@@ -414,16 +486,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               float val = 0.f;
               if (j < d1) {
                 const float sd = S.sd[j], m = S.mu[j];
-                const float z = e[i] * sd + m;
-                const float t = z / sd - m / sd;                         // TFP op order
-                lq1 += -0.5f * t * t - (LOG2PI_HALF_F + S.lsd[j]);
-                if (!P.two_layer) {
-                  if (P.learned_prior) {
-                    const float ps = S.psd[j];
-                    const float tp = z / ps - S.pmu[j] / ps;
-                    lpz += -0.5f * tp * tp - (LOG2PI_HALF_F + S.lpsd[j]);
-                  } else {
-                    lpz += -0.5f * z * z - LOG2PI_HALF_F;
+                const float z = fmaf(e[i], sd, m);
+                if (FAST) {
+                  lq1 = fmaf(e[i], e[i], lq1);
+                  if (P.learned_prior) { const float tp = (z - S.pmu[j]) * S.ipsd[j]; lpz = fmaf(tp, tp, lpz); }
+                  else if (!P.two_layer) lpz = fmaf(z, z, lpz);
+                } else {
+                  const float t = z / sd - m / sd;                         // TFP op order
+                  lq1 += -0.5f * t * t - (LOG2PI_HALF_F + S.lsd[j]);
+                  if (!P.two_layer) {
+                    if (P.learned_prior) {
+                      const float ps = S.psd[j];
+                      const float tp = z / ps - S.pmu[j] / ps;
+                      lpz += -0.5f * tp * tp - (LOG2PI_HALF_F + S.lpsd[j]);
+                    } else {
+                      lpz += -0.5f * z * z - LOG2PI_HALF_F;
+                    }
                   }
                 }
                 val = z;
@@ -435,7 +513,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               v[4 * qq + i] = val;
             }
           }
-          store16(S.bufZ, row, k0, v);
+          store8(S.bufZ, row, k0, v);
+        }
+        if (FAST) {
+          lq1 = -0.5f * lq1 - (sum_lsd + (float)d1 * LOG2PI_HALF_F);
+          if (P.two_layer) lpz = 0.f;     // the top-layer prior term is accumulated by the GSAMPLE layer
+          else lpz = -0.5f * lpz - ((P.learned_prior ? sum_lpsd : 0.f) + (float)d1 * LOG2PI_HALF_F);
         }
       }
       fence_proxy_async();
@@ -443,6 +526,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       if (lane == 0) mbar_arrive(&S.act_ready);
 
       // ---- layers
+      float bern_s = 0.f, bern_a = 0.f, bern_lg = 0.f;     // FAST Bernoulli accumulators (log2 units)
       for (int l = 0; l < P.nlayers; ++l) {
         const Layer& Ly = P.L[l];
         uint8_t* dst = Ly.dst ? S.bufP : S.bufZ;
@@ -465,24 +549,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
 
           if (Ly.kind == EPI_TANH) {
-            for (int g = 0; g < cn; g += 16) {
-              uint32_t r[16];
-              tmem_ld16(tbase + g, r);
-              tmem_ld_wait();
+            // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
+            // bias 30 (tanh(30) == 1.0f): no per-element special cases
+            for_each_16cols(tbase, cn, [&](const uint32_t (&r)[16], int g) {
               float v[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int u = off + g + i;
-                float t = act_tanh<FAST>(__uint_as_float(r[i]));
-                if (u >= Ly.n_real) t = (u == Ly.n_real) ? 1.f : 0.f;      // constant-1 bias column, zero pad
-                v[i] = t;
-              }
-              if (off + g < Ly.next_kpad) store16(dst, row, off + g, v);
-            }
+              for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
+              store16(dst, row, off + g, v);
+            });
           } else if (Ly.kind == EPI_GSAMPLE) {
-            // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8].
+            // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8]
+            // (FAST: the log-std head is pre-scaled by log2(e) at pack time).
             // z2 = mu2 + std2*eps2 (iwae2.py:65); one 16-byte A-operand row segment per group.
             const uint32_t gimg = (uint32_t)(args.img_offset + img);
+            float e2sum = 0.f, z2sum = 0.f, lgsum = 0.f;
             for (int g8 = 0; g8 < Ly.next_kpad; g8 += 8) {
               float v[8];
               if (g8 < cnt) {
@@ -491,7 +571,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                 tmem_ld_wait();
 #pragma unroll
                 for (int qq = 0; qq < 2; ++qq) {
-                  const float4 n4 = philox_normal4(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2) + qq);
+                  const float4 n4 = normal4<FAST>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2) + qq);
                   const float e[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
@@ -499,12 +579,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                     float val = 0.f;
                     if (j < cnt) {
                       const float m = __uint_as_float(r[4 * qq + i]);
-                      const float sd = act_exp<FAST>(__uint_as_float(r[8 + 4 * qq + i])) + 1e-6f;
-                      const float z = e[i] * sd + m;
-                      const float t = z / sd - m / sd;
-                      lq2 += -0.5f * t * t - (LOG2PI_HALF_F + act_log<FAST>(sd));      // iwae2.py:118
-                      lpz += -0.5f * z * z - LOG2PI_HALF_F;                             // iwae2.py:116
-                      val = z;
+                      const float a = __uint_as_float(r[8 + 4 * qq + i]);
+                      if (FAST) {
+                        const float sd = ex2_approx(a) + 1e-6f;
+                        const float z = fmaf(e[i], sd, m);
+                        e2sum = fmaf(e[i], e[i], e2sum);
+                        z2sum = fmaf(z, z, z2sum);
+                        lgsum += lg2_approx(sd);
+                        val = z;
+                      } else {
+                        const float sd = expf(a) + 1e-6f;
+                        const float z = e[i] * sd + m;
+                        const float t = z / sd - m / sd;
+                        lq2 += -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));               // iwae2.py:118
+                        lpz += -0.5f * z * z - LOG2PI_HALF_F;                             // iwae2.py:116
+                        val = z;
+                      }
                     } else if (j == cnt) {
                       val = 1.f;
                     }
@@ -517,8 +607,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               }
               store8(dst, row, g8, v);
             }
+            if (FAST) {
+              lq2 += -0.5f * e2sum - LN2_F * lgsum - (float)cnt * LOG2PI_HALF_F;
+              lpz += -0.5f * z2sum - (float)cnt * LOG2PI_HALF_F;
+            }
           } else if (Ly.kind == EPI_GLOGP) {
             // same column layout; log p(z1|z2) over dims off..off+cnt (iwae2.py:120), z1 re-read from bufZ
+            float t2sum = 0.f, lssum = 0.f;
             for (int g8 = 0; g8 < cnt; g8 += 8) {
               uint32_t r[16];
               tmem_ld16(tbase + 2 * g8, r);
@@ -531,29 +626,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                   const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
                   const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
                   const float m = __uint_as_float(r[i]);
-                  const float sd = act_exp<FAST>(__uint_as_float(r[8 + i])) + 1e-6f;
-                  const float t = z / sd - m / sd;
-                  lp12 += -0.5f * t * t - (LOG2PI_HALF_F + act_log<FAST>(sd));          // iwae2.py:120
+                  const float a = __uint_as_float(r[8 + i]);
+                  if (FAST) {
+                    // sd = e^a + 1e-6 with a' = a*log2(e) in TMEM.  One MUFU: inv = 2^-a' = e^-a, then
+                    // 1/sd = inv*(1 - 1e-6*inv) and log sd = a + 1e-6*inv to first order in 1e-6*inv
+                    // (error <= (1e-6*inv)^2); exact path when that is not small (sd < ~1e-3).
+                    const float inv = ex2_approx(-a);
+                    float isd, ls;
+                    if (inv < 1024.f) {
+                      isd = fmaf(-1e-6f * inv, inv, inv);
+                      ls = fmaf(a, LN2_F, 1e-6f * inv);
+                    } else {
+                      const float sd = ex2_approx(a) + 1e-6f;
+                      isd = rcp_approx(sd);
+                      ls = LN2_F * lg2_approx(sd);
+                    }
+                    const float t = (z - m) * isd;
+                    t2sum = fmaf(t, t, t2sum);
+                    lssum += ls;
+                  } else {
+                    const float sd = expf(a) + 1e-6f;
+                    const float t = z / sd - m / sd;
+                    lp12 += -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                   // iwae2.py:120
+                  }
                 }
               }
             }
-          } else {   // EPI_BERN: log p(x|z) = -softplus((1-2x) l), product-of-(1+e^-|s|) batching of the logs
-            float relu_sum = 0.f, prod = 1.f;
-            for (int g = 0; g < cn; g += 16) {
-              uint32_t r[16];
-              tmem_ld16(tbase + g, r);
-              tmem_ld_wait();
+            if (FAST) lp12 += -0.5f * t2sum - lssum - (float)cnt * LOG2PI_HALF_F;
+          } else {
+            // EPI_BERN: log p(x|z) = -sum_j softplus(s_j), s_j = (1-2x_j) l_j   (A.3 with x in {0,1})
+            //   softplus(s) = max(s,0) + log(1 + e^-|s|),  max(s,0) = (s + |l|)/2,  |s| = |l|
+            // FAST: the accumulators hold l' = l*log2(e) (folded into W3/b3 at pack time), so the
+            // exponential is a bare ex2 of -|l'| and the sign only enters through one FFMA; the logs
+            // are batched: one lg2 per 28 factors (1 + 2^-|l'|) in (1, 2].
+            if (FAST) {
+              float p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
+              for_each_16cols(tbase, cn, [&](const uint32_t (&r)[16], int g) {
+                const float4* sg4 = reinterpret_cast<const float4*>(&S.sgn[off + g]);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int pix = off + g + i;
-                if (g + i < cnt) {
-                  const float sv = __uint_as_float(r[i]) * S.sgn[pix];
-                  relu_sum += fmaxf(sv, 0.f);
-                  prod = fmaf(prod, act_exp<FAST>(-fabsf(sv)), prod);
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const float4 sg = sg4[i4];
+                  const float l0 = __uint_as_float(r[4 * i4]), l1 = __uint_as_float(r[4 * i4 + 1]);
+                  const float l2 = __uint_as_float(r[4 * i4 + 2]), l3 = __uint_as_float(r[4 * i4 + 3]);
+                  s0 = fmaf(sg.x, l0, s0); s1 = fmaf(sg.y, l1, s1); s0 = fmaf(sg.z, l2, s0); s1 = fmaf(sg.w, l3, s1);
+                  a0 += fabsf(l0); a1 += fabsf(l1); a0 += fabsf(l2); a1 += fabsf(l3);
+                  p0 = fmaf(p0, ex2_approx(-fabsf(l0)), p0); p1 = fmaf(p1, ex2_approx(-fabsf(l1)), p1);
+                  p2 = fmaf(p2, ex2_approx(-fabsf(l2)), p2); p3 = fmaf(p3, ex2_approx(-fabsf(l3)), p3);
                 }
-              }
+              });
+              bern_s += s0 + s1; bern_a += a0 + a1;
+              bern_lg += lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
+            } else {
+              float acc = 0.f;
+              for_each_16cols(tbase, cn, [&](const uint32_t (&r)[16], int g) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float lgt = __uint_as_float(r[i]);
+                  const float sv = lgt * S.sgn[off + g + i];
+                  acc += fmaxf(sv, 0.f) + log1pf(expf(-fabsf(lgt)));
+                }
+              });
+              lpxz -= acc;
             }
-            lpxz -= relu_sum + act_log<FAST>(prod);
           }
           tc_fence_before();
           __syncwarp();
@@ -566,6 +700,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
           if (lane == 0) mbar_arrive(&S.act_ready);
         }
       }
+      // padded pixel columns (zero weights, sgn 0) each contributed softplus(0) = ln 2
+      if (FAST) lpxz = -LN2_F * (0.5f * (bern_s + bern_a) + bern_lg) + (float)(nx_pad - nx) * LN2_F;
+      else lpxz += (float)(nx_pad - nx) * LN2_F;
 
       // ---- log-weight of this row and the tile's (max, sum exp) partial
       float lw = P.two_layer ? (lpxz + lp12 + lpz - lq1 - lq2) : (lpxz + (lpz - lq1));
@@ -615,6 +752,8 @@ struct PackLayer {
   const float *W2, *b2;     // second head (log-std) for Gaussian layers, else null
   int k_real, k_pad, ldw;
   int nchunks, gauss;
+  int one_unit;             // TANH layers: output unit that must evaluate to 1 (the next layer's bias input), else -1
+  float scale, scale2;      // multiplies (W,b) / (W2,b2): log2(e) where the FAST epilogue works in base 2
   int chunk_n[MAX_CHUNKS], chunk_cnt[MAX_CHUNKS], chunk_off[MAX_CHUNKS];
   int64_t chunk_base[MAX_CHUNKS];   // half offset of the chunk's first slab inside the packed buffer
 };
@@ -638,8 +777,11 @@ __global__ void pack_layer_kernel(PackLayer pl, __half* __restrict__ out) {
         if (dl < cnt) { col = off + dl; if (n & 8) { W = pl.W2; b = pl.b2; } }
       }
       if (col >= 0) {
-        if (k < pl.k_real) v = W[(int64_t)k * pl.ldw + col];
-        else if (k == pl.k_real) v = b[col];
+        const float sc = (W == pl.W2 && pl.gauss) ? pl.scale2 : pl.scale;
+        if (k < pl.k_real) v = sc * W[(int64_t)k * pl.ldw + col];
+        else if (k == pl.k_real) v = sc * b[col];
+      } else if (!pl.gauss && off + n == pl.one_unit && k == pl.k_real) {
+        v = 30.f;           // tanh(30) == 1.0f: the constant-1 activation that carries the next layer's bias
       }
       out[pos] = __float2half_rn(v);
     }
@@ -674,7 +816,7 @@ static void split_chunks(int n_pad, tc::Layer& L) {
   }
 }
 
-static int build_program(const ModelP& m, TcPack& tp, const float* P) {
+static int build_program(const ModelP& m, TcPack& tp, const float* P, bool fast) {
   using namespace tc;
   const iwae_config& c = m.cfg;
   Program& pr = tp.prog;
@@ -695,6 +837,7 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P) {
     split_chunks(L.next_kpad, L);
     for (int i = 0; i < L.nchunks; ++i) L.chunk_cnt[i] = std::max(0, std::min(L.chunk_n[i], D.n_out - L.chunk_off[i]));
     K.W = P + D.w; K.b = P + D.b; K.k_real = D.n_in; K.k_pad = k_pad; K.ldw = D.n_out; K.gauss = 0;
+    K.one_unit = D.n_out; K.scale = 1.f; K.scale2 = 1.f;
   };
   auto gauss_layer = [&](const BlockP& B, int kind, int src, int dst, int k_pad, int next_kpad, int per_chunk) {
     Layer& L = pr.L[nl]; PackLayer& K = tp.pl[nl]; ++nl;
@@ -708,6 +851,7 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P) {
     }
     K.W = P + B.lmu.w; K.b = P + B.lmu.b; K.W2 = P + B.lstd.w; K.b2 = P + B.lstd.b;
     K.k_real = B.lmu.n_in; K.k_pad = k_pad; K.ldw = d; K.gauss = 1;
+    K.one_unit = -1; K.scale = 1.f; K.scale2 = fast ? 1.44269504088896340736f : 1.f;
   };
   if (m.two_layer()) {
     IWAE_REQUIRE(c.h2 + 1 <= KP_MAX && c.d2 <= 56, "tensor-core path: needs h2 <= %d and d2 <= 56", KP_MAX - 1);
@@ -730,6 +874,7 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P) {
     for (int i = 0; i < L.nchunks; ++i) L.chunk_cnt[i] = std::max(0, std::min(L.chunk_n[i], c.n_x - L.chunk_off[i]));
     IWAE_REQUIRE(L.nchunks <= MAX_CHUNKS, "tensor-core path: n_x too large");
     K.W = P + m.dec.d2.w; K.b = P + m.dec.d2.b; K.k_real = c.h1; K.k_pad = kh1; K.ldw = c.n_x; K.gauss = 0;
+    K.one_unit = -1; K.scale = fast ? 1.44269504088896340736f : 1.f; K.scale2 = 1.f;
   }
   pr.nlayers = nl;
   // synchronisation flags: a layer waits for act_ready iff its input was produced by the previous
@@ -755,10 +900,10 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P) {
   return 0;
 }
 
-int tc_pack_weights(iwae_ctx* ctx, const float* params, cudaStream_t st) {
+int tc_pack_weights(iwae_ctx* ctx, const float* params, bool fast, cudaStream_t st) {
   if (!ctx->tc) ctx->tc = new TcPack();
   TcPack& tp = *ctx->tc;
-  IWAE_TRY(build_program(ctx->model, tp, params));
+  IWAE_TRY(build_program(ctx->model, tp, params, fast));
   if (!tp.wpack) CUDA_TRY(cudaMalloc((void**)&tp.wpack, tp.wpack_bytes));
   for (int l = 0; l < tp.prog.nlayers; ++l) {
     tc::pack_layer_kernel<<<64, 256, 0, st>>>(tp.pl[l], reinterpret_cast<__half*>(tp.wpack));
@@ -781,7 +926,7 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   const ModelP& m = ctx->model;
   const iwae_config& c = m.cfg;
   IWAE_REQUIRE(!m.cond() || y, "tensor-core path: CIWAE needs labels");
-  IWAE_TRY(tc_pack_weights(ctx, params, st));
+  IWAE_TRY(tc_pack_weights(ctx, params, fast != 0, st));
   TcPack& tp = *ctx->tc;
   Arena& ar = ctx->arena;
 
