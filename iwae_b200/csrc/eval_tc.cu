@@ -208,7 +208,8 @@ constexpr int BUFZ_BYTES = TILE_M * KZ_MAX * 2;        // 28672
 constexpr int BUFP_BYTES = TILE_M * KP_MAX * 2;        // 53248
 constexpr int NX_MAX = 784;
 constexpr int D_MAX = 104;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_THREADS = 256;                  // 8 epilogue warps
+constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;     // + producer warp + MMA warp
 constexpr int TMEM_COLS = 256;
 
 enum { EPI_TANH = 0, EPI_GSAMPLE = 1, EPI_GLOGP = 2, EPI_BERN = 3 };
@@ -253,6 +254,7 @@ struct __align__(16) SmemLayout {
   float sgn[NX_MAX];           // 1 - 2x per pixel of the current image (0 for padded columns); 16-byte aligned
   float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX], ipsd[D_MAX];
   float red[8];
+  float lwpart[TILE_M];        // partial log-weights of the second column half of each row
   uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready;
   uint32_t tmem_base;
   int label;
@@ -263,7 +265,7 @@ static_assert(2 * (sizeof(SmemLayout) + 128 + 1024) <= 228 * 1024, "fused eval k
 
 #define LOG2PI_HALF_F 0.91893853320467274178f
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <bool FAST>
 __device__ __forceinline__ float act_tanh(float v) {
@@ -320,23 +322,25 @@ __device__ __forceinline__ float4 normal4(uint64_t seed, uint32_t stream_id, uin
   return make_float4(o[0], o[1], o[2], o[3]);
 }
 
-// TMEM -> registers, 16 columns at a time, software-pipelined: the load of group g+1 is in flight
-// while group g is processed (tcgen05.wait::ld waits for ALL outstanding loads, so the order is
-// wait(g) -> issue(g+1) -> process(g)).  f(regs, g) is called for g = 0, 16, ... < ncols.
+// TMEM -> registers, 16 columns at a time, software-pipelined: the load of this warp's next group is
+// in flight while the current one is processed (tcgen05.wait::ld waits for ALL outstanding loads, so
+// the order is wait(g) -> issue(next) -> process(g)).
 template <class F>
-__device__ __forceinline__ void for_each_16cols(uint32_t taddr, int ncols, F&& f) {
+__device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int ncols, F&& f) {
+  // this warp's groups: g_first, g_first+32, ... (the partner warp of the lane quarter takes the others)
+  if (g_first >= ncols) return;
   uint32_t ra[16], rb[16];
-  tmem_ld16(taddr, ra);
+  tmem_ld16(taddr + g_first, ra);
   tmem_ld_wait();
-  for (int g = 0; g < ncols; g += 32) {
-    const bool has_b = g + 16 < ncols;
-    if (has_b) tmem_ld16(taddr + g + 16, rb);
+  for (int g = g_first; g < ncols; g += 64) {
+    const bool has_b = g + 32 < ncols;
+    if (has_b) tmem_ld16(taddr + g + 32, rb);
     f(ra, g);
     if (has_b) {
       tmem_ld_wait();
-      const bool has_a = g + 32 < ncols;
-      if (has_a) tmem_ld16(taddr + g + 32, ra);
-      f(rb, g + 16);
+      const bool has_a = g + 64 < ncols;
+      if (has_a) tmem_ld16(taddr + g + 64, ra);
+      f(rb, g + 32);
       if (has_a) tmem_ld_wait();
     }
   }
@@ -351,8 +355,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], 4); }
-    mbar_init(&S.act_ready, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], 8); }
+    mbar_init(&S.act_ready, 8);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&S.tmem_base, TMEM_COLS); tmem_relinquish(); }
@@ -422,10 +426,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       }
     }
   } else {
-    // ===================== epilogue warps (one row per thread) =====================
+    // ===================== epilogue warps =====================
+    // Eight warps: warps e and e+4 share one TMEM lane quarter (one row per lane) and split the
+    // COLUMNS of every accumulator chunk between them (alternating 16-column groups), so 16 epilogue
+    // warps per SM (two CTAs) hide each other's MUFU / TMEM-load latency.  Every log-density term is
+    // a sum over columns, so each thread keeps one partial log-weight; the two halves of a row are
+    // added through shared memory at the end of the tile.
+    const int e_warp = warp - 2;             // 0..7
+    const int half = e_warp >> 2;            // which half of the column groups this warp takes
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int et = (warp - 2) * 32 + lane;   // 0..127 among epilogue threads
+    const int et = e_warp * 32 + lane;       // 0..255 among epilogue threads
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t full_phase[2] = {0, 0};
     uint32_t cc = 0;
@@ -440,8 +451,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
 
       // ---- per-image constants into smem
       epi_bar_sync();
-      for (int j = et; j < nx_pad; j += 128) S.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
-      for (int j = et; j < d1; j += 128) {
+      for (int j = et; j < nx_pad; j += NUM_EPI_THREADS)
+        S.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
+      for (int j = et; j < d1; j += NUM_EPI_THREADS) {
         const float sd = __ldg(args.std1 + img * d1 + j);
         S.mu[j] = __ldg(args.mu1 + img * d1 + j); S.sd[j] = sd; S.lsd[j] = logf(sd);
         if (P.learned_prior) {
@@ -452,25 +464,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       if (et == 0 && P.cond) S.label = (int)(unsigned char)(int)__ldg(args.y + img);
       epi_bar_sync();
 
-      // Accumulators of the row's log-density terms.  Precise mode adds log-probabilities term by
-      // term in TFP's op order; FAST mode accumulates sums of squares / logs and applies the
-      // constants once (algebraically identical: (z-mu)/sd == eps for a reparameterised sample).
-      float lq1 = 0.f, lpz = 0.f, lq2 = 0.f, lp12 = 0.f, lpxz = 0.f;
-      float sum_lsd = 0.f, sum_lpsd = 0.f;
-      if (FAST) {
-        for (int j = lane; j < d1; j += 32) { sum_lsd += S.lsd[j]; if (P.learned_prior) sum_lpsd += S.lpsd[j]; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          sum_lsd += __shfl_xor_sync(0xffffffffu, sum_lsd, o);
-          sum_lpsd += __shfl_xor_sync(0xffffffffu, sum_lpsd, o);
-        }
-      }
+      // This thread's partial log-weight: log_w = lpxz + lp(prior terms) - lq(terms), all sums over
+      // columns.  Precise mode adds log-probabilities term by term in TFP's op order; FAST mode
+      // accumulates sums of squares / logs and applies the constants once (algebraically identical:
+      // (z-mu)/sd == eps for a reparameterised sample).
+      float lw = 0.f;
 
       // ---- stage 0: z1 = mu + std*eps (A.2), lq1, lpz; fp16 z1 | onehot(y) | 1 | 0.. into bufZ
       {
         const uint32_t gimg = (uint32_t)(args.img_offset + img);
         const int one_col = d1 + P.nc;
-        for (int k0 = 0; k0 < P.kz_pad; k0 += 8) {
+        float e1sum = 0.f, z1sum = 0.f;
+        for (int k0 = 8 * half; k0 < P.kz_pad; k0 += 16) {
           float v[8];
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {
@@ -488,19 +493,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                 const float sd = S.sd[j], m = S.mu[j];
                 const float z = fmaf(e[i], sd, m);
                 if (FAST) {
-                  lq1 = fmaf(e[i], e[i], lq1);
-                  if (P.learned_prior) { const float tp = (z - S.pmu[j]) * S.ipsd[j]; lpz = fmaf(tp, tp, lpz); }
-                  else if (!P.two_layer) lpz = fmaf(z, z, lpz);
+                  e1sum = fmaf(e[i], e[i], e1sum);
+                  if (P.learned_prior) { const float tp = (z - S.pmu[j]) * S.ipsd[j]; z1sum = fmaf(tp, tp, z1sum); }
+                  else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
                 } else {
                   const float t = z / sd - m / sd;                         // TFP op order
-                  lq1 += -0.5f * t * t - (LOG2PI_HALF_F + S.lsd[j]);
+                  lw -= -0.5f * t * t - (LOG2PI_HALF_F + S.lsd[j]);        // - lq(z1|x)
                   if (!P.two_layer) {
                     if (P.learned_prior) {
                       const float ps = S.psd[j];
                       const float tp = z / ps - S.pmu[j] / ps;
-                      lpz += -0.5f * tp * tp - (LOG2PI_HALF_F + S.lpsd[j]);
+                      lw += -0.5f * tp * tp - (LOG2PI_HALF_F + S.lpsd[j]);
                     } else {
-                      lpz += -0.5f * z * z - LOG2PI_HALF_F;
+                      lw += -0.5f * z * z - LOG2PI_HALF_F;
                     }
                   }
                 }
@@ -515,11 +520,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
           }
           store8(S.bufZ, row, k0, v);
         }
-        if (FAST) {
-          lq1 = -0.5f * lq1 - (sum_lsd + (float)d1 * LOG2PI_HALF_F);
-          if (P.two_layer) lpz = 0.f;     // the top-layer prior term is accumulated by the GSAMPLE layer
-          else lpz = -0.5f * lpz - ((P.learned_prior ? sum_lpsd : 0.f) + (float)d1 * LOG2PI_HALF_F);
-        }
+        if (FAST) lw += 0.5f * e1sum - 0.5f * z1sum;     // constants are added once per row at the end
       }
       fence_proxy_async();
       __syncwarp();
@@ -547,11 +548,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
           tc_fence_after();
           const uint32_t tbase = tmem_base + lane_addr + buf * 128;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
+          const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
 
           if (Ly.kind == EPI_TANH) {
             // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
             // bias 30 (tanh(30) == 1.0f): no per-element special cases
-            for_each_16cols(tbase, cn, [&](const uint32_t (&r)[16], int g) {
+            for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
@@ -563,7 +565,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
             // z2 = mu2 + std2*eps2 (iwae2.py:65); one 16-byte A-operand row segment per group.
             const uint32_t gimg = (uint32_t)(args.img_offset + img);
             float e2sum = 0.f, z2sum = 0.f, lgsum = 0.f;
-            for (int g8 = 0; g8 < Ly.next_kpad; g8 += 8) {
+            int n_mine = 0;
+            for (int g8 = 8 * half; g8 < Ly.next_kpad; g8 += 16) {
               float v[8];
               if (g8 < cnt) {
                 uint32_t r[16];
@@ -580,6 +583,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                     if (j < cnt) {
                       const float m = __uint_as_float(r[4 * qq + i]);
                       const float a = __uint_as_float(r[8 + 4 * qq + i]);
+                      ++n_mine;
                       if (FAST) {
                         const float sd = ex2_approx(a) + 1e-6f;
                         const float z = fmaf(e[i], sd, m);
@@ -591,8 +595,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                         const float sd = expf(a) + 1e-6f;
                         const float z = e[i] * sd + m;
                         const float t = z / sd - m / sd;
-                        lq2 += -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));               // iwae2.py:118
-                        lpz += -0.5f * z * z - LOG2PI_HALF_F;                             // iwae2.py:116
+                        lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                // - lqz2z1 (iwae2.py:118)
+                        lw += -0.5f * z * z - LOG2PI_HALF_F;                              // + lpz2   (iwae2.py:116)
                         val = z;
                       }
                     } else if (j == cnt) {
@@ -607,14 +611,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               }
               store8(dst, row, g8, v);
             }
-            if (FAST) {
-              lq2 += -0.5f * e2sum - LN2_F * lgsum - (float)cnt * LOG2PI_HALF_F;
-              lpz += -0.5f * z2sum - (float)cnt * LOG2PI_HALF_F;
-            }
+            // -lq2 + lpz2: the two log(2 pi)/2 constants cancel
+            if (FAST) lw += 0.5f * e2sum + LN2_F * lgsum - 0.5f * z2sum;
           } else if (Ly.kind == EPI_GLOGP) {
             // same column layout; log p(z1|z2) over dims off..off+cnt (iwae2.py:120), z1 re-read from bufZ
             float t2sum = 0.f, lssum = 0.f;
-            for (int g8 = 0; g8 < cnt; g8 += 8) {
+            int n_mine = 0;
+            for (int g8 = 8 * ((half + c) & 1); g8 < cnt; g8 += 16) {
               uint32_t r[16];
               tmem_ld16(tbase + 2 * g8, r);
               tmem_ld_wait();
@@ -627,6 +630,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                   const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
                   const float m = __uint_as_float(r[i]);
                   const float a = __uint_as_float(r[8 + i]);
+                  ++n_mine;
                   if (FAST) {
                     // sd = e^a + 1e-6 with a' = a*log2(e) in TMEM.  One MUFU: inv = 2^-a' = e^-a, then
                     // 1/sd = inv*(1 - 1e-6*inv) and log sd = a + 1e-6*inv to first order in 1e-6*inv
@@ -647,21 +651,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                   } else {
                     const float sd = expf(a) + 1e-6f;
                     const float t = z / sd - m / sd;
-                    lp12 += -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                   // iwae2.py:120
+                    lw += -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                     // + lpz1z2 (iwae2.py:120)
                   }
                 }
               }
             }
-            if (FAST) lp12 += -0.5f * t2sum - lssum - (float)cnt * LOG2PI_HALF_F;
+            if (FAST) lw += -0.5f * t2sum - lssum - (float)n_mine * LOG2PI_HALF_F;
           } else {
             // EPI_BERN: log p(x|z) = -sum_j softplus(s_j), s_j = (1-2x_j) l_j   (A.3 with x in {0,1})
             //   softplus(s) = max(s,0) + log(1 + e^-|s|),  max(s,0) = (s + |l|)/2,  |s| = |l|
             // FAST: the accumulators hold l' = l*log2(e) (folded into W3/b3 at pack time), so the
             // exponential is a bare ex2 of -|l'| and the sign only enters through one FFMA; the logs
-            // are batched: one lg2 per 28 factors (1 + 2^-|l'|) in (1, 2].
+            // are batched: one lg2 per <= 32 factors (1 + 2^-|l'|) in (1, 2].
             if (FAST) {
               float p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
-              for_each_16cols(tbase, cn, [&](const uint32_t (&r)[16], int g) {
+              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
                 const float4* sg4 = reinterpret_cast<const float4*>(&S.sgn[off + g]);
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
@@ -678,15 +682,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               bern_lg += lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
             } else {
               float acc = 0.f;
-              for_each_16cols(tbase, cn, [&](const uint32_t (&r)[16], int g) {
+              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float lgt = __uint_as_float(r[i]);
-                  const float sv = lgt * S.sgn[off + g + i];
-                  acc += fmaxf(sv, 0.f) + log1pf(expf(-fabsf(lgt)));
+                  const float sg = S.sgn[off + g + i];
+                  // padded columns (sgn 0, logit 0) must contribute nothing
+                  acc += (sg != 0.f) ? fmaxf(lgt * sg, 0.f) + log1pf(expf(-fabsf(lgt))) : 0.f;
                 }
               });
-              lpxz -= acc;
+              lw -= acc;
             }
           }
           tc_fence_before();
@@ -700,24 +705,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
           if (lane == 0) mbar_arrive(&S.act_ready);
         }
       }
-      // padded pixel columns (zero weights, sgn 0) each contributed softplus(0) = ln 2
-      if (FAST) lpxz = -LN2_F * (0.5f * (bern_s + bern_a) + bern_lg) + (float)(nx_pad - nx) * LN2_F;
-      else lpxz += (float)(nx_pad - nx) * LN2_F;
+      if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
 
-      // ---- log-weight of this row and the tile's (max, sum exp) partial
-      float lw = P.two_layer ? (lpxz + lp12 + lpz - lq1 - lq2) : (lpxz + (lpz - lq1));
-      if (!valid) lw = -INFINITY;
-      float mx = lw;
+      // ---- combine the two column halves of each row, then the tile's (max, sum exp) partial
+      if (half == 1) S.lwpart[row] = lw;
+      epi_bar_sync();
+      if (half == 0) {
+        lw += S.lwpart[row];
+        if (FAST) {
+          // constants of the FAST accumulation: padded pixel columns each added softplus(0) = ln 2 to
+          // the Bernoulli sum; sum_j log sd_j of q(z1|x) (and of the learned prior); the log(2 pi)/2
+          // terms of lq1 and of the first-layer prior cancel (two-layer: those of lp12 are added in place)
+          float c0 = (float)(nx_pad - nx) * LN2_F;
+          for (int j = 0; j < d1; ++j) c0 += S.lsd[j] - (P.learned_prior ? S.lpsd[j] : 0.f);
+          if (P.two_layer) c0 += (float)d1 * LOG2PI_HALF_F;    // lq1's constant has no first-layer N(0,1) partner
+          lw += c0;
+        }
+        if (!valid) lw = -INFINITY;
+      }
+      float mx = (half == 0) ? lw : -INFINITY;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      epi_bar_sync();
-      if (lane == 0) S.red[warp - 2] = mx;
+      if (lane == 0 && half == 0) S.red[q] = mx;
       epi_bar_sync();
       mx = fmaxf(fmaxf(S.red[0], S.red[1]), fmaxf(S.red[2], S.red[3]));
-      float se = valid ? expf(lw - mx) : 0.f;
+      float se = (half == 0 && valid) ? expf(lw - mx) : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-      if (lane == 0) S.red[4 + warp - 2] = se;
+      if (lane == 0 && half == 0) S.red[4 + q] = se;
       epi_bar_sync();
       if (et == 0) args.partial[tile] = make_float2(mx, S.red[4] + S.red[5] + S.red[6] + S.red[7]);
     }
