@@ -19,6 +19,8 @@
 #include <math.h>
 #include <stdio.h>
 #include <algorithm>
+#include <stdlib.h>
+#include <vector>
 
 namespace tc {
 
@@ -243,7 +245,18 @@ struct EvalArgs {
   int64_t n_tiles;
   int tiles_per_img, rows_per_tile, k;
   uint64_t seed; int64_t img_offset;
+  long long* trace;            // debug timeline (IWAE_TC_TRACE=<file>): [cta<4][role<3][512] (tag, clock64) pairs, else null
 };
+
+#define TRACE_SLOTS 512
+// tag = tile_local*10000 + layer*100 + chunk*10 + phase
+__device__ __forceinline__ void trace_ev(const EvalArgs& a, int role, int& n, int tag) {
+  if (a.trace && blockIdx.x < 4 && n < TRACE_SLOTS) {
+    long long* p = a.trace + (((size_t)blockIdx.x * 3 + role) * TRACE_SLOTS + n) * 2;
+    p[0] = tag; p[1] = clock64();
+    ++n;
+  }
+}
 
 __constant__ Program c_prog;
 
@@ -392,16 +405,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       uint32_t stage = 0, phase = 0, act_phase = 0, cc = 0;
       uint32_t empty_phase[2] = {0, 0};
       const uint32_t zaddr = smem_u32(S.bufZ), paddr = smem_u32(S.bufP);
-      for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+      int tn = 0, tl = 0;
+      for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++tl) {
         for (int l = 0; l < P.nlayers; ++l) {
           const Layer& Ly = P.L[l];
+          trace_ev(args, 1, tn, tl * 10000 + l * 100 + 0);
           if (Ly.wait_act) { mbar_wait(&S.act_ready, act_phase, 200); act_phase ^= 1; tc_fence_after(); }
+          trace_ev(args, 1, tn, tl * 10000 + l * 100 + 1);
           const uint32_t a_base = Ly.src ? paddr : zaddr;
           for (int c = 0; c < Ly.nchunks; ++c) {
             const uint32_t buf = cc & 1;
             mbar_wait(&S.acc_empty[buf], empty_phase[buf] ^ 1, 201);
             empty_phase[buf] ^= 1;
             tc_fence_after();
+            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
             const uint32_t n = (uint32_t)Ly.chunk_n[c];
             const uint32_t idesc = make_idesc(n);
             const uint32_t d_tmem = tmem_base + buf * 128;
@@ -420,6 +437,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(&S.acc_full[buf]);
+            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
             ++cc;
           }
         }
@@ -442,8 +460,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
     uint32_t cc = 0;
     const int d1 = P.d1, nx = P.nx;
     const int nx_pad = (nx + 15) & ~15;
+    int tn = (et == 0) ? 0 : TRACE_SLOTS, tl = 0;     // only epilogue thread 0 records
 
-    for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++tl) {
+      trace_ev(args, 2, tn, tl * 10000 + 9000);
       const int64_t img = tile / args.tiles_per_img;
       const int tin = (int)(tile % args.tiles_per_img);
       const int s = tin * args.rows_per_tile + row;                 // sample index of this row
@@ -525,6 +545,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.act_ready);
+      trace_ev(args, 2, tn, tl * 10000 + 9100);
 
       // ---- layers
       float bern_s = 0.f, bern_a = 0.f, bern_lg = 0.f;     // FAST Bernoulli accumulators (log2 units)
@@ -546,6 +567,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
             full_phase[buf] ^= 1;
           }
           tc_fence_after();
+          trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 5);
           const uint32_t tbase = tmem_base + lane_addr + buf * 128;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
           const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
@@ -697,6 +719,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.acc_empty[buf]);
+          trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 6);
           ++cc;
         }
         if (Ly.signal_act) {
@@ -979,6 +1002,12 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
     tp.partial_cap = need;
   }
   a.partial = tp.partial;
+  a.trace = nullptr;
+  const char* trace_path = getenv("IWAE_TC_TRACE");
+  if (trace_path && *trace_path) {
+    CUDA_TRY(cudaMalloc((void**)&a.trace, sizeof(long long) * 4 * 3 * TRACE_SLOTS * 2));
+    CUDA_TRY(cudaMemsetAsync(a.trace, 0, sizeof(long long) * 4 * 3 * TRACE_SLOTS * 2, st));
+  }
 
   const size_t smem = sizeof(tc::SmemLayout) + 128;
   auto kern = fast ? tc::iwae_eval_tc_kernel<true> : tc::iwae_eval_tc_kernel<false>;
@@ -996,6 +1025,21 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   ctx->ev_valid = true;
   tc::combine_partials_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(tp.partial, N, a.tiles_per_img, k, out_per_example);
   LAUNCH_CHECK();
+  if (a.trace) {     // debug only: synchronous dump of the timeline
+    std::vector<long long> h(4 * 3 * TRACE_SLOTS * 2);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpy(h.data(), a.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFree(a.trace));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int cta = 0; cta < 4; ++cta)
+        for (int role = 0; role < 3; ++role)
+          for (int i = 0; i < TRACE_SLOTS; ++i) {
+            const long long* p = &h[(((size_t)cta * 3 + role) * TRACE_SLOTS + i) * 2];
+            if (p[1]) fprintf(f, "%d %d %lld %lld\n", cta, role, p[0], p[1]);
+          }
+      fclose(f);
+    }
+  }
   return 0;
 }
 
