@@ -201,7 +201,8 @@ constexpr int TILE_M = 128;
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_CHUNKS = 7;
 constexpr int CHUNK_N_MAX = 112;
-constexpr int NSTAGES = 3;
+constexpr int NSTAGES = 7;                            // weight-slab ring depth (50 KB in flight)
+constexpr int NSUB = 2;                               // 128-row sub-tiles per CTA (macro-tile = 256 rows)
 constexpr int SLAB_K = 32;
 constexpr int SLAB_BYTES = CHUNK_N_MAX * SLAB_K * 2;   // 7168
 constexpr int KZ_MAX = 112;                            // K capacity of the z1 buffer
@@ -210,9 +211,9 @@ constexpr int BUFZ_BYTES = TILE_M * KZ_MAX * 2;        // 28672
 constexpr int BUFP_BYTES = TILE_M * KP_MAX * 2;        // 53248
 constexpr int NX_MAX = 784;
 constexpr int D_MAX = 104;
-constexpr int NUM_EPI_THREADS = 256;                  // 8 epilogue warps
-constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;     // + producer warp + MMA warp
-constexpr int TMEM_COLS = 256;
+constexpr int NUM_EPI_WARPS = 8 * NSUB;               // 8 epilogue warps per sub-tile
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // producer warp, MMA warp, epilogue warps
+constexpr int TMEM_COLS = 512;                        // 2 sub-tiles x 2 accumulator buffers x 128 columns
 
 enum { EPI_TANH = 0, EPI_GSAMPLE = 1, EPI_GLOGP = 2, EPI_BERN = 3 };
 
@@ -260,25 +261,29 @@ __device__ __forceinline__ void trace_ev(const EvalArgs& a, int role, int& n, in
 
 __constant__ Program c_prog;
 
-struct __align__(16) SmemLayout {
+struct __align__(16) SubTile {       // per 128-row sub-tile
   uint8_t bufZ[BUFZ_BYTES];
   uint8_t bufP[BUFP_BYTES];
-  uint8_t ring[NSTAGES][SLAB_BYTES];
-  float sgn[NX_MAX];           // 1 - 2x per pixel of the current image (0 for padded columns); 16-byte aligned
+  float sgn[NX_MAX];           // 1 - 2x per pixel of the sub-tile's image (0 for padded columns); 16-byte aligned
   float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX], ipsd[D_MAX];
-  float red[8];
+  float red[16];               // [0,4) max, [4,8) sum-exp, [8,16) per-warp constant partials
   float lwpart[TILE_M];        // partial log-weights of the second column half of each row
+  int label; int pad_[3];
+};
+struct __align__(16) SmemLayout {
+  SubTile sub[NSUB];
+  uint8_t ring[NSTAGES][SLAB_BYTES];
   uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready;
   uint32_t tmem_base;
-  int label;
 };
 
-// two CTAs per SM: 2 * (dynamic smem + 1 KB reserved) must fit the 228 KB of an SM
-static_assert(2 * (sizeof(SmemLayout) + 128 + 1024) <= 228 * 1024, "fused eval kernel: two CTAs must fit one SM");
+// one persistent CTA per SM: the dynamic shared memory of one CTA is at most 227 KB
+static_assert(sizeof(SmemLayout) + 128 <= 227 * 1024, "fused eval kernel: shared memory exceeds 227 KB");
 
 #define LOG2PI_HALF_F 0.91893853320467274178f
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// named barrier of one sub-tile's 8 epilogue warps
+__device__ __forceinline__ void epi_bar_sync(int u) { asm volatile("bar.sync %0, 256;" ::"r"(1 + u) : "memory"); }
 
 template <bool FAST>
 __device__ __forceinline__ float act_tanh(float v) {
@@ -360,16 +365,17 @@ __device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs args) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) iwae_eval_tc_kernel(EvalArgs args) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
   const Program& P = c_prog;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_macro = (args.n_tiles + NSUB - 1) / NSUB;
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], 8); }
-    mbar_init(&S.act_ready, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], NUM_EPI_WARPS); }
+    mbar_init(&S.act_ready, NUM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&S.tmem_base, TMEM_COLS); tmem_relinquish(); }
@@ -380,9 +386,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
 
   if (warp == 0) {
     // ===================== weight producer =====================
+    // One pass over the packed weights per macro-tile; every slab is used by the MMAs of BOTH
+    // sub-tiles, so each weight byte crosses L2 -> smem once per 256 rows.
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+      for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x) {
         const uint8_t* src = args.wpack;
         for (int l = 0; l < P.nlayers; ++l) {
           const Layer& Ly = P.L[l];
@@ -404,15 +412,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, act_phase = 0, cc = 0;
       uint32_t empty_phase[2] = {0, 0};
-      const uint32_t zaddr = smem_u32(S.bufZ), paddr = smem_u32(S.bufP);
+      uint32_t zaddr[NSUB], paddr[NSUB];
+#pragma unroll
+      for (int u = 0; u < NSUB; ++u) { zaddr[u] = smem_u32(S.sub[u].bufZ); paddr[u] = smem_u32(S.sub[u].bufP); }
       int tn = 0, tl = 0;
-      for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++tl) {
+      for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
         for (int l = 0; l < P.nlayers; ++l) {
           const Layer& Ly = P.L[l];
           trace_ev(args, 1, tn, tl * 10000 + l * 100 + 0);
           if (Ly.wait_act) { mbar_wait(&S.act_ready, act_phase, 200); act_phase ^= 1; tc_fence_after(); }
           trace_ev(args, 1, tn, tl * 10000 + l * 100 + 1);
-          const uint32_t a_base = Ly.src ? paddr : zaddr;
           for (int c = 0; c < Ly.nchunks; ++c) {
             const uint32_t buf = cc & 1;
             mbar_wait(&S.acc_empty[buf], empty_phase[buf] ^ 1, 201);
@@ -421,7 +430,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
             trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
             const uint32_t n = (uint32_t)Ly.chunk_n[c];
             const uint32_t idesc = make_idesc(n);
-            const uint32_t d_tmem = tmem_base + buf * 128;
             for (int k0 = 0; k0 < Ly.k_pad; k0 += SLAB_K) {
               mbar_wait(&S.full[stage], phase, 202);
               tc_fence_after();
@@ -429,9 +437,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               const uint32_t b_base = smem_u32(S.ring[stage]);
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint32_t kk = (uint32_t)k0 + 16u * ks;
-                const uint64_t ad = make_smem_desc(a_base + (kk >> 3) * (TILE_M * 16), TILE_M * 16, 128);
                 const uint64_t bd = make_smem_desc(b_base + (uint32_t)ks * 2u * n * 16u, n * 16u, 128);
-                umma_f16(d_tmem, ad, bd, idesc, kk > 0);
+#pragma unroll
+                for (int u = 0; u < NSUB; ++u) {
+                  const uint32_t a_base = Ly.src ? paddr[u] : zaddr[u];
+                  const uint64_t ad = make_smem_desc(a_base + (kk >> 3) * (TILE_M * 16), TILE_M * 16, 128);
+                  umma_f16(tmem_base + (uint32_t)(u * 2 + buf) * 128u, ad, bd, idesc, kk > 0);
+                }
               }
               umma_commit(&S.empty[stage]);     // slab consumed when these MMAs retire
               if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
@@ -445,44 +457,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
     }
   } else {
     // ===================== epilogue warps =====================
-    // Eight warps: warps e and e+4 share one TMEM lane quarter (one row per lane) and split the
-    // COLUMNS of every accumulator chunk between them (alternating 16-column groups), so 16 epilogue
-    // warps per SM (two CTAs) hide each other's MUFU / TMEM-load latency.  Every log-density term is
-    // a sum over columns, so each thread keeps one partial log-weight; the two halves of a row are
-    // added through shared memory at the end of the tile.
-    const int e_warp = warp - 2;             // 0..7
-    const int half = e_warp >> 2;            // which half of the column groups this warp takes
+    // Sixteen warps: eight per 128-row sub-tile.  Within a sub-tile, warps e and e+4 share one TMEM
+    // lane quarter (one row per lane) and split the COLUMNS of every accumulator chunk between them
+    // (alternating 16-column groups).  Every log-density term is a sum over columns, so each thread
+    // keeps one partial log-weight; the two halves of a row are added through shared memory at the
+    // end of the tile.
+    const int e_warp = warp - 2;             // 0..15
+    const int u = e_warp >> 3;               // sub-tile
+    const int half = (e_warp >> 2) & 1;      // which half of the column groups this warp takes
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int et = e_warp * 32 + lane;       // 0..255 among epilogue threads
+    const int et = (e_warp & 7) * 32 + lane; // 0..255 among the sub-tile's epilogue threads
+    SubTile& T = S.sub[u];
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t full_phase[2] = {0, 0};
     uint32_t cc = 0;
     const int d1 = P.d1, nx = P.nx;
     const int nx_pad = (nx + 15) & ~15;
-    int tn = (et == 0) ? 0 : TRACE_SLOTS, tl = 0;     // only epilogue thread 0 records
+    const int d1_full = d1 & ~7;             // dims covered by complete 8-wide groups
+    int tn = (e_warp == 0 && lane == 0) ? 0 : TRACE_SLOTS, tl = 0;     // only one thread records
 
-    for (int64_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++tl) {
+    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
       trace_ev(args, 2, tn, tl * 10000 + 9000);
+      int64_t tile = mt * NSUB + u;
+      const bool tile_ok = tile < args.n_tiles;       // the last macro-tile may be half empty
+      if (!tile_ok) tile = args.n_tiles - 1;
       const int64_t img = tile / args.tiles_per_img;
       const int tin = (int)(tile % args.tiles_per_img);
       const int s = tin * args.rows_per_tile + row;                 // sample index of this row
-      const bool valid = (row < args.rows_per_tile) && (s < args.k);
+      const bool valid = tile_ok && (row < args.rows_per_tile) && (s < args.k);
 
       // ---- per-image constants into smem
-      epi_bar_sync();
-      for (int j = et; j < nx_pad; j += NUM_EPI_THREADS)
-        S.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
-      for (int j = et; j < d1; j += NUM_EPI_THREADS) {
+      epi_bar_sync(u);
+      for (int j = et; j < nx_pad; j += 256)
+        T.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
+      float csum = 0.f;
+      for (int j = et; j < d1; j += 256) {
         const float sd = __ldg(args.std1 + img * d1 + j);
-        S.mu[j] = __ldg(args.mu1 + img * d1 + j); S.sd[j] = sd; S.lsd[j] = logf(sd);
+        const float ls = logf(sd);
+        T.mu[j] = __ldg(args.mu1 + img * d1 + j); T.sd[j] = sd; T.lsd[j] = ls;
+        csum += ls;
         if (P.learned_prior) {
           const float ps = __ldg(args.pstd + img * d1 + j);
-          S.pmu[j] = __ldg(args.pmu + img * d1 + j); S.psd[j] = ps; S.lpsd[j] = logf(ps); S.ipsd[j] = 1.f / ps;
+          const float lps = logf(ps);
+          T.pmu[j] = __ldg(args.pmu + img * d1 + j); T.psd[j] = ps; T.lpsd[j] = lps; T.ipsd[j] = 1.f / ps;
+          csum -= lps;
         }
       }
-      if (et == 0 && P.cond) S.label = (int)(unsigned char)(int)__ldg(args.y + img);
-      epi_bar_sync();
+      if (FAST) {
+        // constants of the FAST accumulation, once per tile: padded pixel columns each add
+        // softplus(0) = ln 2 to the Bernoulli sum; sum_j log sd_j of q(z1|x) minus that of a learned
+        // prior; the log(2 pi)/2 terms of lq1 and of a first-layer prior cancel, in the two-layer
+        // model lq1's constant has no first-layer N(0,1) partner.
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        if (lane == 0) T.red[8 + (e_warp & 7)] = csum;
+      }
+      if (et == 0 && P.cond) T.label = (int)(unsigned char)(int)__ldg(args.y + img);
+      epi_bar_sync(u);
 
       // This thread's partial log-weight: log_w = lpxz + lp(prior terms) - lq(terms), all sums over
       // columns.  Precise mode adds log-probabilities term by term in TFP's op order; FAST mode
@@ -497,48 +529,71 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
         float e1sum = 0.f, z1sum = 0.f;
         for (int k0 = 8 * half; k0 < P.kz_pad; k0 += 16) {
           float v[8];
+          if (FAST && k0 < d1_full) {
+            // complete group of 8 latent dims: no per-element predicates, vector constant loads
+            const float4 na = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2));
+            const float4 nb = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 1u);
+            const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+            const float4 m0 = *reinterpret_cast<const float4*>(&T.mu[k0]), m1 = *reinterpret_cast<const float4*>(&T.mu[k0 + 4]);
+            const float4 s0 = *reinterpret_cast<const float4*>(&T.sd[k0]), s1 = *reinterpret_cast<const float4*>(&T.sd[k0 + 4]);
+            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {
-            const int j0 = k0 + 4 * qq;
-            float e[4] = {0.f, 0.f, 0.f, 0.f};
-            if (j0 < d1) {
-              const float4 n4 = normal4<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
-              e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+            for (int i = 0; i < 8; ++i) {
+              v[i] = fmaf(e[i], ss[i], mm[i]);
+              e1sum = fmaf(e[i], e[i], e1sum);
             }
+            if (P.learned_prior) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int j = j0 + i;
-              float val = 0.f;
-              if (j < d1) {
-                const float sd = S.sd[j], m = S.mu[j];
-                const float z = fmaf(e[i], sd, m);
-                if (FAST) {
-                  e1sum = fmaf(e[i], e[i], e1sum);
-                  if (P.learned_prior) { const float tp = (z - S.pmu[j]) * S.ipsd[j]; z1sum = fmaf(tp, tp, z1sum); }
-                  else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
-                } else {
-                  const float t = z / sd - m / sd;                         // TFP op order
-                  lw -= -0.5f * t * t - (LOG2PI_HALF_F + S.lsd[j]);        // - lq(z1|x)
-                  if (!P.two_layer) {
-                    if (P.learned_prior) {
-                      const float ps = S.psd[j];
-                      const float tp = z / ps - S.pmu[j] / ps;
-                      lw += -0.5f * tp * tp - (LOG2PI_HALF_F + S.lpsd[j]);
-                    } else {
-                      lw += -0.5f * z * z - LOG2PI_HALF_F;
+              for (int i = 0; i < 8; ++i) { const float tp = (v[i] - T.pmu[k0 + i]) * T.ipsd[k0 + i]; z1sum = fmaf(tp, tp, z1sum); }
+            } else if (!P.two_layer) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) z1sum = fmaf(v[i], v[i], z1sum);
+            }
+          } else {
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int j0 = k0 + 4 * qq;
+              float e[4] = {0.f, 0.f, 0.f, 0.f};
+              if (j0 < d1) {
+                const float4 n4 = normal4<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
+                e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j0 + i;
+                float val = 0.f;
+                if (j < d1) {
+                  const float sd = T.sd[j], m = T.mu[j];
+                  const float z = fmaf(e[i], sd, m);
+                  if (FAST) {
+                    e1sum = fmaf(e[i], e[i], e1sum);
+                    if (P.learned_prior) { const float tp = (z - T.pmu[j]) * T.ipsd[j]; z1sum = fmaf(tp, tp, z1sum); }
+                    else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
+                  } else {
+                    const float t = z / sd - m / sd;                         // TFP op order
+                    lw -= -0.5f * t * t - (LOG2PI_HALF_F + T.lsd[j]);        // - lq(z1|x)
+                    if (!P.two_layer) {
+                      if (P.learned_prior) {
+                        const float ps = T.psd[j];
+                        const float tp = z / ps - T.pmu[j] / ps;
+                        lw += -0.5f * tp * tp - (LOG2PI_HALF_F + T.lpsd[j]);
+                      } else {
+                        lw += -0.5f * z * z - LOG2PI_HALF_F;
+                      }
                     }
                   }
+                  val = z;
+                } else if (j < one_col) {
+                  val = (T.label == j - d1) ? 1.f : 0.f;
+                } else if (j == one_col) {
+                  val = 1.f;
                 }
-                val = z;
-              } else if (j < one_col) {
-                val = (S.label == j - d1) ? 1.f : 0.f;
-              } else if (j == one_col) {
-                val = 1.f;
+                v[4 * qq + i] = val;
               }
-              v[4 * qq + i] = val;
             }
           }
-          store8(S.bufZ, row, k0, v);
+          store8(T.bufZ, row, k0, v);
         }
         if (FAST) lw += 0.5f * e1sum - 0.5f * z1sum;     // constants are added once per row at the end
       }
@@ -551,7 +606,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       float bern_s = 0.f, bern_a = 0.f, bern_lg = 0.f;     // FAST Bernoulli accumulators (log2 units)
       for (int l = 0; l < P.nlayers; ++l) {
         const Layer& Ly = P.L[l];
-        uint8_t* dst = Ly.dst ? S.bufP : S.bufZ;
+        uint8_t* dst = Ly.dst ? T.bufP : T.bufZ;
         if (Ly.inplace && Ly.nchunks > 1) {
           // all chunks' MMAs must have retired before the input buffer is overwritten
           for (int c = 0; c < Ly.nchunks; ++c) {
@@ -568,7 +623,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
           }
           tc_fence_after();
           trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 5);
-          const uint32_t tbase = tmem_base + lane_addr + buf * 128;
+          const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(u * 2 + buf) * 128u;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
           const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
 
@@ -587,7 +642,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
             // z2 = mu2 + std2*eps2 (iwae2.py:65); one 16-byte A-operand row segment per group.
             const uint32_t gimg = (uint32_t)(args.img_offset + img);
             float e2sum = 0.f, z2sum = 0.f, lgsum = 0.f;
-            int n_mine = 0;
             for (int g8 = 8 * half; g8 < Ly.next_kpad; g8 += 16) {
               float v[8];
               if (g8 < cnt) {
@@ -605,7 +659,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
                     if (j < cnt) {
                       const float m = __uint_as_float(r[4 * qq + i]);
                       const float a = __uint_as_float(r[8 + 4 * qq + i]);
-                      ++n_mine;
                       if (FAST) {
                         const float sd = ex2_approx(a) + 1e-6f;
                         const float z = fmaf(e[i], sd, m);
@@ -643,7 +696,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
               uint32_t r[16];
               tmem_ld16(tbase + 2 * g8, r);
               tmem_ld_wait();
-              const uint4 za = *reinterpret_cast<const uint4*>(S.bufZ + (size_t)((off + g8) >> 3) * (TILE_M * 16) + row * 16);
+              const uint4 za = *reinterpret_cast<const uint4*>(T.bufZ + (size_t)((off + g8) >> 3) * (TILE_M * 16) + row * 16);
               const uint32_t zw[4] = {za.x, za.y, za.z, za.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -688,7 +741,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
             if (FAST) {
               float p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
               for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
-                const float4* sg4 = reinterpret_cast<const float4*>(&S.sgn[off + g]);
+                const float4* sg4 = reinterpret_cast<const float4*>(&T.sgn[off + g]);
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
                   const float4 sg = sg4[i4];
@@ -708,7 +761,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float lgt = __uint_as_float(r[i]);
-                  const float sg = S.sgn[off + g + i];
+                  const float sg = T.sgn[off + g + i];
                   // padded columns (sgn 0, logit 0) must contribute nothing
                   acc += (sg != 0.f) ? fmaxf(lgt * sg, 0.f) + log1pf(expf(-fabsf(lgt))) : 0.f;
                 }
@@ -731,17 +784,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
 
       // ---- combine the two column halves of each row, then the tile's (max, sum exp) partial
-      if (half == 1) S.lwpart[row] = lw;
-      epi_bar_sync();
+      if (half == 1) T.lwpart[row] = lw;
+      epi_bar_sync(u);
       if (half == 0) {
-        lw += S.lwpart[row];
+        lw += T.lwpart[row];
         if (FAST) {
-          // constants of the FAST accumulation: padded pixel columns each added softplus(0) = ln 2 to
-          // the Bernoulli sum; sum_j log sd_j of q(z1|x) (and of the learned prior); the log(2 pi)/2
-          // terms of lq1 and of the first-layer prior cancel (two-layer: those of lp12 are added in place)
-          float c0 = (float)(nx_pad - nx) * LN2_F;
-          for (int j = 0; j < d1; ++j) c0 += S.lsd[j] - (P.learned_prior ? S.lpsd[j] : 0.f);
-          if (P.two_layer) c0 += (float)d1 * LOG2PI_HALF_F;    // lq1's constant has no first-layer N(0,1) partner
+          float c0 = (float)(nx_pad - nx) * LN2_F + (P.two_layer ? (float)d1 * LOG2PI_HALF_F : 0.f);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) c0 += T.red[8 + w];
           lw += c0;
         }
         if (!valid) lw = -INFINITY;
@@ -749,15 +799,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) iwae_eval_tc_kernel(EvalArgs a
       float mx = (half == 0) ? lw : -INFINITY;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0 && half == 0) S.red[q] = mx;
-      epi_bar_sync();
-      mx = fmaxf(fmaxf(S.red[0], S.red[1]), fmaxf(S.red[2], S.red[3]));
+      if (lane == 0 && half == 0) T.red[q] = mx;
+      epi_bar_sync(u);
+      mx = fmaxf(fmaxf(T.red[0], T.red[1]), fmaxf(T.red[2], T.red[3]));
       float se = (half == 0 && valid) ? expf(lw - mx) : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-      if (lane == 0 && half == 0) S.red[4 + q] = se;
-      epi_bar_sync();
-      if (et == 0) args.partial[tile] = make_float2(mx, S.red[4] + S.red[5] + S.red[6] + S.red[7]);
+      if (lane == 0 && half == 0) T.red[4 + q] = se;
+      epi_bar_sync(u);
+      if (et == 0 && tile_ok) args.partial[tile] = make_float2(mx, T.red[4] + T.red[5] + T.red[6] + T.red[7]);
     }
   }
 
@@ -1016,7 +1066,7 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
     CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tp.attr_set = true;
   }
-  int grid = (int)std::min<int64_t>(a.n_tiles, (int64_t)2 * ctx->sm_count);
+  int grid = (int)std::min<int64_t>((a.n_tiles + tc::NSUB - 1) / tc::NSUB, (int64_t)ctx->sm_count);
   if (!ctx->ev_k0) { CUDA_TRY(cudaEventCreate(&ctx->ev_k0)); CUDA_TRY(cudaEventCreate(&ctx->ev_k1)); }
   CUDA_TRY(cudaEventRecord(ctx->ev_k0, st));
   kern<<<grid, tc::NUM_THREADS, smem, st>>>(a);
