@@ -71,6 +71,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
+// One lane of a fully converged warp (the same lane every time): PTX elect.sync.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -388,70 +396,80 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) iwae_eval_tc_kernel(EvalArgs a
     // ===================== weight producer =====================
     // One pass over the packed weights per macro-tile; every slab is used by the MMAs of BOTH
     // sub-tiles, so each weight byte crosses L2 -> smem once per 256 rows.
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x) {
-        const uint8_t* src = args.wpack;
-        for (int l = 0; l < P.nlayers; ++l) {
-          const Layer& Ly = P.L[l];
-          for (int c = 0; c < Ly.nchunks; ++c) {
-            for (int k0 = 0; k0 < Ly.k_pad; k0 += SLAB_K) {
-              const uint32_t bytes = (uint32_t)Ly.chunk_n[c] * (uint32_t)min(SLAB_K, Ly.k_pad - k0) * 2u;
-              mbar_wait(&S.empty[stage], phase ^ 1, 100);
+    // The whole warp walks the loops convergently and ONE elected lane issues: in warp-uniform code
+    // the compiler feeds UBLKCP / UTCHMMA from uniform registers directly; inside an `if (lane == 0)`
+    // region it wraps every such instruction in an ELECT / R2UR / BRA.U.ANY waterfall loop (v3: ~160
+    // cycles of issue per MMA, three times the tensor-pipe time of the MMA itself).
+    uint32_t stage = 0, phase = 0;
+    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x) {
+      const uint8_t* src = args.wpack;
+      for (int l = 0; l < P.nlayers; ++l) {
+        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad;
+        for (int c = 0; c < nchunks; ++c) {
+          const uint32_t cn = (uint32_t)P.L[l].chunk_n[c];
+          for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
+            const uint32_t bytes = cn * (uint32_t)min(SLAB_K, k_pad - k0) * 2u;
+            mbar_wait(&S.empty[stage], phase ^ 1, 100);
+            if (elect_one_sync()) {
               mbar_expect_tx(&S.full[stage], bytes);
               bulk_g2s(S.ring[stage], src, bytes, &S.full[stage]);
-              src += bytes;
-              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            src += bytes;
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, act_phase = 0, cc = 0;
-      uint32_t empty_phase[2] = {0, 0};
-      uint32_t zaddr[NSUB], paddr[NSUB];
-#pragma unroll
-      for (int u = 0; u < NSUB; ++u) { zaddr[u] = smem_u32(S.sub[u].bufZ); paddr[u] = smem_u32(S.sub[u].bufP); }
-      int tn = 0, tl = 0;
-      for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
-        for (int l = 0; l < P.nlayers; ++l) {
-          const Layer& Ly = P.L[l];
-          trace_ev(args, 1, tn, tl * 10000 + l * 100 + 0);
-          if (Ly.wait_act) { mbar_wait(&S.act_ready, act_phase, 200); act_phase ^= 1; tc_fence_after(); }
-          trace_ev(args, 1, tn, tl * 10000 + l * 100 + 1);
-          for (int c = 0; c < Ly.nchunks; ++c) {
-            const uint32_t buf = cc & 1;
-            mbar_wait(&S.acc_empty[buf], empty_phase[buf] ^ 1, 201);
-            empty_phase[buf] ^= 1;
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    uint32_t stage = 0, phase = 0, act_phase = 0, cc = 0;
+    uint32_t empty_phase[2] = {0, 0};
+    const uint32_t ring0 = smem_u32(S.ring[0]);
+    const uint32_t z0 = smem_u32(S.sub[0].bufZ), p0 = smem_u32(S.sub[0].bufP);
+    const uint32_t sub_stride = (uint32_t)sizeof(SubTile);
+    int tn = (lane == 0) ? 0 : TRACE_SLOTS, tl = 0;
+    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
+      for (int l = 0; l < P.nlayers; ++l) {
+        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad;
+        const uint32_t a_base0 = P.L[l].src ? p0 : z0;
+        trace_ev(args, 1, tn, tl * 10000 + l * 100 + 0);
+        if (P.L[l].wait_act) { mbar_wait(&S.act_ready, act_phase, 200); act_phase ^= 1; tc_fence_after(); }
+        trace_ev(args, 1, tn, tl * 10000 + l * 100 + 1);
+        for (int c = 0; c < nchunks; ++c) {
+          const uint32_t buf = cc & 1;
+          mbar_wait(&S.acc_empty[buf], empty_phase[buf] ^ 1, 201);
+          empty_phase[buf] ^= 1;
+          tc_fence_after();
+          trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
+          const uint32_t n = (uint32_t)P.L[l].chunk_n[c];
+          const uint32_t idesc = make_idesc(n);
+          const uint32_t d0 = tmem_base + buf * 128u;
+          for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
+            mbar_wait(&S.full[stage], phase, 202);
             tc_fence_after();
-            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
-            const uint32_t n = (uint32_t)Ly.chunk_n[c];
-            const uint32_t idesc = make_idesc(n);
-            for (int k0 = 0; k0 < Ly.k_pad; k0 += SLAB_K) {
-              mbar_wait(&S.full[stage], phase, 202);
-              tc_fence_after();
-              const int ksteps = min(SLAB_K, Ly.k_pad - k0) / 16;
-              const uint32_t b_base = smem_u32(S.ring[stage]);
+            if (elect_one_sync()) {
+              // descriptors: only the 14-bit start-address field changes between MMAs
+              const uint64_t bd0 = make_smem_desc(ring0 + stage * SLAB_BYTES, n * 16u, 128);
+              const uint64_t ad0 = make_smem_desc(a_base0 + ((uint32_t)k0 >> 3) * (TILE_M * 16), TILE_M * 16, 128);
+              const int ksteps = min(SLAB_K, k_pad - k0) / 16;
               for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t kk = (uint32_t)k0 + 16u * ks;
-                const uint64_t bd = make_smem_desc(b_base + (uint32_t)ks * 2u * n * 16u, n * 16u, 128);
+                const uint64_t bd = bd0 + (uint64_t)((uint32_t)ks * 2u * n);              // + ks*2*n*16 bytes >> 4
+                const uint64_t ad = ad0 + (uint64_t)((uint32_t)ks * 2u * TILE_M);         // + ks*2*128*16 bytes >> 4
+                const uint32_t acc = (k0 | ks) != 0;
 #pragma unroll
-                for (int u = 0; u < NSUB; ++u) {
-                  const uint32_t a_base = Ly.src ? paddr[u] : zaddr[u];
-                  const uint64_t ad = make_smem_desc(a_base + (kk >> 3) * (TILE_M * 16), TILE_M * 16, 128);
-                  umma_f16(tmem_base + (uint32_t)(u * 2 + buf) * 128u, ad, bd, idesc, kk > 0);
-                }
+                for (int u = 0; u < NSUB; ++u)
+                  umma_f16(d0 + (uint32_t)u * 256u, ad + (uint64_t)(u * (sub_stride >> 4)), bd, idesc, acc);
               }
               umma_commit(&S.empty[stage]);     // slab consumed when these MMAs retire
-              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&S.acc_full[buf]);
-            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
-            ++cc;
+            __syncwarp();
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
+          if (elect_one_sync()) umma_commit(&S.acc_full[buf]);
+          __syncwarp();
+          trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
+          ++cc;
         }
       }
     }
