@@ -182,6 +182,11 @@ int iwae_bernoulli_sample(const float* p, int64_t n, uint64_t seed, uint64_t epo
 int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, int32_t variant, float* D,
                        void* stream);
 
+/* Tensor-core micro-benchmark (diagnostic): `reps` back-to-back tcgen05.mma of shape M=128, N, K=16 in the
+ * fused kernel's operand layout on `nctas` CTAs; out_cycles [nctas] (device) receives the SM cycles from
+ * first issue to completion.  Used to size the fused kernel's MMA width (scripts/umma_bench.py). */
+int iwae_umma_bench(int32_t N, int32_t reps, int32_t nctas, int64_t* out_cycles, void* stream);
+
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t iwae_launch_count(void);
 

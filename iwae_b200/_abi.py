@@ -65,6 +65,7 @@ def _load():
         "iwae_bernoulli_sample": (C.c_int, [vp, i64, u64, u64, vp, vp]),
         "iwae_umma_selftest": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "iwae_launch_count": (i64, []),
+        "iwae_umma_bench": (C.c_int, [i32, i32, i32, vp, vp]),
         "iwae_llh_kernel_ms": (C.c_int, [vp, P(C.c_float)]),
     }
     for name, (res, args) in sigs.items():
@@ -78,7 +79,7 @@ lib = _load()
 EXPORTS = ("iwae_last_error", "iwae_version", "iwae_create", "iwae_destroy", "iwae_param_count",
            "iwae_param_layout", "iwae_layout_for_config", "iwae_forward", "iwae_llh_eval", "iwae_llh_eval_host",
            "iwae_grads", "iwae_adam_step", "iwae_train_step", "iwae_philox_normal", "iwae_decode", "iwae_sir",
-           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms")
+           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_umma_bench")
 
 
 def check(rc: int, what: str = ""):

@@ -185,4 +185,5 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
                   float* mu, float* sd, cudaStream_t st);
 void tc_release(iwae_ctx* ctx);
+int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream_t st);
 int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st);

@@ -57,13 +57,19 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU.
+// Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU.  The watchdog clock is
+// read only every 4096 polls so that waiting warps spend as few issue slots as possible.
 __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) {
-      printf("iwae_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-      __trap();
+    if ((++polls & 0xFFFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("iwae_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -202,6 +208,47 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   if (warp == 0) tmem_dealloc(tmem_base, ncols);
 }
 
+// Micro-benchmark: `reps` back-to-back tcgen05.mma (M=128, K=16, fp16, smem A and B in the fused kernel's
+// no-swizzle K-major layout) of width N into one accumulator; returns cycles from first issue to the
+// commit's mbarrier completion.  Sizes the chunk width of the fused kernel (SS-mode A-operand fetch).
+__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int nctas_dummy, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + N) * 16 * 2 * 4 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  __syncwarp();
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  long long t0 = 0;
+  if (warp == 1) {
+    const uint32_t idesc = make_idesc((uint32_t)N);
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem) + 128 * 16 * 2 * 4;
+    t0 = clock64();
+    if (elect_one_sync()) {
+      for (int r = 0; r < reps; ++r) {
+        const uint32_t ks = r & 3;
+        const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
+        const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
+        umma_f16(tmem_base, ad, bd, idesc, r > 0);
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0, 901);
+    const long long t1 = clock64();
+    if (tid == 32) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fused evaluation kernel
 // ------------------------------------------------------------------------------------------------
@@ -281,7 +328,7 @@ struct __align__(16) SubTile {       // per 128-row sub-tile
 struct __align__(16) SmemLayout {
   SubTile sub[NSUB];
   uint8_t ring[NSTAGES][SLAB_BYTES];
-  uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready;
+  uint64_t full[NSTAGES], empty[NSTAGES], acc_full[NSUB][2], acc_empty[NSUB][2], act_ready[NSUB];
   uint32_t tmem_base;
 };
 
@@ -382,8 +429,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) iwae_eval_tc_kernel(EvalArgs a
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], NUM_EPI_WARPS); }
-    mbar_init(&S.act_ready, NUM_EPI_WARPS);
+    for (int u = 0; u < NSUB; ++u) {
+      for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[u][i], 1); mbar_init(&S.acc_empty[u][i], 8); }
+      mbar_init(&S.act_ready[u], 8);
+    }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&S.tmem_base, TMEM_COLS); tmem_relinquish(); }
@@ -423,52 +472,96 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) iwae_eval_tc_kernel(EvalArgs a
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-    uint32_t stage = 0, phase = 0, act_phase = 0, cc = 0;
-    uint32_t empty_phase[2] = {0, 0};
+    // Two issue orders per layer:
+    //  * layers whose K fits four slabs (the q(z2|z1) / p(z1|z2) chain and the first decoder layer) run
+    //    SUB-TILE-SEQUENTIAL: all MMAs of sub-tile 0, then all MMAs of sub-tile 1 over the same slabs
+    //    (still resident in the ring).  The two sub-tiles therefore run half a layer apart, and the
+    //    epilogue of one overlaps the MMAs of the other - the dependent layer chain no longer leaves
+    //    the tensor pipe and the MUFU idle in turns.
+    //  * wide layers (K = 208: second decoder layer and the 784-logit layer) interleave the sub-tiles
+    //    per slab so a slab leaves the ring as soon as both have used it; there the double-buffered
+    //    accumulators provide the overlap.
+    uint32_t stage = 0, phase = 0, cc = 0;
+    uint32_t act_phase[NSUB] = {0, 0};
+    uint32_t empty_phase[NSUB][2] = {{0, 0}, {0, 0}};
     const uint32_t ring0 = smem_u32(S.ring[0]);
     const uint32_t z0 = smem_u32(S.sub[0].bufZ), p0 = smem_u32(S.sub[0].bufP);
-    const uint32_t sub_stride = (uint32_t)sizeof(SubTile);
+    const uint32_t sub_stride16 = (uint32_t)sizeof(SubTile) >> 4;
     int tn = (lane == 0) ? 0 : TRACE_SLOTS, tl = 0;
+
+    // MMAs of one slab for sub-tile u (one elected lane)
+    auto issue_slab = [&](int u, uint32_t st, uint32_t a_base0, int k0, int k_pad, uint32_t n, uint32_t idesc,
+                          uint32_t d_tmem, bool release) {
+      if (elect_one_sync()) {
+        // descriptors: only the 14-bit start-address field changes between MMAs
+        const uint64_t bd0 = make_smem_desc(ring0 + st * SLAB_BYTES, n * 16u, 128);
+        const uint64_t ad0 = make_smem_desc(a_base0 + ((uint32_t)k0 >> 3) * (TILE_M * 16), TILE_M * 16, 128) +
+                             (uint64_t)((uint32_t)u * sub_stride16);
+        const int ksteps = min(SLAB_K, k_pad - k0) / 16;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_f16(d_tmem, ad0 + (uint64_t)((uint32_t)ks * 2u * TILE_M), bd0 + (uint64_t)((uint32_t)ks * 2u * n), idesc,
+                   (k0 | ks) != 0);
+        if (release) umma_commit(&S.empty[st]);     // slab consumed when these MMAs retire
+      }
+      __syncwarp();
+    };
+
     for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
       for (int l = 0; l < P.nlayers; ++l) {
-        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad;
+        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act;
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
+        const int nslabs = (k_pad + SLAB_K - 1) / SLAB_K;
+        const bool sequential = nslabs <= 4;
         trace_ev(args, 1, tn, tl * 10000 + l * 100 + 0);
-        if (P.L[l].wait_act) { mbar_wait(&S.act_ready, act_phase, 200); act_phase ^= 1; tc_fence_after(); }
-        trace_ev(args, 1, tn, tl * 10000 + l * 100 + 1);
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = cc & 1;
-          mbar_wait(&S.acc_empty[buf], empty_phase[buf] ^ 1, 201);
-          empty_phase[buf] ^= 1;
-          tc_fence_after();
-          trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
           const uint32_t n = (uint32_t)P.L[l].chunk_n[c];
           const uint32_t idesc = make_idesc(n);
-          const uint32_t d0 = tmem_base + buf * 128u;
-          for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
-            mbar_wait(&S.full[stage], phase, 202);
-            tc_fence_after();
-            if (elect_one_sync()) {
-              // descriptors: only the 14-bit start-address field changes between MMAs
-              const uint64_t bd0 = make_smem_desc(ring0 + stage * SLAB_BYTES, n * 16u, 128);
-              const uint64_t ad0 = make_smem_desc(a_base0 + ((uint32_t)k0 >> 3) * (TILE_M * 16), TILE_M * 16, 128);
-              const int ksteps = min(SLAB_K, k_pad - k0) / 16;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t bd = bd0 + (uint64_t)((uint32_t)ks * 2u * n);              // + ks*2*n*16 bytes >> 4
-                const uint64_t ad = ad0 + (uint64_t)((uint32_t)ks * 2u * TILE_M);         // + ks*2*128*16 bytes >> 4
-                const uint32_t acc = (k0 | ks) != 0;
+          if (sequential) {
+            uint32_t st_end = stage, ph_end = phase;
 #pragma unroll
-                for (int u = 0; u < NSUB; ++u)
-                  umma_f16(d0 + (uint32_t)u * 256u, ad + (uint64_t)(u * (sub_stride >> 4)), bd, idesc, acc);
+            for (int u = 0; u < NSUB; ++u) {
+              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; }
+              mbar_wait(&S.acc_empty[u][buf], empty_phase[u][buf] ^ 1, 201);
+              empty_phase[u][buf] ^= 1;
+              tc_fence_after();
+              trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2 + 5 * u);
+              uint32_t st = stage, ph = phase;
+              for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
+                if (u == 0) { mbar_wait(&S.full[st], ph, 202); tc_fence_after(); }
+                issue_slab(u, st, a_base0, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
+                if (++st == NSTAGES) { st = 0; ph ^= 1; }
               }
-              umma_commit(&S.empty[stage]);     // slab consumed when these MMAs retire
+              if (elect_one_sync()) umma_commit(&S.acc_full[u][buf]);
+              __syncwarp();
+              trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3 + 5 * u);
+              st_end = st; ph_end = ph;
+            }
+            stage = st_end; phase = ph_end;
+          } else {
+#pragma unroll
+            for (int u = 0; u < NSUB; ++u) {
+              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; }
+              mbar_wait(&S.acc_empty[u][buf], empty_phase[u][buf] ^ 1, 201);
+              empty_phase[u][buf] ^= 1;
+            }
+            tc_fence_after();
+            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
+            for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
+              mbar_wait(&S.full[stage], phase, 202);
+              tc_fence_after();
+#pragma unroll
+              for (int u = 0; u < NSUB; ++u)
+                issue_slab(u, stage, a_base0, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
+              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int u = 0; u < NSUB; ++u) umma_commit(&S.acc_full[u][buf]);
             }
             __syncwarp();
-            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
           }
-          if (elect_one_sync()) umma_commit(&S.acc_full[buf]);
-          __syncwarp();
-          trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
           ++cc;
         }
       }
@@ -617,7 +710,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) iwae_eval_tc_kernel(EvalArgs a
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.act_ready);
+      if (lane == 0) mbar_arrive(&S.act_ready[u]);
       trace_ev(args, 2, tn, tl * 10000 + 9100);
 
       // ---- layers
@@ -629,14 +722,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) iwae_eval_tc_kernel(EvalArgs a
           // all chunks' MMAs must have retired before the input buffer is overwritten
           for (int c = 0; c < Ly.nchunks; ++c) {
             const uint32_t b = (cc + c) & 1;
-            mbar_wait(&S.acc_full[b], full_phase[b], 300);
+            mbar_wait(&S.acc_full[u][b], full_phase[b], 300);
             full_phase[b] ^= 1;
           }
         }
         for (int c = 0; c < Ly.nchunks; ++c) {
           const uint32_t buf = cc & 1;
           if (!(Ly.inplace && Ly.nchunks > 1)) {
-            mbar_wait(&S.acc_full[buf], full_phase[buf], 301);
+            mbar_wait(&S.acc_full[u][buf], full_phase[buf], 301);
             full_phase[buf] ^= 1;
           }
           tc_fence_after();
@@ -789,14 +882,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) iwae_eval_tc_kernel(EvalArgs a
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&S.acc_empty[buf]);
+          if (lane == 0) mbar_arrive(&S.acc_empty[u][buf]);
           trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 6);
           ++cc;
         }
         if (Ly.signal_act) {
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&S.act_ready);
+          if (lane == 0) mbar_arrive(&S.act_ready[u]);
         }
       }
       if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
@@ -1108,6 +1201,15 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
       fclose(f);
     }
   }
+  return 0;
+}
+
+int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream_t st) {
+  IWAE_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && nctas > 0, "umma_bench: bad argument");
+  const size_t smem = (size_t)(128 + N) * 16 * 2 * 4;
+  CUDA_TRY(cudaFuncSetAttribute(tc::umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::umma_bench_kernel<<<nctas, 128, smem, st>>>(N, reps, nctas, out_cycles_dev);
+  LAUNCH_CHECK();
   return 0;
 }
 
