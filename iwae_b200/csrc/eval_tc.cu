@@ -126,12 +126,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor bit layout):
@@ -265,10 +259,11 @@ constexpr int CHUNK_N_MAX = 112;
 #ifndef IWAE_NSUB
 #define IWAE_NSUB 1
 #endif
-constexpr int NSUB = IWAE_NSUB;                       // 128-row sub-tiles per CTA: 2 = one persistent CTA per SM working
-                                                      // on a 256-row macro-tile, 1 = two independent CTAs per SM
+constexpr int NSUB = IWAE_NSUB;                       // 128-row sub-tiles per CTA: 1 = two independent CTAs per SM (default,
+                                                      // fastest measured), 2 = one persistent CTA per SM on a 256-row macro-tile
+                                                      // whose sub-tiles share every weight slab
 constexpr int CTAS_PER_SM = (NSUB == 2) ? 1 : 2;
-constexpr int NSTAGES = (NSUB == 2) ? 6 : 3;          // weight-slab ring depth (7 KB slabs)
+constexpr int NSTAGES = (NSUB == 2) ? 7 : 3;          // weight-slab ring depth (7 KB slabs)
 constexpr int SLAB_K = 32;
 constexpr int SLAB_BYTES = CHUNK_N_MAX * SLAB_K * 2;   // 7168
 constexpr int KZ_MAX = 112;                            // K capacity of the z1 buffer
@@ -327,18 +322,14 @@ __device__ __forceinline__ void trace_ev(const EvalArgs& a, int role, int& n, in
 
 __constant__ Program c_prog;
 
-struct __align__(16) ImgConsts {     // q(z1|x) (and learned-prior) parameters of one image
-  float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX], ipsd[D_MAX];
-  float cpart[8];              // per-warp partials of sum_j log sd_j - sum_j log psd_j
-  int label; int pad_[3];
-};
 struct __align__(16) SubTile {       // per 128-row sub-tile
   uint8_t bufZ[BUFZ_BYTES];
   uint8_t bufP[BUFP_BYTES];
   float sgn[NX_MAX];           // 1 - 2x per pixel of the sub-tile's image (0 for padded columns); 16-byte aligned
-  ImgConsts cst[2];            // current image and (prefetched) next image
-  float red[8];                // [0,4) max, [4,8) sum-exp
+  float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX], ipsd[D_MAX];
+  float red[16];               // [0,4) max, [4,8) sum-exp, [8,16) per-warp constant partials
   float lwpart[TILE_M];        // partial log-weights of the second column half of each row
+  int label; int pad_[3];
 };
 struct __align__(16) SmemLayout {
   SubTile sub[NSUB];
@@ -410,25 +401,25 @@ __device__ __forceinline__ float4 normal4(uint64_t seed, uint32_t stream_id, uin
   return make_float4(o[0], o[1], o[2], o[3]);
 }
 
-// TMEM -> registers, 8 columns at a time, software-pipelined: the load of this warp's next group is in
-// flight while the current one is processed (tcgen05.wait::ld waits for ALL outstanding loads, so the
-// order is wait(g) -> issue(next) -> process(g)).  This warp's groups are g_first, g_first + 16, ...;
-// the partner warp of the lane quarter takes the others.
+// TMEM -> registers, 16 columns at a time, software-pipelined: the load of this warp's next group is
+// in flight while the current one is processed (tcgen05.wait::ld waits for ALL outstanding loads, so
+// the order is wait(g) -> issue(next) -> process(g)).
 template <class F>
-__device__ __forceinline__ void for_each_8cols(uint32_t taddr, int g_first, int ncols, F&& f) {
+__device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int ncols, F&& f) {
+  // this warp's groups: g_first, g_first+32, ... (the partner warp of the lane quarter takes the others)
   if (g_first >= ncols) return;
-  uint32_t ra[8], rb[8];
-  tmem_ld8(taddr + g_first, ra);
+  uint32_t ra[16], rb[16];
+  tmem_ld16(taddr + g_first, ra);
   tmem_ld_wait();
-  for (int g = g_first; g < ncols; g += 32) {
-    const bool has_b = g + 16 < ncols;
-    if (has_b) tmem_ld8(taddr + g + 16, rb);
+  for (int g = g_first; g < ncols; g += 64) {
+    const bool has_b = g + 32 < ncols;
+    if (has_b) tmem_ld16(taddr + g + 32, rb);
     f(ra, g);
     if (has_b) {
       tmem_ld_wait();
-      const bool has_a = g + 32 < ncols;
-      if (has_a) tmem_ld8(taddr + g + 32, ra);
-      f(rb, g + 16);
+      const bool has_a = g + 64 < ncols;
+      if (has_a) tmem_ld16(taddr + g + 64, ra);
+      f(rb, g + 32);
       if (has_a) tmem_ld_wait();
     }
   }
@@ -441,9 +432,6 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
   const Program& P = c_prog;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_macro = (args.n_tiles + NSUB - 1) / NSUB;
-  // contiguous range of macro-tiles per CTA: consecutive tiles mostly share one image's constants
-  const int64_t mt_begin = n_macro * (int64_t)blockIdx.x / gridDim.x;
-  const int64_t mt_end = n_macro * ((int64_t)blockIdx.x + 1) / gridDim.x;
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
@@ -468,7 +456,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     // region it wraps every such instruction in an ELECT / R2UR / BRA.U.ANY waterfall loop (v3: ~160
     // cycles of issue per MMA, three times the tensor-pipe time of the MMA itself).
     uint32_t stage = 0, phase = 0;
-    for (int64_t mt = mt_begin; mt < mt_end; ++mt) {
+    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x) {
       const uint8_t* src = args.wpack;
       for (int l = 0; l < P.nlayers; ++l) {
         const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad;
@@ -524,7 +512,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       __syncwarp();
     };
 
-    for (int64_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
+    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
       for (int l = 0; l < P.nlayers; ++l) {
         const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act;
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
@@ -586,15 +574,12 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     }
   } else {
     // ===================== epilogue warps =====================
-    // Eight warps per 128-row sub-tile.  Warps e and e+4 share one TMEM lane quarter (one row per lane)
-    // and split the COLUMNS of every accumulator chunk between them in alternating 8-column groups
-    // (equal work for both).  Every log-density term is a sum over columns, so each thread keeps one
-    // partial log-weight; the two halves of a row are added through shared memory at the end of the tile.
-    //
-    // Stage 0 of the NEXT tile (Philox + Box-Muller + reparameterisation: ALU-bound) is interleaved
-    // into the chunks of the current tile's 784-logit layer (MUFU-bound, issue slots to spare); its
-    // z1 buffer is free by then (all MMAs and reads of the current z1 have retired).
-    const int e_warp = warp - 2;             // 0..8*NSUB-1
+    // Sixteen warps: eight per 128-row sub-tile.  Within a sub-tile, warps e and e+4 share one TMEM
+    // lane quarter (one row per lane) and split the COLUMNS of every accumulator chunk between them
+    // (alternating 16-column groups).  Every log-density term is a sum over columns, so each thread
+    // keeps one partial log-weight; the two halves of a row are added through shared memory at the
+    // end of the tile.
+    const int e_warp = warp - 2;             // 0..15
     const int u = e_warp >> 3;               // sub-tile
     const int half = (e_warp >> 2) & 1;      // which half of the column groups this warp takes
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
@@ -607,161 +592,138 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     const int d1 = P.d1, nx = P.nx;
     const int nx_pad = (nx + 15) & ~15;
     const int d1_full = d1 & ~7;             // dims covered by complete 8-wide groups
-    const int one_col = d1 + P.nc;
     int tn = (e_warp == 0 && lane == 0) ? 0 : TRACE_SLOTS, tl = 0;     // only one thread records
 
-    struct TileInfo { int64_t tile, img; int s; bool ok, valid; };
-    auto tile_info = [&](int64_t mt) {
-      TileInfo ti;
-      ti.tile = mt * NSUB + u;
-      ti.ok = ti.tile < args.n_tiles;                 // the last macro-tile may be half empty
-      if (!ti.ok) ti.tile = args.n_tiles - 1;
-      ti.img = ti.tile / args.tiles_per_img;
-      ti.s = (int)(ti.tile % args.tiles_per_img) * args.rows_per_tile + row;     // sample index of this row
-      ti.valid = ti.ok && (row < args.rows_per_tile) && (ti.s < args.k);
-      return ti;
-    };
-    // per-image constants of q(z1|x) (and of a learned prior) into constant set `ci`
-    auto load_consts = [&](int ci, int64_t img) {
-      ImgConsts& C = T.cst[ci];
+    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
+      trace_ev(args, 2, tn, tl * 10000 + 9000);
+      int64_t tile = mt * NSUB + u;
+      const bool tile_ok = tile < args.n_tiles;       // the last macro-tile may be half empty
+      if (!tile_ok) tile = args.n_tiles - 1;
+      const int64_t img = tile / args.tiles_per_img;
+      const int tin = (int)(tile % args.tiles_per_img);
+      const int s = tin * args.rows_per_tile + row;                 // sample index of this row
+      const bool valid = tile_ok && (row < args.rows_per_tile) && (s < args.k);
+
+      // ---- per-image constants into smem
+      epi_bar_sync(u);
+      for (int j = et; j < nx_pad; j += 256)
+        T.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
       float csum = 0.f;
       for (int j = et; j < d1; j += 256) {
         const float sd = __ldg(args.std1 + img * d1 + j);
         const float ls = logf(sd);
-        C.mu[j] = __ldg(args.mu1 + img * d1 + j); C.sd[j] = sd; C.lsd[j] = ls;
+        T.mu[j] = __ldg(args.mu1 + img * d1 + j); T.sd[j] = sd; T.lsd[j] = ls;
         csum += ls;
         if (P.learned_prior) {
           const float ps = __ldg(args.pstd + img * d1 + j);
           const float lps = logf(ps);
-          C.pmu[j] = __ldg(args.pmu + img * d1 + j); C.psd[j] = ps; C.lpsd[j] = lps; C.ipsd[j] = 1.f / ps;
+          T.pmu[j] = __ldg(args.pmu + img * d1 + j); T.psd[j] = ps; T.lpsd[j] = lps; T.ipsd[j] = 1.f / ps;
           csum -= lps;
         }
       }
-      // FAST-mode constant: sum_j log sd_j of q(z1|x) minus that of a learned prior
+      if (FAST) {
+        // constants of the FAST accumulation, once per tile: padded pixel columns each add
+        // softplus(0) = ln 2 to the Bernoulli sum; sum_j log sd_j of q(z1|x) minus that of a learned
+        // prior; the log(2 pi)/2 terms of lq1 and of a first-layer prior cancel, in the two-layer
+        // model lq1's constant has no first-layer N(0,1) partner.
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-      if (lane == 0) C.cpart[e_warp & 7] = csum;
-      if (et == 0 && P.cond) C.label = (int)(unsigned char)(int)__ldg(args.y + img);
-    };
-    // one 8-wide group (A-operand columns k0..k0+7) of stage 0: z1 = mu + std*eps (A.2) | onehot(y) | 1 | 0..
-    // as fp16 into bufZ, and this group's share of -lq(z1|x) + lp(z1) into lw
-    auto stage0_group = [&](const ImgConsts& C, int k0, int s, uint32_t gimg, float& lw) {
-      float v[8];
-      if (FAST && k0 < d1_full) {
-        // complete group of 8 latent dims: no per-element predicates, vector constant loads
-        const float4 na = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2));
-        const float4 nb = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 1u);
-        const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
-        const float4 m0 = *reinterpret_cast<const float4*>(&C.mu[k0]), m1 = *reinterpret_cast<const float4*>(&C.mu[k0 + 4]);
-        const float4 s0 = *reinterpret_cast<const float4*>(&C.sd[k0]), s1 = *reinterpret_cast<const float4*>(&C.sd[k0 + 4]);
-        const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        float e1 = 0.f, z1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i] = fmaf(e[i], ss[i], mm[i]);
-          e1 = fmaf(e[i], e[i], e1);
-        }
-        if (P.learned_prior) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { const float tp = (v[i] - C.pmu[k0 + i]) * C.ipsd[k0 + i]; z1 = fmaf(tp, tp, z1); }
-        } else if (!P.two_layer) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) z1 = fmaf(v[i], v[i], z1);
-        }
-        lw += 0.5f * e1 - 0.5f * z1;          // constants are added once per row at the end of the tile
-      } else {
-#pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int j0 = k0 + 4 * qq;
-          float e[4] = {0.f, 0.f, 0.f, 0.f};
-          if (j0 < d1) {
-            const float4 n4 = normal4<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
-            e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = j0 + i;
-            float val = 0.f;
-            if (j < d1) {
-              const float sd = C.sd[j], m = C.mu[j];
-              const float z = fmaf(e[i], sd, m);
-              if (FAST) {
-                lw = fmaf(0.5f * e[i], e[i], lw);
-                if (P.learned_prior) { const float tp = (z - C.pmu[j]) * C.ipsd[j]; lw = fmaf(-0.5f * tp, tp, lw); }
-                else if (!P.two_layer) lw = fmaf(-0.5f * z, z, lw);
-              } else {
-                const float t = z / sd - m / sd;                         // TFP op order
-                lw -= -0.5f * t * t - (LOG2PI_HALF_F + C.lsd[j]);        // - lq(z1|x)
-                if (!P.two_layer) {
-                  if (P.learned_prior) {
-                    const float ps = C.psd[j];
-                    const float tp = z / ps - C.pmu[j] / ps;
-                    lw += -0.5f * tp * tp - (LOG2PI_HALF_F + C.lpsd[j]);
-                  } else {
-                    lw += -0.5f * z * z - LOG2PI_HALF_F;
-                  }
-                }
-              }
-              val = z;
-            } else if (j < one_col) {
-              val = (C.label == j - d1) ? 1.f : 0.f;
-            } else if (j == one_col) {
-              val = 1.f;
-            }
-            v[4 * qq + i] = val;
-          }
-        }
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        if (lane == 0) T.red[8 + (e_warp & 7)] = csum;
       }
-      store8(T.bufZ, row, k0, v);
-    };
-    const int n_groups = (P.kz_pad - 8 * half + 15) / 16;      // this warp's stage-0 groups: k0 = 8*half + 16*i
-    auto publish_z = [&]() {      // z1 of a tile complete (this warp's part): hand it to the MMA issuer
+      if (et == 0 && P.cond) T.label = (int)(unsigned char)(int)__ldg(args.y + img);
+      epi_bar_sync(u);
+
+      // This thread's partial log-weight: log_w = lpxz + lp(prior terms) - lq(terms), all sums over
+      // columns.  Precise mode adds log-probabilities term by term in TFP's op order; FAST mode
+      // accumulates sums of squares / logs and applies the constants once (algebraically identical:
+      // (z-mu)/sd == eps for a reparameterised sample).
+      float lw = 0.f;
+
+      // ---- stage 0: z1 = mu + std*eps (A.2), lq1, lpz; fp16 z1 | onehot(y) | 1 | 0.. into bufZ
+      {
+        const uint32_t gimg = (uint32_t)(args.img_offset + img);
+        const int one_col = d1 + P.nc;
+        float e1sum = 0.f, z1sum = 0.f;
+        for (int k0 = 8 * half; k0 < P.kz_pad; k0 += 16) {
+          float v[8];
+          if (FAST && k0 < d1_full) {
+            // complete group of 8 latent dims: no per-element predicates, vector constant loads
+            const float4 na = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2));
+            const float4 nb = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 1u);
+            const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+            const float4 m0 = *reinterpret_cast<const float4*>(&T.mu[k0]), m1 = *reinterpret_cast<const float4*>(&T.mu[k0 + 4]);
+            const float4 s0 = *reinterpret_cast<const float4*>(&T.sd[k0]), s1 = *reinterpret_cast<const float4*>(&T.sd[k0 + 4]);
+            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[i] = fmaf(e[i], ss[i], mm[i]);
+              e1sum = fmaf(e[i], e[i], e1sum);
+            }
+            if (P.learned_prior) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const float tp = (v[i] - T.pmu[k0 + i]) * T.ipsd[k0 + i]; z1sum = fmaf(tp, tp, z1sum); }
+            } else if (!P.two_layer) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) z1sum = fmaf(v[i], v[i], z1sum);
+            }
+          } else {
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int j0 = k0 + 4 * qq;
+              float e[4] = {0.f, 0.f, 0.f, 0.f};
+              if (j0 < d1) {
+                const float4 n4 = normal4<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
+                e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j0 + i;
+                float val = 0.f;
+                if (j < d1) {
+                  const float sd = T.sd[j], m = T.mu[j];
+                  const float z = fmaf(e[i], sd, m);
+                  if (FAST) {
+                    e1sum = fmaf(e[i], e[i], e1sum);
+                    if (P.learned_prior) { const float tp = (z - T.pmu[j]) * T.ipsd[j]; z1sum = fmaf(tp, tp, z1sum); }
+                    else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
+                  } else {
+                    const float t = z / sd - m / sd;                         // TFP op order
+                    lw -= -0.5f * t * t - (LOG2PI_HALF_F + T.lsd[j]);        // - lq(z1|x)
+                    if (!P.two_layer) {
+                      if (P.learned_prior) {
+                        const float ps = T.psd[j];
+                        const float tp = z / ps - T.pmu[j] / ps;
+                        lw += -0.5f * tp * tp - (LOG2PI_HALF_F + T.lpsd[j]);
+                      } else {
+                        lw += -0.5f * z * z - LOG2PI_HALF_F;
+                      }
+                    }
+                  }
+                  val = z;
+                } else if (j < one_col) {
+                  val = (T.label == j - d1) ? 1.f : 0.f;
+                } else if (j == one_col) {
+                  val = 1.f;
+                }
+                v[4 * qq + i] = val;
+              }
+            }
+          }
+          store8(T.bufZ, row, k0, v);
+        }
+        if (FAST) lw += 0.5f * e1sum - 0.5f * z1sum;     // constants are added once per row at the end
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.act_ready[u]);
-    };
-
-    // ---- prologue: constants and stage 0 of this CTA's first tile
-    int ci = 0;                  // constant set of the current tile's image
-    float lw_next = 0.f;
-    if (mt_begin < mt_end) {
-      const TileInfo t0 = tile_info(mt_begin);
-      load_consts(0, t0.img);
-      epi_bar_sync(u);
-      for (int i = 0; i < n_groups; ++i)
-        stage0_group(T.cst[0], 8 * half + 16 * i, t0.s, (uint32_t)(args.img_offset + t0.img), lw_next);
-      publish_z();
-    }
-
-    for (int64_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
-      trace_ev(args, 2, tn, tl * 10000 + 9000);
-      const TileInfo ti = tile_info(mt);
-      const bool has_next = mt + 1 < mt_end;
-      const TileInfo tnx = tile_info(has_next ? mt + 1 : mt);
-      const bool next_new_img = has_next && (tnx.img != ti.img);
-      const ImgConsts& Cnext = T.cst[next_new_img ? (ci ^ 1) : ci];
-      float lw = lw_next;        // stage-0 share of this tile, computed during the previous tile
-      lw_next = 0.f;
-
-      // ---- pixel signs of this tile's image (used by the last layer only)
-      epi_bar_sync(u);           // every warp is done with the previous tile's sgn / reductions
-      for (int j = et; j < nx_pad; j += 256)
-        T.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + ti.img * nx + j) : 0.f;
-      // (made visible by the epi_bar_sync inside the last layer, before its first chunk is processed)
+      trace_ev(args, 2, tn, tl * 10000 + 9100);
 
       // ---- layers
       float bern_s = 0.f, bern_a = 0.f, bern_lg = 0.f;     // FAST Bernoulli accumulators (log2 units)
       for (int l = 0; l < P.nlayers; ++l) {
         const Layer& Ly = P.L[l];
         uint8_t* dst = Ly.dst ? T.bufP : T.bufZ;
-        const bool last = (Ly.kind == EPI_BERN);
-        if (last) {
-          // all eight warps have finished every earlier layer's reads of z1 once the issuer could start
-          // this layer; load the next image's constants (if it changes) while waiting for its first chunk
-          if (next_new_img) load_consts(ci ^ 1, tnx.img);
-          epi_bar_sync(u);
-        }
         if (Ly.inplace && Ly.nchunks > 1) {
           // all chunks' MMAs must have retired before the input buffer is overwritten
           for (int c = 0; c < Ly.nchunks; ++c) {
@@ -780,22 +742,22 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 5);
           const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(u * 2 + buf) * 128u;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
-          const int g_first = 8 * half;          // this warp's 8-column groups: g_first, g_first + 16, ...
+          const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
 
           if (Ly.kind == EPI_TANH) {
             // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
             // bias 30 (tanh(30) == 1.0f): no per-element special cases
-            for_each_8cols(tbase, g_first, cn, [&](const uint32_t (&r)[8], int g) {
-              float v[8];
+            for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
+              float v[16];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
-              store8(dst, row, off + g, v);
+              for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
+              store16(dst, row, off + g, v);
             });
           } else if (Ly.kind == EPI_GSAMPLE) {
             // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8]
             // (FAST: the log-std head is pre-scaled by log2(e) at pack time).
             // z2 = mu2 + std2*eps2 (iwae2.py:65); one 16-byte A-operand row segment per group.
-            const uint32_t gimg = (uint32_t)(args.img_offset + ti.img);
+            const uint32_t gimg = (uint32_t)(args.img_offset + img);
             float e2sum = 0.f, z2sum = 0.f, lgsum = 0.f;
             for (int g8 = 8 * half; g8 < Ly.next_kpad; g8 += 16) {
               float v[8];
@@ -805,7 +767,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                 tmem_ld_wait();
 #pragma unroll
                 for (int qq = 0; qq < 2; ++qq) {
-                  const float4 n4 = normal4<FAST>(args.seed, 2u, gimg, (uint32_t)ti.s, (uint32_t)((off + g8) >> 2) + qq);
+                  const float4 n4 = normal4<FAST>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2) + qq);
                   const float e[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
@@ -892,13 +854,13 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
             //   softplus(s) = max(s,0) + log(1 + e^-|s|),  max(s,0) = (s + |l|)/2,  |s| = |l|
             // FAST: the accumulators hold l' = l*log2(e) (folded into W3/b3 at pack time), so the
             // exponential is a bare ex2 of -|l'| and the sign only enters through one FFMA; the logs
-            // are batched: one lg2 per <= 28 factors (1 + 2^-|l'|) in (1, 2].
+            // are batched: one lg2 per <= 32 factors (1 + 2^-|l'|) in (1, 2].
             if (FAST) {
               float p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
-              for_each_8cols(tbase, g_first, cn, [&](const uint32_t (&r)[8], int g) {
+              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
                 const float4* sg4 = reinterpret_cast<const float4*>(&T.sgn[off + g]);
 #pragma unroll
-                for (int i4 = 0; i4 < 2; ++i4) {
+                for (int i4 = 0; i4 < 4; ++i4) {
                   const float4 sg = sg4[i4];
                   const float l0 = __uint_as_float(r[4 * i4]), l1 = __uint_as_float(r[4 * i4 + 1]);
                   const float l2 = __uint_as_float(r[4 * i4 + 2]), l3 = __uint_as_float(r[4 * i4 + 3]);
@@ -912,9 +874,9 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
               bern_lg += lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
             } else {
               float acc = 0.f;
-              for_each_8cols(tbase, g_first, cn, [&](const uint32_t (&r)[8], int g) {
+              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 16; ++i) {
                   const float lgt = __uint_as_float(r[i]);
                   const float sg = T.sgn[off + g + i];
                   // padded columns (sgn 0, logit 0) must contribute nothing
@@ -929,12 +891,6 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           if (lane == 0) mbar_arrive(&S.acc_empty[u][buf]);
           trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 6);
           ++cc;
-          if (last && has_next) {
-            // a slice of the next tile's stage 0 between two chunks of the 784-logit layer
-            const int per = (n_groups + Ly.nchunks - 1) / Ly.nchunks;
-            for (int i = c * per; i < min(n_groups, (c + 1) * per); ++i)
-              stage0_group(Cnext, 8 * half + 16 * i, tnx.s, (uint32_t)(args.img_offset + tnx.img), lw_next);
-          }
         }
         if (Ly.signal_act) {
           fence_proxy_async();
@@ -942,7 +898,6 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           if (lane == 0) mbar_arrive(&S.act_ready[u]);
         }
       }
-      if (has_next) publish_z();
       if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
 
       // ---- combine the two column halves of each row, then the tile's (max, sum exp) partial
@@ -951,15 +906,12 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       if (half == 0) {
         lw += T.lwpart[row];
         if (FAST) {
-          // constants of the FAST accumulation: padded pixel columns each add softplus(0) = ln 2 to the
-          // Bernoulli sum; sum_j log sd_j of q(z1|x) minus that of a learned prior; the log(2 pi)/2 terms of
-          // lq1 and of a first-layer prior cancel, in the two-layer model lq1's has no first-layer partner
           float c0 = (float)(nx_pad - nx) * LN2_F + (P.two_layer ? (float)d1 * LOG2PI_HALF_F : 0.f);
 #pragma unroll
-          for (int w = 0; w < 8; ++w) c0 += T.cst[ci].cpart[w];
+          for (int w = 0; w < 8; ++w) c0 += T.red[8 + w];
           lw += c0;
         }
-        if (!ti.valid) lw = -INFINITY;
+        if (!valid) lw = -INFINITY;
       }
       float mx = (half == 0) ? lw : -INFINITY;
 #pragma unroll
@@ -967,13 +919,12 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       if (lane == 0 && half == 0) T.red[q] = mx;
       epi_bar_sync(u);
       mx = fmaxf(fmaxf(T.red[0], T.red[1]), fmaxf(T.red[2], T.red[3]));
-      float se = (half == 0 && ti.valid) ? expf(lw - mx) : 0.f;
+      float se = (half == 0 && valid) ? expf(lw - mx) : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
       if (lane == 0 && half == 0) T.red[4 + q] = se;
       epi_bar_sync(u);
-      if (et == 0 && ti.ok) args.partial[ti.tile] = make_float2(mx, T.red[4] + T.red[5] + T.red[6] + T.red[7]);
-      if (next_new_img) ci ^= 1;
+      if (et == 0 && tile_ok) args.partial[tile] = make_float2(mx, T.red[4] + T.red[5] + T.red[6] + T.red[7]);
     }
   }
 
