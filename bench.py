@@ -87,6 +87,11 @@ def cpu_llh_pass(params32, X, k, layers, torch, oracle, gen):
 
 def cpu_setup(args):
     import torch
+    # torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     from oracle import iwae_oracle as oracle
     P, X = synthetic(max(args.ref_images, 1000))
     rs = np.random.RandomState(123)
