@@ -1,0 +1,20 @@
+#!/bin/bash
+# Full evidence package for one kernel version: tests, bench, launch lists, ncu capture, timeline.
+mkdir -p gpurun_out
+echo "== pytest -m gpu" ; timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/test_gpu.log 2>&1 ; echo "rc=$?" ; tail -n 4 gpurun_out/test_gpu.log
+echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1 ; echo "rc=$?" ; tail -n 2 gpurun_out/smoke.log
+echo "== full bench" ; timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err ; echo "rc=$?" ; tail -n 2 gpurun_out/bench_full.err
+echo "== reference arm" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ; echo "rc=$?"
+echo "== ncu launch list (eval)"
+timeout 300 python bench.py --images 1000 --steps 2 --warmup 1 --no-train --no-cpu-baseline > gpurun_out/plain_launches.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --images 1000 --steps 2 --warmup 1 --no-train --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1 ; echo "rc=$?"
+echo "== ncu launch list (train)"
+timeout 300 python scripts/train_probe.py 20 > gpurun_out/train_probe.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 200 --csv --log-file gpurun_out/launches_train.csv \
+    python scripts/train_probe.py 20 > gpurun_out/ncu_launches_train.log 2>&1 ; echo "rc=$?" ; cat gpurun_out/train_probe.log
+echo "== ncu full capture"
+timeout 300 python scripts/prof_eval.py --images 592 --reps 2 > gpurun_out/plain_prof.log 2>&1 && \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:iwae_eval_tc_kernel -s 1 -c 1 -f -o gpurun_out/prof_eval \
+    python scripts/prof_eval.py --images 592 --reps 2 > gpurun_out/ncu_full.log 2>&1 ; echo "rc=$?" ; cat gpurun_out/plain_prof.log
+IWAE_TC_TRACE=gpurun_out/trace.txt timeout 300 python scripts/prof_eval.py --images 592 --reps 1 > gpurun_out/trace_run.log 2>&1; echo "trace rc=$?"

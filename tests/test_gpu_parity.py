@@ -290,3 +290,38 @@ def test_decoder_tools(oracle):
     assert zz.shape == (4, 2, 2)
     probs, xs = m.sample(z[:, 0])
     assert probs.shape == (9, 784) and set(np.unique(xs.numpy())) <= {0.0, 1.0}
+
+
+def test_val_step_full_test_set_shape(oracle):
+    """val_step on a test-set-sized batch (main.py:152: all test images at k=n_samples).  B=2,000 here keeps
+    the fp64 oracle to seconds; the kernels are the same at B=10,000."""
+    B, k = 2000, 20
+    P, X, _ = oracle.synthetic_data(B, seed=7)
+    rs = np.random.RandomState(3)
+    shapes = oracle.param_shapes("iwae2", [200, 100], [100, 50])
+    params = oracle.glorot_params(shapes, rs, out_bias=oracle.get_bias(P.mean(0)), scale=0.5)
+    import iwae_b200 as ib
+    m = ib.IWAE2([200, 100], [100, 50])
+    m.set_weights(params)
+    eps1 = rs.randn(k, B, 100).astype(np.float32)
+    eps2 = rs.randn(k, B, 50).astype(np.float32)
+    res = m.val_step(X, k, 1.0) if False else m(X, k, 1.0, eps=eps1, eps2=eps2)
+    p = oracle.to_torch(params)
+    ref = oracle.iwae2_call(p, torch.tensor(X, dtype=torch.float64), k, 1.0, torch.tensor(eps1, dtype=torch.float64),
+                            torch.tensor(eps2, dtype=torch.float64))
+    for key in ("vae_elbo", "iwae_elbo", "iwae_eq14"):
+        assert rel(float(res[key]), float(ref[key])) < RTOL, key
+    assert rel(res["iwae_elbo_per_example"].numpy(), ref["iwae_elbo_per_example"].numpy()) < RTOL
+    assert res["lpxz1"].shape == (k, B) and res["snis_z1"].shape == (B, 100)
+    # the monitoring call itself (Philox noise) runs and returns finite scalars
+    mon = m.val_step(X, k, 1.0)
+    assert np.isfinite(float(mon["iwae_elbo"])) and float(mon["iwae_elbo"]) > float(mon["vae_elbo"])
+
+
+def test_sharded_eval_single_rank(oracle):
+    """iwae_b200.dist.model_llh_sharded without a process group == one rank: mean of the per-example LLH."""
+    from iwae_b200.dist import model_llh_sharded
+    case = make_case(oracle, "iwae2", [200, 100], [100, 50], 6, 1, seed=71)
+    m = build("iwae2", dict(h=[200, 100], d=[100, 50]), case)
+    mean, per = model_llh_sharded(m, case["x"], 200, precision="tc_f16_fast", seed=5)
+    assert per.shape == (6,) and abs(float(mean) - float(per.double().mean())) < 1e-9 * abs(float(mean))
