@@ -57,12 +57,16 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU.  The watchdog clock is
-// read only every 4096 polls so that waiting warps spend as few issue slots as possible.
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
+// Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU.
+// The waiting warp SLEEPS between polls (nanosleep): ncu showed that the hardware-suspended try_wait
+// returns early whenever any mbarrier of the CTA changes, so a free-running poll loop of the producer
+// warp alone executed 42 % of all instructions of the kernel and took issue slots from the epilogue
+// warps of its SM sub-partition - whose rows then finish every layer last.
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns) {
   uint64_t t0 = 0;
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
     if ((++polls & 0xFFFu) == 0) {
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
@@ -73,9 +77,11 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int 
     }
   }
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+// sleep_ns: poll period once the first (hardware-suspended) try_wait has failed - short for waits on the
+// critical path (MMA issuer, epilogue), long for the weight producer, which runs ahead of its consumer
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns = 32) {
   if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow(bar, parity, tag);
+  mbar_wait_slow(bar, parity, tag, sleep_ns);
 }
 // One lane of a fully converged warp (the same lane every time): PTX elect.sync.
 __device__ __forceinline__ uint32_t elect_one_sync() {
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           const uint32_t cn = (uint32_t)P.L[l].chunk_n[c];
           for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
             const uint32_t bytes = cn * (uint32_t)min(SLAB_K, k_pad - k0) * 2u;
-            mbar_wait(&S.empty[stage], phase ^ 1, 100);
+            mbar_wait(&S.empty[stage], phase ^ 1, 100, 200);
             if (elect_one_sync()) {
               mbar_expect_tx(&S.full[stage], bytes);
               bulk_g2s(S.ring[stage], src, bytes, &S.full[stage]);
