@@ -302,8 +302,13 @@ def run_ours(args):
         kms = float(np.mean(kernel_ms))
         flop_row = FLOP_PER_ROW_2L if args.layers == 2 else FLOP_PER_ROW_1L
         ach = (b - a) * args.k * flop_row / (kms * 1e-3) / 1e12
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of this kernel on the default
+        # single-GPU workload, from the ncu capture committed as profiles/r01_v5_ncu_traffic_full_launch.csv;
+        # other workloads were not captured
+        traffic = 40567040 + 34816 if (world == 1 and args.images == 10000 and args.k == 5000 and args.layers == 2) else None
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                           "traffic": None, "kernel": "tc::iwae_eval_tc_kernel", "kernel_ms": kms,
+                           "traffic": traffic, "traffic_unit": "bytes/launch (DRAM; L2->SM weight streaming is 221 GB/launch)",
+                           "kernel": "tc::iwae_eval_tc_kernel", "kernel_ms": kms,
                            "kernel_share_of_step": kms / (ms_total / args.steps),
                            "flop_per_row": flop_row, "rows_per_launch": (b - a) * args.k, "peak_source": which,
                            "note": "fp16 operands; peak is the measured dense bf16 cuBLAS figure (same tensor rate)"}
