@@ -193,6 +193,7 @@ static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ld
   g.C = Y; g.ldc = L.n_out;
   g.M = (int)M; g.N = L.n_out; g.K = L.n_in;
   g.bias = P + L.b; g.act = act;
+  g.small_tile = (((M + 63) / 64) * ((L.n_out + 63) / 64) < 100) ? 1 : 0;
   return gemm_f32(g, st);
 }
 
@@ -435,6 +436,13 @@ extern "C" int iwae_llh_eval_host(iwae_ctx* ctx, const float* params, const floa
 // ---------------------------------------------------------------------------------------------
 // backward (fp32 path)
 // ---------------------------------------------------------------------------------------------
+// Parameter gradients are produced as GRAD_SPLITS partial sums over the rows (split-K): a weight gradient
+// dW = X^T dY has few output tiles (100x100 .. 200x784) but a long reduction (k*B = 1,000 rows), so the
+// row range is split over gridDim.z to fill the SMs.  `grads` points to slice 0 of a zeroed
+// [GRAD_SPLITS][n_params] workspace; grad_reduce / adam_from_partials sum the slices in a fixed order.
+constexpr int GRAD_SPLITS = 8;
+static int g_grad_stride = 0;      // n_params of the model whose backward is running (slice stride)
+
 // dW = X^T dY, db = colsum(dY)
 static int dense_bwd_w(const DenseP& L, const float* X, int64_t ldx, int64_t M, const float* dY, float* grads,
                        cudaStream_t st) {
@@ -444,8 +452,12 @@ static int dense_bwd_w(const DenseP& L, const float* X, int64_t ldx, int64_t M, 
   g.C = grads + L.w; g.ldc = L.n_out;
   g.M = L.n_in; g.N = L.n_out; g.K = (int)M;
   g.small_tile = 1;
+  const int tiles = ((L.n_in + 31) / 32) * ((L.n_out + 31) / 32);
+  int split = std::min<int>(GRAD_SPLITS, (296 + tiles - 1) / tiles);
+  split = (int)std::max<int64_t>(1, std::min<int64_t>(split, M / 64));     // at least 64 rows per slice
+  g.split_k = split; g.split_stride = g_grad_stride;
   IWAE_TRY(gemm_f32(g, st));
-  return colsum_f32(dY, L.n_out, (int)M, L.n_out, grads + L.b, st);
+  return colsum_f32(dY, L.n_out, (int)M, L.n_out, grads + L.b, st, GRAD_SPLITS, g_grad_stride);
 }
 // dX = dY W^T, optionally accumulated into dX and/or multiplied by tanh'(H) = 1 - H^2
 static int dense_bwd_x(const float* P, const DenseP& L, const float* dY, int64_t M, float* dX, int64_t ld_dx,
@@ -456,6 +468,7 @@ static int dense_bwd_x(const float* P, const DenseP& L, const float* dY, int64_t
   g.C = dX; g.ldc = ld_dx;
   g.M = (int)M; g.N = L.n_in; g.K = L.n_out;
   g.accumulate = accumulate; g.mul_h = H; g.ld_h = ld_h;
+  g.small_tile = (((M + 63) / 64) * ((L.n_in + 63) / 64) < 100) ? 1 : 0;
   return gemm_f32(g, st);
 }
 
@@ -541,11 +554,14 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
   return 0;
 }
 
+struct AdamArgs { float *params, *m, *v; float lr, b1, b2, eps; int64_t t; };
+
 static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, const float* y, int B, int k, float beta,
                           int objective, int B_norm, const float* eps1, const float* eps2, uint64_t seed,
-                          int64_t img_offset, float* grads, const iwae_outputs* outs, cudaStream_t st) {
+                          int64_t img_offset, float* grads, const iwae_outputs* outs, cudaStream_t st,
+                          const AdamArgs* adam = nullptr) {
   const ModelP& m = ctx->model;
-  IWAE_REQUIRE(grads, "iwae_grads: null grads");
+  IWAE_REQUIRE(grads || adam, "iwae_grads: null grads");
   IWAE_REQUIRE(objective >= IWAE_OBJ_VAE_ELBO && objective <= IWAE_OBJ_DREG, "unknown objective %d", objective);
   // iwae2.IWAE.call has no 'vae_elbo_kl' key -> KeyError in the reference (iwae2.py:154-167,173)
   IWAE_REQUIRE(!(m.two_layer() && objective == IWAE_OBJ_VAE_ELBO_KL), "KeyError: 'vae_elbo_kl' (two stochastic layers)");
@@ -555,7 +571,16 @@ static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, co
   opt.keep_for_bwd = true;
   opt.want_dreg = (objective == IWAE_OBJ_DREG);
   IWAE_TRY(forward_internal(ctx, params, x, y, B, k, beta, eps1, eps2, seed, img_offset, outs, opt, f, st));
-  return backward_internal(ctx, params, f, beta, objective, B_norm, grads, st);
+  // backward into the zeroed [GRAD_SPLITS][n_params] workspace, then one fixed-order reduction
+  float* ws;
+  const int64_t n = m.n_params;
+  IWAE_TRY(ctx->arena.get(&ws, (size_t)GRAD_SPLITS * n));
+  CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(float) * GRAD_SPLITS * n, st));
+  g_grad_stride = (int)n;
+  IWAE_TRY(backward_internal(ctx, params, f, beta, objective, B_norm, ws, st));
+  if (adam) return adam_from_partials(adam->params, ws, GRAD_SPLITS, adam->m, adam->v, n, adam->lr, adam->b1, adam->b2,
+                                      adam->eps, adam->t, st);
+  return grad_reduce(ws, GRAD_SPLITS, n, grads, st);
 }
 
 extern "C" int iwae_grads(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,
@@ -581,10 +606,9 @@ extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, floa
   IWAE_REQUIRE(ctx && params && adam_m && adam_v, "iwae_train_step: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   ctx->arena.reset();
-  float* grads;
-  IWAE_TRY(ctx->arena.get(&grads, (size_t)ctx->model.n_params));
-  IWAE_TRY(grads_internal(ctx, params, x, y, B, k, beta, objective, B, eps1, eps2, seed, img_offset, grads, outs, st));
-  return adam_f32(params, grads, adam_m, adam_v, ctx->model.n_params, lr, beta1, beta2, adam_eps, t, st);
+  IWAE_REQUIRE(t >= 1, "iwae_train_step: t is the step count after increment (>= 1)");
+  AdamArgs ad = {params, adam_m, adam_v, lr, beta1, beta2, adam_eps, t};
+  return grads_internal(ctx, params, x, y, B, k, beta, objective, B, eps1, eps2, seed, img_offset, nullptr, outs, st, &ad);
 }
 
 extern "C" int iwae_philox_normal(uint64_t seed, int32_t stream_id, int64_t img_offset, int32_t B, int32_t k, int32_t d,

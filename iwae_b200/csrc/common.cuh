@@ -104,11 +104,14 @@ struct GemmArgs {
   const float* bern_x = nullptr; int bern_B = 0;          // fused Bernoulli log-lik: x[(m % B), n]
   float* bern_partial = nullptr;                          // [M, n_tiles_n] partial row sums
   int small_tile = 0;                                     // 32x32 tiles (more CTAs for skinny outputs)
+  int split_k = 1;                                        // >1: gridDim.z partial products, C + z*split_stride (plain products only)
+  int64_t split_stride = 0;
 };
 int gemm_f32(const GemmArgs& a, cudaStream_t st);
 int gemm_f32_ntiles_n(int N, int small_tile);
 
-int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st);
+int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st, int splits = 1,
+               int64_t split_stride = 0);   // splits > 1: per-row-range partial sums at out + s*split_stride
 int concat_onehot(const float* x, int64_t ldx, int n, const float* y, int B, int rows, int nc,
                   float* out, cudaStream_t st);   // out[r] = [x[r, :n] | onehot(y[r % B])]
 int onehot_f32(const float* y, int B, int nc, float* out, cudaStream_t st);
@@ -136,6 +139,7 @@ struct LogwArgs {
   const float *z1 = nullptr, *z2 = nullptr; int d1 = 0, d2 = 0;
   float *log_w = nullptr, *al = nullptr, *iwae = nullptr, *vae = nullptr, *eq14 = nullptr, *dreg = nullptr;
   float *snis1 = nullptr, *snis2 = nullptr;
+  int al_in_smem = 0;                       // set by logw_reduce
 };
 int logw_reduce(const LogwArgs& a, cudaStream_t st);
 struct ScalarArgs {
@@ -171,6 +175,9 @@ int latent2_bwd(const Latent2BwdArgs& a, cudaStream_t st);
 int gauss_rows_bwd(const float* g, const float* z, const float* pmu, const float* pstd, int64_t R, int d,
                    float* dpmu, float* dpa, cudaStream_t st);
 
+int grad_reduce(const float* ws, int splits, int64_t n, float* grads, cudaStream_t st);
+int adam_from_partials(float* p, const float* ws, int splits, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                       float eps, int64_t t, cudaStream_t st);
 int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
              float eps, int64_t t, cudaStream_t st);
 int bernoulli_sample_f32(const float* p, int64_t n, uint64_t seed, uint64_t epoch, float* out, cudaStream_t st);

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "rng.cuh"
 #include <math.h>
+#include <algorithm>
 
 // =============================================================================================
 // Tiled SGEMM with fused epilogues.  C(m,n) = epi( sum_k A(m,k) B(k,n) ).
@@ -10,25 +11,27 @@
 // mapping that walks the unit-stride dimension so global loads stay coalesced in all three.
 // =============================================================================================
 template <int BM, int BN, int TM, int TN>
-struct GemmCfg {
-  static constexpr int BK = 16;
-  static constexpr int THREADS = (BM / TM) * (BN / TN);
-};
-
-template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_f32_kernel(GemmArgs a) {
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int TX = BN / TN;   // threads along n
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+  constexpr int EA = BM * BK / NT, EB = BN * BK / NT;   // elements of the A / B tile each thread stages
+  static_assert(EA * NT == BM * BK && EB * NT == BN * BK, "tile must divide evenly among the threads");
+  // double-buffered tiles: global -> registers (next tile) overlaps the FFMAs on the current tile
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
 
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;   // M tiles on x (no 65535 limit)
   const bool a_kcontig = (a.sa_k == 1);
   const bool b_ncontig = (a.sb_n == 1);
+  // split-K: blockIdx.z owns K range [k_begin, k_end) and writes its partial tile to C + z * split_stride
+  const int k_chunk = (a.split_k > 1) ? ((a.K + a.split_k - 1) / a.split_k + BK - 1) / BK * BK : a.K;
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(a.K, k_begin + k_chunk);
+  float* __restrict__ Cout = a.C ? a.C + (size_t)blockIdx.z * a.split_stride : nullptr;
 
   float acc[TM][TN];
 #pragma unroll
@@ -36,39 +39,66 @@ gemm_f32_kernel(GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < a.K; k0 += BK) {
-    // ---- A tile
-    for (int e = tid; e < BM * BK; e += NT) {
+  float ra[EA], rb[EB];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < EA; ++i) {
+      const int e = tid + i * NT;
       int mm, kk;
       if (a_kcontig) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
       const int gm = m0 + mm, gk = k0 + kk;
-      float v = 0.f;
-      if (gm < a.M && gk < a.K) v = __ldg(a.A + (int64_t)gm * a.sa_m + (int64_t)gk * a.sa_k);
-      As[kk][mm] = v;
+      ra[i] = (gm < a.M && gk < k_end) ? __ldg(a.A + (int64_t)gm * a.sa_m + (int64_t)gk * a.sa_k) : 0.f;
     }
-    // ---- B tile
-    for (int e = tid; e < BN * BK; e += NT) {
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      const int e = tid + i * NT;
       int nn, kk;
       if (b_ncontig) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
       const int gn = n0 + nn, gk = k0 + kk;
-      float v = 0.f;
-      if (gn < a.N && gk < a.K) v = __ldg(a.B + (int64_t)gk * a.sb_k + (int64_t)gn * a.sb_n);
-      Bs[kk][nn] = v;
+      rb[i] = (gn < a.N && gk < k_end) ? __ldg(a.B + (int64_t)gk * a.sb_k + (int64_t)gn * a.sb_n) : 0.f;
     }
-    __syncthreads();
+  };
+  auto store_tile = [&](int buf) {
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      float av[TM], bv[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    for (int i = 0; i < EA; ++i) {
+      const int e = tid + i * NT;
+      int mm, kk;
+      if (a_kcontig) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
+      As[buf][kk][mm] = ra[i];
     }
+#pragma unroll
+    for (int i = 0; i < EB; ++i) {
+      const int e = tid + i * NT;
+      int nn, kk;
+      if (b_ncontig) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
+      Bs[buf][kk][nn] = rb[i];
+    }
+  };
+
+  if (k_begin < k_end) {
+    load_tile(k_begin);
+    store_tile(0);
     __syncthreads();
+    int buf = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+      const bool more = k0 + BK < k_end;
+      if (more) load_tile(k0 + BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float av[TM], bv[TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) av[i] = As[buf][kk][ty * TM + i];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][kk][tx * TN + j];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (more) store_tile(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 
   // ---- epilogue
@@ -84,12 +114,12 @@ gemm_f32_kernel(GemmArgs a) {
         if (a.bias) v += __ldg(a.bias + gn);
         if (a.act == ACT_TANH) v = tanhf(v);
         else if (a.act == ACT_EXP_EPS) v = expf(v) + 1e-6f;
-        if (a.accumulate) v += a.C[(int64_t)gm * a.ldc + gn];
+        if (a.accumulate) v += Cout[(int64_t)gm * a.ldc + gn];
         if (a.mul_h) {
           const float h = __ldg(a.mul_h + (int64_t)gm * a.ld_h + gn);
           v *= (1.f - h * h);
         }
-        if (a.C) a.C[(int64_t)gm * a.ldc + gn] = v;
+        if (Cout) Cout[(int64_t)gm * a.ldc + gn] = v;
         if (a.bern_x) {
           // tfd.Bernoulli(logits).log_prob(x) = -(1-x) softplus(l) - x softplus(-l)   (A.3)
           const float xv = __ldg(a.bern_x + (int64_t)(gm % a.bern_B) * a.N + gn);
@@ -111,11 +141,14 @@ int gemm_f32_ntiles_n(int N, int small_tile) { return small_tile ? (N + 31) / 32
 
 int gemm_f32(const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return 0;
+  const int z = a.split_k > 1 ? a.split_k : 1;
+  IWAE_REQUIRE(z == 1 || (!a.bias && a.act == ACT_NONE && !a.accumulate && !a.mul_h && !a.bern_x),
+               "gemm_f32: split-K supports plain products only");
   if (a.small_tile) {
-    dim3 grid((a.M + 31) / 32, (a.N + 31) / 32);
+    dim3 grid((a.M + 31) / 32, (a.N + 31) / 32, z);
     gemm_f32_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(a);
   } else {
-    dim3 grid((a.M + 63) / 64, (a.N + 63) / 64);
+    dim3 grid((a.M + 63) / 64, (a.N + 63) / 64, z);
     gemm_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);
   }
   LAUNCH_CHECK();
@@ -125,24 +158,29 @@ int gemm_f32(const GemmArgs& a, cudaStream_t st) {
 // =============================================================================================
 // Small elementwise / reduction kernels
 // =============================================================================================
-__global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, int N, float* __restrict__ out) {
-  // one warp-wide strip of 32 columns per block.x; blockDim = (32, 8): 8 row-lanes then smem reduce
+__global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, int N, float* __restrict__ out,
+                              int64_t split_stride) {
+  // one strip of 32 columns per blockIdx.x, one row range per blockIdx.y (partial sum -> out + y*split_stride);
+  // blockDim = (32, 8): 8 row-lanes then an smem reduce in a fixed order
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
   float s = 0.f;
   if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += A[(int64_t)m * lda + n];
+    for (int m = r0 + threadIdx.y; m < r1; m += 8) s += A[(int64_t)m * lda + n];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[n] = t;
+    out[(int64_t)blockIdx.y * split_stride + n] = t;
   }
 }
-int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st) {
-  colsum_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(A, lda, M, N, out);
+int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st, int splits, int64_t split_stride) {
+  if (splits < 1 || M < 64 * splits) splits = 1;
+  colsum_kernel<<<dim3((N + 31) / 32, splits), dim3(32, 8), 0, st>>>(A, lda, M, N, out, split_stride);
   LAUNCH_CHECK();
   return 0;
 }
@@ -340,6 +378,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 
 __global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
   __shared__ float red[8];
+  extern __shared__ float s_al[];      // normalised weights of this image when k fits (a.al_in_smem)
   const int b = blockIdx.x, B = a.B, k = a.k;
   // pass 1: log_w and its max
   float mx = -INFINITY, sm = 0.f;
@@ -377,12 +416,14 @@ __global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
                            : a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);
     const float w = expf(lw - mx) / se;
     if (a.al) a.al[r] = w;
+    if (a.al_in_smem) s_al[s] = w;
     e14 += w * lw;
     if (a.dreg) dr += w * w * (a.lpz[r] + a.lpxz[r] - a.lq_stopped[r]);                // task02.py:70-73
   }
   if (a.eq14) { e14 = block_reduce(e14, red, false); if (threadIdx.x == 0) a.eq14[b] = e14; }
   if (a.dreg) { dr = block_reduce(dr, red, false); if (threadIdx.x == 0) a.dreg[b] = dr; }
   // pass 4: snis_z = sum_k al * z  (thread per latent dim, coalesced over the dim)
+  __syncthreads();
   for (int which = 0; which < 2; ++which) {
     float* out = which ? a.snis2 : a.snis1;
     const float* z = which ? a.z2 : a.z1;
@@ -392,17 +433,24 @@ __global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
       float acc = 0.f;
       for (int s = 0; s < k; ++s) {
         const int64_t r = (int64_t)s * B + b;
-        float lw = a.two_layer ? a.lpxz[r] + a.lp12[r] + a.lpz[r] - a.lq1[r] - a.lq2[r]
-                               : a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);
-        acc += (expf(lw - mx) / se) * z[r * d + j];
+        float w;
+        if (a.al_in_smem) w = s_al[s];
+        else {
+          float lw = a.two_layer ? a.lpxz[r] + a.lp12[r] + a.lpz[r] - a.lq1[r] - a.lq2[r]
+                                 : a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);
+          w = expf(lw - mx) / se;
+        }
+        acc += w * z[r * d + j];
       }
       out[(int64_t)b * d + j] = acc;
     }
   }
 }
-int logw_reduce(const LogwArgs& a, cudaStream_t st) {
-  if (a.B == 0) return 0;
-  logw_reduce_kernel<<<a.B, 256, 0, st>>>(a);
+int logw_reduce(const LogwArgs& a0, cudaStream_t st) {
+  if (a0.B == 0) return 0;
+  LogwArgs a = a0;
+  a.al_in_smem = (a.k <= 10240 && (a.snis1 || a.snis2)) ? 1 : 0;
+  logw_reduce_kernel<<<a.B, 256, a.al_in_smem ? sizeof(float) * a.k : 0, st>>>(a);
   LAUNCH_CHECK();
   return 0;
 }
@@ -496,67 +544,83 @@ int dlogits_f32(const float* logits, const float* x, const float* g, int R, int 
   return 0;
 }
 
-// First stochastic layer.  One thread per (b, j), looping over the k samples (fixed order).
+// First stochastic layer.  One CTA per image; thread (ks, j) sums dim j over the samples s = ks, ks+KS, ...
+// and the KS partial sums are added in a fixed order through shared memory.
 // Uses the total-derivative identities of A.4: d lq/d mu = 0, d lq/d std = -1/std.
-__global__ void latent1_bwd_kernel(Latent1BwdArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.B * a.d) return;
-  const int b = idx / a.d, j = idx % a.d;
-  const float mu = a.mu[idx], sd = a.std[idx];
+__global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
+  __shared__ float red[4][256];
+  const int b = blockIdx.x;
+  const int KS = max(1, 256 / a.d);                 // sample slices handled in parallel
+  const int dpad = (a.d + 0);
+  const int j = threadIdx.x % dpad, ks = threadIdx.x / dpad;
+  const bool active = threadIdx.x < KS * a.d && KS * a.d <= 256;
   const bool dreg = (a.objective == IWAE_OBJ_DREG);
   const bool klobj = (a.objective == IWAE_OBJ_VAE_ELBO_KL);
   float acc_mu = 0.f, acc_sd = 0.f, acc_pmu = 0.f, acc_psd = 0.f;
-  for (int s = 0; s < a.k; ++s) {
-    const int64_t r = (int64_t)s * a.B + b;
-    const float g = a.g[r];
-    const float z = a.z[r * a.d + j], e = a.eps[r * a.d + j];
-    float dz = a.dz_dec[r * a.ld_dz + j];
-    if (a.dz_q2) dz += a.dz_q2[r * a.d + j];
-    if (dreg) {
-      // task02.py:60-76: encoder signal = al * (decoder-path dz) - (al^2/B) * d(lpz - lq_stopped)/dz
-      const float al = a.al[r];
-      const float sd2 = sd + 1e-6f;
-      dz = al * dz - (al * al / (float)a.B_norm) * (-z + (z - mu) / (sd2 * sd2));
+  const int idx = b * a.d + j;
+  float mu = 0.f, sd = 1.f;
+  if (active) {
+    mu = a.mu[idx]; sd = a.std[idx];
+    for (int s = ks; s < a.k; s += KS) {
+      const int64_t r = (int64_t)s * a.B + b;
+      const float g = a.g[r];
+      const float z = a.z[r * a.d + j], e = a.eps[r * a.d + j];
+      float dz = a.dz_dec[r * a.ld_dz + j];
+      if (a.dz_q2) dz += a.dz_q2[r * a.d + j];
+      if (dreg) {
+        // task02.py:60-76: encoder signal = al * (decoder-path dz) - (al^2/B) * d(lpz - lq_stopped)/dz
+        const float al = a.al[r];
+        const float sd2 = sd + 1e-6f;
+        dz = al * dz - (al * al / (float)a.B_norm) * (-z + (z - mu) / (sd2 * sd2));
+        acc_mu += dz;
+        acc_sd += dz * e;
+        continue;
+      }
+      if (!klobj) {
+        if (a.prior_rows == 0) {
+          dz += g * a.beta * (-z);
+        } else {
+          const int64_t pr = (a.prior_rows == 1) ? (int64_t)b * a.d + j : r * a.d + j;
+          const float pm = a.pmu[pr], ps = a.pstd[pr];
+          const float bt = (a.prior_rows == 1) ? a.beta : 1.f;    // iwae2 ignores beta (iwae2.py:128)
+          const float t = (z - pm) / (ps * ps);
+          dz += g * bt * (-t);
+          const float dpm = g * bt * t;
+          const float dps = g * bt * ((z - pm) * t / ps - 1.f / ps);
+          if (a.prior_rows == 1) { acc_pmu += dpm; acc_psd += dps; }
+          else if (a.dpmu) { a.dpmu[pr] = dpm; a.dpa[pr] = dps * (ps - 1e-6f); }
+        }
+        const float bt = (a.prior_rows == 2) ? 1.f : a.beta;
+        acc_sd += g * bt / sd;                                     // -beta * d lq/d std (total) = +beta/std
+      }
       acc_mu += dz;
       acc_sd += dz * e;
-      continue;
     }
-    if (!klobj) {
-      if (a.prior_rows == 0) {
-        dz += g * a.beta * (-z);
-      } else {
-        const int64_t pr = (a.prior_rows == 1) ? (int64_t)b * a.d + j : r * a.d + j;
-        const float pm = a.pmu[pr], ps = a.pstd[pr];
-        const float bt = (a.prior_rows == 1) ? a.beta : 1.f;    // iwae2 ignores beta (iwae2.py:128)
-        const float t = (z - pm) / (ps * ps);
-        dz += g * bt * (-t);
-        const float dpm = g * bt * t;
-        const float dps = g * bt * ((z - pm) * t / ps - 1.f / ps);
-        if (a.prior_rows == 1) { acc_pmu += dpm; acc_psd += dps; }
-        else if (a.dpmu) { a.dpmu[pr] = dpm; a.dpa[pr] = dps * (ps - 1e-6f); }
-      }
-      const float bt = (a.prior_rows == 2) ? 1.f : a.beta;
-      acc_sd += g * bt / sd;                                     // -beta * d lq/d std (total) = +beta/std
+  }
+  red[0][threadIdx.x] = acc_mu; red[1][threadIdx.x] = acc_sd; red[2][threadIdx.x] = acc_pmu; red[3][threadIdx.x] = acc_psd;
+  __syncthreads();
+  if (active && ks == 0) {
+    for (int q = 1; q < KS; ++q) {
+      acc_mu += red[0][q * a.d + j]; acc_sd += red[1][q * a.d + j];
+      acc_pmu += red[2][q * a.d + j]; acc_psd += red[3][q * a.d + j];
     }
-    acc_mu += dz;
-    acc_sd += dz * e;
-  }
-  if (klobj) {
-    // loss = -mean lpxz + beta * mean_b kl ; d kl/d mu = mu, d kl/d std = std - 1/std
-    acc_mu += a.beta / (float)a.B_norm * mu;
-    acc_sd += a.beta / (float)a.B_norm * (sd - 1.f / sd);
-  }
-  a.dmu[idx] = acc_mu;
-  a.da[idx] = acc_sd * (sd - 1e-6f);      // std = exp(a) + 1e-6
-  if (a.prior_rows == 1 && a.dpmu) {
-    a.dpmu[idx] = acc_pmu;
-    a.dpa[idx] = acc_psd * (a.pstd[idx] - 1e-6f);
+    if (klobj) {
+      // loss = -mean lpxz + beta * mean_b kl ; d kl/d mu = mu, d kl/d std = std - 1/std
+      acc_mu += a.beta / (float)a.B_norm * mu;
+      acc_sd += a.beta / (float)a.B_norm * (sd - 1.f / sd);
+    }
+    a.dmu[idx] = acc_mu;
+    a.da[idx] = acc_sd * (sd - 1e-6f);      // std = exp(a) + 1e-6
+    if (a.prior_rows == 1 && a.dpmu) {
+      a.dpmu[idx] = acc_pmu;
+      a.dpa[idx] = acc_psd * (a.pstd[idx] - 1e-6f);
+    }
   }
 }
 int latent1_bwd(const Latent1BwdArgs& a, cudaStream_t st) {
-  const int n = a.B * a.d;
-  if (n == 0) return 0;
-  latent1_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+  if (a.B * a.d == 0) return 0;
+  IWAE_REQUIRE(a.d <= 256, "latent1_bwd: latent size above 256 is not supported");
+  latent1_bwd_kernel<<<a.B, 256, 0, st>>>(a);
   LAUNCH_CHECK();
   return 0;
 }
@@ -642,6 +706,40 @@ int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
   const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   int blocks = (int)((n / 4 + 255) / 256); if (blocks > 148 * 4) blocks = 148 * 4; if (blocks < 1) blocks = 1;
   adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, aligned ? 1 : 0, (float)lr_t, b1, b2, eps);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- split-K gradient partials: fixed-order reduction, optionally fused with the Keras-Adam update ----
+__global__ void grad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t n, float* __restrict__ g,
+                                   float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float lr_t,
+                                   float b1, float b2, float eps) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gg = 0.f;
+    for (int s = 0; s < splits; ++s) gg += ws[(int64_t)s * n + i];
+    if (g) g[i] = gg;
+    if (p) {
+      const float mm = b1 * m[i] + (1.f - b1) * gg;
+      const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+      m[i] = mm; v[i] = vv;
+      p[i] = p[i] - lr_t * mm / (sqrtf(vv) + eps);
+    }
+  }
+}
+int grad_reduce(const float* ws, int splits, int64_t n, float* grads, cudaStream_t st) {
+  if (n == 0) return 0;
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, grads, nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f);
+  LAUNCH_CHECK();
+  return 0;
+}
+int adam_from_partials(float* p, const float* ws, int splits, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                       float eps, int64_t t, cudaStream_t st) {
+  if (n == 0) return 0;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, nullptr, p, m, v, (float)lr_t, b1, b2, eps);
   LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_driver.py -m gpu -q --timeout 300 -p no:cacheprovider 2>&1 | tail -n 6
+timeout 300 python scripts/train_probe.py 300
+timeout 300 python scripts/train_probe.py 20 > gpurun_out/train_probe.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 200 --csv --log-file gpurun_out/launches_train.csv \
+    python scripts/train_probe.py 20 > gpurun_out/ncu_launches_train.log 2>&1 ; echo "rc=$?"
