@@ -114,6 +114,14 @@ int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const floa
                   int64_t N, int32_t k, uint64_t seed, int64_t img_offset, int32_t precision,
                   float* out_per_example, double* out_sum, void* stream);
 
+/* Monitoring pass (model.val_step on the whole test set, main.py:152) through the same
+ * fused kernel: per-example logmeanexp_k(log_w) AND mean_k(log_w) for N images at beta = 1, i.e. the
+ * iwae_elbo / vae_elbo the training loop prints, without materialising [k,B,784].
+ *   out_iwae, out_vae [N]; out_sums: two doubles on the device (sum of each) or NULL. */
+int iwae_monitor_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N,
+                      int32_t k, uint64_t seed, int64_t img_offset, int32_t precision, float* out_iwae,
+                      float* out_vae, double* out_sums, void* stream);
+
 /* Device time (ms) of the fused tensor-core evaluation kernel in the most recent iwae_llh_eval /
  * iwae_llh_eval_host call with a TC precision on this context (CUDA events recorded around that one
  * launch on the caller's stream); synchronises on the second event.  bench.py's roofline uses it. */

@@ -53,6 +53,7 @@ def _load():
         "iwae_layout_for_config": (C.c_int, [P(Config), P(i64), P(i32), P(i64), P(i32), P(i32)]),
         "iwae_forward": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, vp, vp, u64, i64, P(Outputs), vp]),
         "iwae_llh_eval": (C.c_int, [vp, vp, vp, vp, i64, i32, u64, i64, i32, vp, vp, vp]),
+        "iwae_monitor_eval": (C.c_int, [vp, vp, vp, vp, i64, i32, u64, i64, i32, vp, vp, vp, vp]),
         "iwae_llh_eval_host": (C.c_int, [vp, vp, vp, vp, i64, i32, u64, i64, i32, vp, vp, vp]),
         "iwae_grads": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp, vp, u64, i64, vp, P(Outputs), vp]),
         "iwae_adam_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, vp]),
@@ -79,7 +80,7 @@ lib = _load()
 EXPORTS = ("iwae_last_error", "iwae_version", "iwae_create", "iwae_destroy", "iwae_param_count",
            "iwae_param_layout", "iwae_layout_for_config", "iwae_forward", "iwae_llh_eval", "iwae_llh_eval_host",
            "iwae_grads", "iwae_adam_step", "iwae_train_step", "iwae_philox_normal", "iwae_decode", "iwae_sir",
-           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_umma_bench")
+           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_umma_bench", "iwae_monitor_eval")
 
 
 def check(rc: int, what: str = ""):

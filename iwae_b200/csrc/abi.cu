@@ -362,9 +362,29 @@ static int grow_dev(float** p, size_t* cap, size_t bytes) {
 // ---------------------------------------------------------------------------------------------
 // k-sample log-likelihood evaluation (main.py:170-184)
 // ---------------------------------------------------------------------------------------------
+static int llh_eval_impl(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
+                         uint64_t seed, int64_t img_offset, int32_t precision, float* out_per_example, float* out_vae,
+                         double* out_sum, void* stream);
+
 extern "C" int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
                              uint64_t seed, int64_t img_offset, int32_t precision, float* out_per_example,
                              double* out_sum, void* stream) {
+  return llh_eval_impl(ctx, params, x, y, N, k, seed, img_offset, precision, out_per_example, nullptr, out_sum, stream);
+}
+
+extern "C" int iwae_monitor_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
+                                 uint64_t seed, int64_t img_offset, int32_t precision, float* out_iwae, float* out_vae,
+                                 double* out_sums, void* stream) {
+  IWAE_REQUIRE(out_iwae && out_vae, "iwae_monitor_eval: null output");
+  IWAE_TRY(llh_eval_impl(ctx, params, x, y, N, k, seed, img_offset, precision, out_iwae, out_vae, out_sums, stream));
+  if (out_sums && N > 0) IWAE_TRY(sum_to_double(out_vae, N, out_sums + 1, 0, (cudaStream_t)stream));
+  else if (out_sums) CUDA_TRY(cudaMemsetAsync(out_sums + 1, 0, sizeof(double), (cudaStream_t)stream));
+  return 0;
+}
+
+static int llh_eval_impl(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
+                         uint64_t seed, int64_t img_offset, int32_t precision, float* out_per_example, float* out_vae,
+                         double* out_sum, void* stream) {
   IWAE_REQUIRE(ctx && params && (x || N == 0), "iwae_llh_eval: null argument");
   IWAE_REQUIRE(N >= 0 && k > 0, "iwae_llh_eval: bad N=%lld k=%d", (long long)N, k);
   cudaStream_t st = (cudaStream_t)stream;
@@ -380,7 +400,7 @@ extern "C" int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x,
     return 0;
   }
   if (precision == IWAE_PREC_TC_F16 || precision == IWAE_PREC_TC_F16_FAST) {
-    IWAE_TRY(tc_llh_eval(ctx, params, x, y, N, k, seed, img_offset, precision == IWAE_PREC_TC_F16_FAST, per, st));
+    IWAE_TRY(tc_llh_eval(ctx, params, x, y, N, k, seed, img_offset, precision == IWAE_PREC_TC_F16_FAST, per, out_vae, st));
   } else {
     IWAE_REQUIRE(precision == IWAE_PREC_FP32, "iwae_llh_eval: unknown precision %d", precision);
     // chunk the images so that one chunk's activations stay around 256k rows
@@ -391,6 +411,7 @@ extern "C" int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x,
       ctx->arena.reset();
       iwae_outputs o = {};
       o.iwae = per + i0;
+      if (out_vae) o.vae = out_vae + i0;
       Fwd f; FwdOpts opt;
       IWAE_TRY(forward_internal(ctx, params, x + i0 * m.cfg.n_x, y ? y + i0 : nullptr, Bi, k, 1.0f, nullptr, nullptr,
                                 seed, img_offset + i0, &o, opt, f, st));

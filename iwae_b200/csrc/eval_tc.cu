@@ -310,6 +310,7 @@ struct EvalArgs {
   const float* pmu;            // [N, d1] learned prior (CIWAE) or null
   const float* pstd;
   float2* partial;             // [N * tiles_per_img] (max, sum exp)
+  float* partial_lw;           // [N * tiles_per_img] sum of log_w over the tile's valid rows (monitoring), or null
   int64_t n_tiles;
   int tiles_per_img, rows_per_tile, k;
   uint64_t seed; int64_t img_offset;
@@ -335,6 +336,7 @@ struct __align__(16) SubTile {       // per 128-row sub-tile
   float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX], ipsd[D_MAX];
   float red[16];               // [0,4) max, [4,8) sum-exp, [8,16) per-warp constant partials
   float lwpart[TILE_M];        // partial log-weights of the second column half of each row
+  float red_lw[4];             // per-quarter sums of log_w (monitoring)
   int label; int pad_[3];
 };
 struct __align__(16) SmemLayout {
@@ -926,11 +928,18 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       epi_bar_sync(u);
       mx = fmaxf(fmaxf(T.red[0], T.red[1]), fmaxf(T.red[2], T.red[3]));
       float se = (half == 0 && valid) ? expf(lw - mx) : 0.f;
+      float sl = (half == 0 && valid) ? lw : 0.f;          // for vae_elbo = mean_k log_w (iwae1.py:119)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-      if (lane == 0 && half == 0) T.red[4 + q] = se;
+      for (int o = 16; o > 0; o >>= 1) {
+        se += __shfl_xor_sync(0xffffffffu, se, o);
+        sl += __shfl_xor_sync(0xffffffffu, sl, o);
+      }
+      if (lane == 0 && half == 0) { T.red[4 + q] = se; T.red_lw[q] = sl; }
       epi_bar_sync(u);
-      if (et == 0 && tile_ok) args.partial[tile] = make_float2(mx, T.red[4] + T.red[5] + T.red[6] + T.red[7]);
+      if (et == 0 && tile_ok) {
+        args.partial[tile] = make_float2(mx, T.red[4] + T.red[5] + T.red[6] + T.red[7]);
+        if (args.partial_lw) args.partial_lw[tile] = T.red_lw[0] + T.red_lw[1] + T.red_lw[2] + T.red_lw[3];
+      }
     }
   }
 
@@ -940,8 +949,8 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
 }
 
 // per image: logmeanexp over its tiles' partials (utils.logmeanexp, utils.py:6-8)
-__global__ void combine_partials_kernel(const float2* __restrict__ partial, int64_t N, int tiles_per_img, int k,
-                                        float* __restrict__ out) {
+__global__ void combine_partials_kernel(const float2* __restrict__ partial, const float* __restrict__ partial_lw, int64_t N,
+                                        int tiles_per_img, int k, float* __restrict__ out, float* __restrict__ out_vae) {
   const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n >= N) return;
   float mx = -INFINITY;
@@ -952,6 +961,11 @@ __global__ void combine_partials_kernel(const float2* __restrict__ partial, int6
     se += p.y * expf(p.x - mx);
   }
   out[n] = logf(se / (float)k) + mx;
+  if (out_vae) {
+    float sl = 0.f;
+    for (int t = 0; t < tiles_per_img; ++t) sl += partial_lw[n * tiles_per_img + t];
+    out_vae[n] = sl / (float)k;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1010,6 +1024,7 @@ struct TcPack {
   uint8_t* wpack = nullptr;
   size_t wpack_bytes = 0;
   float2* partial = nullptr;
+  float* partial_lw = nullptr;
   size_t partial_cap = 0;
   bool attr_set = false;
 };
@@ -1128,12 +1143,13 @@ void tc_release(iwae_ctx* ctx) {
   if (!ctx->tc) return;
   if (ctx->tc->wpack) cudaFree(ctx->tc->wpack);
   if (ctx->tc->partial) cudaFree(ctx->tc->partial);
+  if (ctx->tc->partial_lw) cudaFree(ctx->tc->partial_lw);
   delete ctx->tc;
   ctx->tc = nullptr;
 }
 
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k, uint64_t seed,
-                int64_t img_offset, int fast, float* out_per_example, cudaStream_t st) {
+                int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st) {
   const ModelP& m = ctx->model;
   const iwae_config& c = m.cfg;
   IWAE_REQUIRE(!m.cond() || y, "tensor-core path: CIWAE needs labels");
@@ -1170,11 +1186,14 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   const size_t need = (size_t)a.n_tiles * sizeof(float2);
   if (tp.partial_cap < need) {
     if (tp.partial) CUDA_TRY(cudaFree(tp.partial));
-    tp.partial = nullptr; tp.partial_cap = 0;
+    if (tp.partial_lw) CUDA_TRY(cudaFree(tp.partial_lw));
+    tp.partial = nullptr; tp.partial_lw = nullptr; tp.partial_cap = 0;
     CUDA_TRY(cudaMalloc((void**)&tp.partial, need));
+    CUDA_TRY(cudaMalloc((void**)&tp.partial_lw, need / 2));
     tp.partial_cap = need;
   }
   a.partial = tp.partial;
+  a.partial_lw = out_vae ? tp.partial_lw : nullptr;
   a.trace = nullptr;
   const char* trace_path = getenv("IWAE_TC_TRACE");
   if (trace_path && *trace_path) {
@@ -1196,7 +1215,8 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   LAUNCH_CHECK();
   CUDA_TRY(cudaEventRecord(ctx->ev_k1, st));
   ctx->ev_valid = true;
-  tc::combine_partials_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(tp.partial, N, a.tiles_per_img, k, out_per_example);
+  tc::combine_partials_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(tp.partial, a.partial_lw, N, a.tiles_per_img, k, out_per_example,
+                                                                         out_vae);
   LAUNCH_CHECK();
   if (a.trace) {     // debug only: synchronous dump of the timeline
     std::vector<long long> h(4 * 3 * TRACE_SLOTS * 2);

@@ -526,6 +526,25 @@ class IWAE:
                                     _ptr(total), _stream_ptr()), "iwae_llh_eval")
         return per, total
 
+    def monitor(self, x, n_samples, y=None, precision="tc_f16_fast", seed=None):
+        """The monitoring numbers of `val_step` on a whole test set (main.py:152) at beta = 1 through the fused
+        evaluation kernel: {'iwae_elbo', 'vae_elbo'} as batch means plus the per-example vectors, without
+        materialising any [k,B,.] tensor."""
+        x, y = self._check_x(x, y)
+        N = x.shape[0]
+        per_i, per_v = self._alloc(max(N, 1))[:N], self._alloc(max(N, 1))[:N]
+        sums = torch.zeros(2, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_monitor_eval(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), N, int(n_samples),
+                                        self._next_seed(seed), 0, _abi.PRECISIONS[precision], _ptr(per_i), _ptr(per_v),
+                                        _ptr(sums), _stream_ptr()), "iwae_monitor_eval")
+        res = Result()
+        res["iwae_elbo"] = DeviceValue((sums[0] / max(N, 1)).float())
+        res["vae_elbo"] = DeviceValue((sums[1] / max(N, 1)).float())
+        res["iwae_elbo_per_example"] = DeviceValue(per_i)
+        res["vae_elbo_per_example"] = DeviceValue(per_v)
+        return res
+
     def llh_host(self, x_host: np.ndarray, n_samples=5000, y_host=None, precision="tc_f16_fast", seed=None,
                  img_offset=0):
         """Same through the reference-facing HOST-buffer entry point (iwae_llh_eval_host): x (and y) are

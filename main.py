@@ -35,6 +35,8 @@ parser.add_argument("--n_test", type=int, default=10000)
 parser.add_argument("--eval_samples", type=int, default=5000)
 parser.add_argument("--reference_eval_loop", action="store_true")
 parser.add_argument("--max_steps", type=int, default=-1, help="stop early (smoke runs)")
+parser.add_argument("--fused_monitor", action="store_true",
+                    help="monitor the test set through the fused evaluation kernel (iwae_elbo / vae_elbo only, beta = 1)")
 
 
 def main(argv=None):
@@ -83,8 +85,11 @@ def main(argv=None):
             res = model.train_step(x_batch, n_samples, beta, optimizer, objective=objective)
             if step % 200 == 0:
                 model.write_to_tensorboard(res, step)
-                test_res = model.val_step(Xtest, n_samples, beta)
-                model.write_to_tensorboard(test_res, step)
+                if args.fused_monitor and objective in ("iwae_elbo", "vae_elbo") and beta == 1.0:
+                    test_res = model.monitor(Xtest, n_samples)
+                else:
+                    test_res = model.val_step(Xtest, n_samples, beta)
+                    model.write_to_tensorboard(test_res, step)
                 took = time.time() - start
                 start = time.time()
                 print("epoch {0}/{1}, step {2}/{3}, train ELBO: {4:.2f}, val ELBO: {5:.2f}, time: {6:.2f}"

@@ -139,3 +139,27 @@ def test_llh_full_size_properties(oracle):
     # one image against the fp64 oracle at the full k
     ref = oracle_llh(oracle, "iwae2", {**case, "x": case["x"][:2]}, 5000)
     assert rel(per_tc[:2].cpu().numpy(), ref) < TC_RTOL
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc_f16_fast"])
+@pytest.mark.parametrize("kind", ["iwae1", "iwae2"])
+def test_monitor_pass_matches_oracle(oracle, kind, precision):
+    """Fused monitoring pass (val_step's iwae_elbo / vae_elbo on a test set, main.py:152) at the training k."""
+    N, k = 7, 50
+    case = _case(oracle, kind, N, scale=0.5)
+    m = build(kind, case, case)
+    res = m.monitor(case["x"], k, precision=precision, seed=SEED)
+    p = oracle.to_torch(case["params"])
+    x = torch.tensor(case["x"], dtype=torch.float64)
+    if kind == "iwae2":
+        e1 = torch.tensor(oracle.philox_normal(SEED, 1, 0, N, k, 100), dtype=torch.float64)
+        e2 = torch.tensor(oracle.philox_normal(SEED, 2, 0, N, k, 50), dtype=torch.float64)
+        ref = oracle.iwae2_call(p, x, k, 1.0, e1, e2)
+    else:
+        e1 = torch.tensor(oracle.philox_normal(SEED, 1, 0, N, k, 100), dtype=torch.float64)
+        ref = oracle.iwae1_call(p, x, k, 1.0, e1)
+    tol = RTOL if precision == "fp32" else TC_RTOL
+    assert rel(res["iwae_elbo_per_example"].numpy(), ref["iwae_elbo_per_example"].numpy()) < tol
+    assert rel(res["vae_elbo_per_example"].numpy(), ref["vae_elbo_per_example"].numpy()) < tol
+    assert rel(float(res["iwae_elbo"]), float(ref["iwae_elbo"])) < tol
+    assert rel(float(res["vae_elbo"]), float(ref["vae_elbo"])) < tol
