@@ -604,11 +604,13 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
 
     for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
       trace_ev(args, 2, tn, tl * 10000 + 9000);
-      int64_t tile = mt * NSUB + u;
-      const bool tile_ok = tile < args.n_tiles;       // the last macro-tile may be half empty
-      if (!tile_ok) tile = args.n_tiles - 1;
-      const int64_t img = tile / args.tiles_per_img;
-      const int tin = (int)(tile % args.tiles_per_img);
+      // (tile indices fit 32 bits: n_tiles < 2^31 is checked on the host; 32-bit division is much cheaper)
+      uint32_t tile = (uint32_t)mt * NSUB + u;
+      const bool tile_ok = tile < (uint32_t)args.n_tiles;       // the last macro-tile may be half empty
+      if (!tile_ok) tile = (uint32_t)args.n_tiles - 1u;
+      const uint32_t img32 = tile / (uint32_t)args.tiles_per_img;
+      const int64_t img = img32;
+      const int tin = (int)(tile - img32 * (uint32_t)args.tiles_per_img);
       const int s = tin * args.rows_per_tile + row;                 // sample index of this row
       const bool valid = tile_ok && (row < args.rows_per_tile) && (s < args.k);
 
@@ -823,33 +825,52 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
               tmem_ld_wait();
               const uint4 za = *reinterpret_cast<const uint4*>(T.bufZ + (size_t)((off + g8) >> 3) * (TILE_M * 16) + row * 16);
               const uint32_t zw[4] = {za.x, za.y, za.z, za.w};
+              const int nv = min(8, cnt - g8);       // valid dims of this group (8 except possibly the last)
+              n_mine += nv;
+              if (FAST) {
+                // sd = e^a + 1e-6 with a' = a*log2(e) in TMEM.  One MUFU per dim: inv = 2^-a' = e^-a, then
+                // 1/sd = inv*(1 - 1e-6*inv) and log sd = a + 1e-6*inv to first order in 1e-6*inv (error
+                // <= (1e-6*inv)^2).  Branch-free over the group; a warp vote re-does the group exactly in
+                // the rare case that some sd is < ~1e-3.
+                float inv[8];
+                bool small = false;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (g8 + i < cnt) {
-                  const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
-                  const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
-                  const float m = __uint_as_float(r[i]);
-                  const float a = __uint_as_float(r[8 + i]);
-                  ++n_mine;
-                  if (FAST) {
-                    // sd = e^a + 1e-6 with a' = a*log2(e) in TMEM.  One MUFU: inv = 2^-a' = e^-a, then
-                    // 1/sd = inv*(1 - 1e-6*inv) and log sd = a + 1e-6*inv to first order in 1e-6*inv
-                    // (error <= (1e-6*inv)^2); exact path when that is not small (sd < ~1e-3).
-                    const float inv = ex2_approx(-a);
-                    float isd, ls;
-                    if (inv < 1024.f) {
-                      isd = fmaf(-1e-6f * inv, inv, inv);
-                      ls = fmaf(a, LN2_F, 1e-6f * inv);
-                    } else {
-                      const float sd = ex2_approx(a) + 1e-6f;
-                      isd = rcp_approx(sd);
-                      ls = LN2_F * lg2_approx(sd);
-                    }
-                    const float t = (z - m) * isd;
+                for (int i = 0; i < 8; ++i) {
+                  inv[i] = ex2_approx(-__uint_as_float(r[8 + i]));
+                  small |= (i < nv) && !(inv[i] < 1024.f);
+                }
+                if (!__any_sync(0xffffffffu, small)) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
+                    const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                    const float isd = fmaf(-1e-6f * inv[i], inv[i], inv[i]);
+                    const float ls = fmaf(__uint_as_float(r[8 + i]), LN2_F, 1e-6f * inv[i]);
+                    const float t = (i < nv) ? (z - __uint_as_float(r[i])) * isd : 0.f;
                     t2sum = fmaf(t, t, t2sum);
-                    lssum += ls;
-                  } else {
-                    const float sd = expf(a) + 1e-6f;
+                    lssum += (i < nv) ? ls : 0.f;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    if (i < nv) {
+                      const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
+                      const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                      const float sd = ex2_approx(__uint_as_float(r[8 + i])) + 1e-6f;
+                      const float t = (z - __uint_as_float(r[i])) * rcp_approx(sd);
+                      t2sum = fmaf(t, t, t2sum);
+                      lssum += LN2_F * lg2_approx(sd);
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (i < nv) {
+                    const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
+                    const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                    const float m = __uint_as_float(r[i]);
+                    const float sd = expf(__uint_as_float(r[8 + i])) + 1e-6f;
                     const float t = z / sd - m / sd;
                     lw += -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                     // + lpz1z2 (iwae2.py:120)
                   }
@@ -1182,6 +1203,7 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   a.tiles_per_img = (k + tc::TILE_M - 1) / tc::TILE_M;
   a.rows_per_tile = (k + a.tiles_per_img - 1) / a.tiles_per_img;
   a.n_tiles = N * a.tiles_per_img;
+  IWAE_REQUIRE(a.n_tiles < ((int64_t)1 << 31), "tensor-core path: too many tiles in one call (N * ceil(k/128) must be < 2^31)");
   a.k = k; a.seed = seed; a.img_offset = img_offset;
   const size_t need = (size_t)a.n_tiles * sizeof(float2);
   if (tp.partial_cap < need) {
