@@ -771,7 +771,23 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
             float e2sum = 0.f, z2sum = 0.f, lgsum = 0.f;
             for (int g8 = 8 * half; g8 < Ly.next_kpad; g8 += 16) {
               float v[8];
-              if (g8 < cnt) {
+              if (FAST && g8 + 8 <= cnt) {
+                // complete group of 8 latent dims: branch-free
+                uint32_t r[16];
+                tmem_ld16(tbase + 2 * g8, r);
+                const float4 na = normal4<true>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2));
+                const float4 nb = normal4<true>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2) + 1u);
+                const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float sd = ex2_approx(__uint_as_float(r[8 + i])) + 1e-6f;
+                  v[i] = fmaf(e[i], sd, __uint_as_float(r[i]));
+                  e2sum = fmaf(e[i], e[i], e2sum);
+                  z2sum = fmaf(v[i], v[i], z2sum);
+                  lgsum += lg2_approx(sd);
+                }
+              } else if (g8 < cnt) {
                 uint32_t r[16];
                 tmem_ld16(tbase + 2 * g8, r);
                 tmem_ld_wait();
