@@ -269,7 +269,7 @@ constexpr int NSUB = IWAE_NSUB;                       // 128-row sub-tiles per C
                                                       // fastest measured), 2 = one persistent CTA per SM on a 256-row macro-tile
                                                       // whose sub-tiles share every weight slab
 constexpr int CTAS_PER_SM = (NSUB == 2) ? 1 : 2;
-constexpr int NSTAGES = (NSUB == 2) ? 7 : 3;          // weight-slab ring depth (7 KB slabs)
+constexpr int NSTAGES = (NSUB == 2) ? 7 : 4;          // weight-slab ring depth (7 KB slabs)
 constexpr int SLAB_K = 32;
 constexpr int SLAB_BYTES = CHUNK_N_MAX * SLAB_K * 2;   // 7168
 constexpr int KZ_MAX = 112;                            // K capacity of the z1 buffer
@@ -277,7 +277,7 @@ constexpr int KP_MAX = 208;                            // K capacity of the acti
 constexpr int BUFZ_BYTES = TILE_M * KZ_MAX * 2;        // 28672
 constexpr int BUFP_BYTES = TILE_M * KP_MAX * 2;        // 53248
 constexpr int NX_MAX = 784;
-constexpr int D_MAX = 104;
+constexpr int D_MAX = 100;
 constexpr int NUM_EPI_WARPS = 8 * NSUB;               // 8 epilogue warps per sub-tile
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // producer warp, MMA warp, epilogue warps
 constexpr int TMEM_COLS = 256 * NSUB;                 // per sub-tile: 2 accumulator buffers x 128 columns
@@ -333,10 +333,12 @@ struct __align__(16) SubTile {       // per 128-row sub-tile
   uint8_t bufZ[BUFZ_BYTES];
   uint8_t bufP[BUFP_BYTES];
   float sgn[NX_MAX];           // 1 - 2x per pixel of the sub-tile's image (0 for padded columns); 16-byte aligned
-  float mu[D_MAX], sd[D_MAX], lsd[D_MAX], pmu[D_MAX], psd[D_MAX], lpsd[D_MAX], ipsd[D_MAX];
+  float mu[D_MAX], sd[D_MAX], pmu[D_MAX];
+  float psd[D_MAX];            // learned prior: 1/std in FAST mode, std in precise mode
   float red[16];               // [0,4) max, [4,8) sum-exp, [8,16) per-warp constant partials
-  float lwpart[TILE_M];        // partial log-weights of the second column half of each row
   float red_lw[4];             // per-quarter sums of log_w (monitoring)
+  // (the partial log-weights of the second column half of each row are parked in bufP, which is dead
+  //  once the last layer's MMAs have retired: a 4th weight slab fits in the shared memory this frees)
   int label; int pad_[3];
 };
 struct __align__(16) SmemLayout {
@@ -622,12 +624,12 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       for (int j = et; j < d1; j += 256) {
         const float sd = __ldg(args.std1 + img * d1 + j);
         const float ls = logf(sd);
-        T.mu[j] = __ldg(args.mu1 + img * d1 + j); T.sd[j] = sd; T.lsd[j] = ls;
+        T.mu[j] = __ldg(args.mu1 + img * d1 + j); T.sd[j] = sd;
         csum += ls;
         if (P.learned_prior) {
           const float ps = __ldg(args.pstd + img * d1 + j);
           const float lps = logf(ps);
-          T.pmu[j] = __ldg(args.pmu + img * d1 + j); T.psd[j] = ps; T.lpsd[j] = lps; T.ipsd[j] = 1.f / ps;
+          T.pmu[j] = __ldg(args.pmu + img * d1 + j); T.psd[j] = FAST ? 1.f / ps : ps;
           csum -= lps;
         }
       }
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
             }
             if (P.learned_prior) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { const float tp = (v[i] - T.pmu[k0 + i]) * T.ipsd[k0 + i]; z1sum = fmaf(tp, tp, z1sum); }
+              for (int i = 0; i < 8; ++i) { const float tp = (v[i] - T.pmu[k0 + i]) * T.psd[k0 + i]; z1sum = fmaf(tp, tp, z1sum); }
             } else if (!P.two_layer) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) z1sum = fmaf(v[i], v[i], z1sum);
@@ -695,16 +697,16 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                   const float z = fmaf(e[i], sd, m);
                   if (FAST) {
                     e1sum = fmaf(e[i], e[i], e1sum);
-                    if (P.learned_prior) { const float tp = (z - T.pmu[j]) * T.ipsd[j]; z1sum = fmaf(tp, tp, z1sum); }
+                    if (P.learned_prior) { const float tp = (z - T.pmu[j]) * T.psd[j]; z1sum = fmaf(tp, tp, z1sum); }
                     else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
                   } else {
                     const float t = z / sd - m / sd;                         // TFP op order
-                    lw -= -0.5f * t * t - (LOG2PI_HALF_F + T.lsd[j]);        // - lq(z1|x)
+                    lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));       // - lq(z1|x)
                     if (!P.two_layer) {
                       if (P.learned_prior) {
                         const float ps = T.psd[j];
                         const float tp = z / ps - T.pmu[j] / ps;
-                        lw += -0.5f * tp * tp - (LOG2PI_HALF_F + T.lpsd[j]);
+                        lw += -0.5f * tp * tp - (LOG2PI_HALF_F + logf(ps));
                       } else {
                         lw += -0.5f * z * z - LOG2PI_HALF_F;
                       }
@@ -946,10 +948,11 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
 
       // ---- combine the two column halves of each row, then the tile's (max, sum exp) partial
-      if (half == 1) T.lwpart[row] = lw;
+      float* lwpart = reinterpret_cast<float*>(T.bufP);
+      if (half == 1) lwpart[row] = lw;
       epi_bar_sync(u);
       if (half == 0) {
-        lw += T.lwpart[row];
+        lw += lwpart[row];
         if (FAST) {
           float c0 = (float)(nx_pad - nx) * LN2_F + (P.two_layer ? (float)d1 * LOG2PI_HALF_F : 0.f);
 #pragma unroll
