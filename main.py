@@ -23,13 +23,13 @@ import iwae2    # noqa: E402
 from iwae_b200 import Adam  # noqa: E402
 
 parser = argparse.ArgumentParser()
-parser.add_argument("--stochastic_layers", type=int, default=1, choices=[1, 2], help="number of stochastic layers in the model")
-parser.add_argument("--n_samples", type=int, default=5, help="number of importance samples")
-parser.add_argument("--batch_size", type=int, default=20, help="batch size")
+parser.add_argument("--stochastic_layers", type=int, default=1, choices=[1, 2], help="1 -> iwae1.IWAE, 2 -> iwae2.IWAE")
+parser.add_argument("--n_samples", type=int, default=5, help="k, importance samples per image")
+parser.add_argument("--batch_size", type=int, default=20, help="images per train step")
 parser.add_argument("--epochs", type=int, default=-1,
-                    help="numper of epochs, if set to -1 number of epochs will be set based on the learning rate scheme from the paper")
+                    help="-1: the 3280-epoch schedule of Burda et al. (learning rate decays at epochs 0,1,4,13,...)")
 parser.add_argument("--objective", type=str, default="iwae_elbo", choices=["vae_elbo", "iwae_elbo", "iwae_eq14", "vae_elbo_kl"])
-parser.add_argument("--gpu", type=str, default="0", help="Choose GPU")
+parser.add_argument("--gpu", type=str, default="0", help="CUDA_VISIBLE_DEVICES")
 parser.add_argument("--n_train", type=int, default=60000)
 parser.add_argument("--n_test", type=int, default=10000)
 parser.add_argument("--eval_samples", type=int, default=5000)
