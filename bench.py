@@ -281,7 +281,9 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16 operands / f32 accumulate (tcgen05), f32 elsewhere" if args.precision != "fp32" else "f32",
+        "dtype": "f16" if args.precision != "fp32" else "f32",
+        "dtype_detail": ("fp16 tcgen05 operands, fp32 TMEM accumulation, fp32 log-density / log-sum-exp arithmetic"
+                         if args.precision != "fp32" else "fp32 FFMA kernels"),
         "data": "synthetic", "config": config_dict(args), "impl": "ours",
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(args.images) * 784 * 4,
