@@ -163,3 +163,26 @@ def test_monitor_pass_matches_oracle(oracle, kind, precision):
     assert rel(res["vae_elbo_per_example"].numpy(), ref["vae_elbo_per_example"].numpy()) < tol
     assert rel(float(res["iwae_elbo"]), float(ref["iwae_elbo"])) < tol
     assert rel(float(res["vae_elbo"]), float(ref["vae_elbo"])) < tol
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_architectures_both_paths(oracle, seed):
+    """Random layer sizes / k / N inside the tensor-core path's limits (h <= 207, d1 + n_cond + 1 <= 112, d2 <= 56):
+    fp32 and fused tensor-core LLH against the oracle on the same Philox noise."""
+    rs = np.random.RandomState(900 + seed)
+    two = bool(seed % 2)
+    h1 = int(rs.choice([16, 37, 64, 128, 200, 207]))
+    d1 = int(rs.choice([1, 2, 3, 8, 17, 50, 64, 100]))
+    N, k = int(rs.randint(1, 6)), int(rs.choice([1, 2, 31, 128, 129, 257]))
+    if two:
+        h2, d2 = int(rs.choice([8, 33, 100, 150])), int(rs.choice([1, 2, 7, 24, 50, 56]))
+        kind, h, d = "iwae2", [h1, h2], [d1, d2]
+    else:
+        kind, h, d = "iwae1", h1, d1
+    case = make_case(oracle, kind, h, d, N, 1, seed=70 + seed, scale=0.7)
+    case["d"], case["h"] = d, h
+    m = build(kind, case, case)
+    ref = oracle_llh(oracle, kind, case, k, img_offset=5)
+    for prec, tol in (("fp32", RTOL), ("tc_f16", TC_RTOL), ("tc_f16_fast", TC_RTOL)):
+        per, _ = m.llh(case["x"], k, precision=prec, seed=SEED, img_offset=5)
+        assert rel(per.cpu().numpy(), ref) < tol, (kind, h, d, N, k, prec, rel(per.cpu().numpy(), ref))
