@@ -660,29 +660,48 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
         const uint32_t gimg = (uint32_t)(args.img_offset + img);
         const int one_col = d1 + P.nc;
         float e1sum = 0.f, z1sum = 0.f;
-        for (int k0 = 8 * half; k0 < P.kz_pad; k0 += 16) {
-          float v[8];
-          if (FAST && k0 < d1_full) {
-            // complete group of 8 latent dims: no per-element predicates, vector constant loads
+        // complete group of 8 latent dims (FAST): no per-element predicates, vector constant loads
+        auto full_group = [&](int k0, const float4 na, const float4 nb, float (&v)[8]) {
+          const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+          const float4 m0 = *reinterpret_cast<const float4*>(&T.mu[k0]), m1 = *reinterpret_cast<const float4*>(&T.mu[k0 + 4]);
+          const float4 s0 = *reinterpret_cast<const float4*>(&T.sd[k0]), s1 = *reinterpret_cast<const float4*>(&T.sd[k0 + 4]);
+          const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] = fmaf(e[i], ss[i], mm[i]);
+            e1sum = fmaf(e[i], e[i], e1sum);
+          }
+          if (P.learned_prior) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float tp = (v[i] - T.pmu[k0 + i]) * T.psd[k0 + i]; z1sum = fmaf(tp, tp, z1sum); }
+          } else if (!P.two_layer) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z1sum = fmaf(v[i], v[i], z1sum);
+          }
+          store8(T.bufZ, row, k0, v);
+        };
+        int k0 = 8 * half;
+        if (FAST) {
+          // two groups per iteration: four independent Philox / Box-Muller chains in flight per thread (the
+          // generator is a long dependent chain - 10 rounds - so one chain alone issues at ~0.25 IPC)
+          for (; k0 + 24 <= d1_full; k0 += 32) {
             const float4 na = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2));
             const float4 nb = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 1u);
-            const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
-            const float4 m0 = *reinterpret_cast<const float4*>(&T.mu[k0]), m1 = *reinterpret_cast<const float4*>(&T.mu[k0 + 4]);
-            const float4 s0 = *reinterpret_cast<const float4*>(&T.sd[k0]), s1 = *reinterpret_cast<const float4*>(&T.sd[k0 + 4]);
-            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[i] = fmaf(e[i], ss[i], mm[i]);
-              e1sum = fmaf(e[i], e[i], e1sum);
-            }
-            if (P.learned_prior) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { const float tp = (v[i] - T.pmu[k0 + i]) * T.psd[k0 + i]; z1sum = fmaf(tp, tp, z1sum); }
-            } else if (!P.two_layer) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) z1sum = fmaf(v[i], v[i], z1sum);
-            }
+            const float4 nc = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 4u);
+            const float4 nd = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 5u);
+            float va[8], vb[8];
+            full_group(k0, na, nb, va);
+            full_group(k0 + 16, nc, nd, vb);
+          }
+        }
+        for (; k0 < P.kz_pad; k0 += 16) {
+          float v[8];
+          if (FAST && k0 < d1_full) {
+            const float4 na = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2));
+            const float4 nb = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 1u);
+            full_group(k0, na, nb, v);
+            continue;
           } else {
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
