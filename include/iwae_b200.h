@@ -9,7 +9,7 @@
  *   - extern "C"; every function returns int: 0 = ok, non-zero = error; iwae_last_error() gives a
  *     thread-local message.  No exception crosses the ABI.
  *   - All data pointers are DEVICE pointers owned by the caller unless the name ends in _host.
- *     The library owns only the opaque iwae_ctx (scratch arena, packed fp16 weights, CUDA graphs).
+ *     The library owns only the opaque iwae_ctx (scratch arena, packed fp16 weights, staging buffers).
  *   - Every launch takes an explicit CUDA stream (cudaStream_t passed as void*).  Device entry points
  *     never synchronise; *_host entry points synchronise the stream before returning.
  *   - Tensors use the reference layout: sample-major [k, B, .] row-major fp32, Dense kernels

@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                   val = z;
                 } else if (j < one_col) {
                   val = (T.label == j - d1) ? 1.f : 0.f;
-                } else if (j == one_col) {
+                } else if (j == one_col || j == one_col + 1) {      // two constant-1 columns: bias hi + lo
                   val = 1.f;
                 }
                 v[4 * qq + i] = val;
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                         lw += -0.5f * z * z - LOG2PI_HALF_F;                              // + lpz2   (iwae2.py:116)
                         val = z;
                       }
-                    } else if (j == cnt) {
+                    } else if (j == cnt || j == cnt + 1) {
                       val = 1.f;
                     }
                     v[4 * qq + i] = val;
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = (g8 + i == cnt) ? 1.f : 0.f;
+                for (int i = 0; i < 8; ++i) v[i] = (g8 + i == cnt || g8 + i == cnt + 1) ? 1.f : 0.f;
               }
               store8(dst, row, g8, v);
             }
@@ -1040,7 +1040,7 @@ struct PackLayer {
   const float *W2, *b2;     // second head (log-std) for Gaussian layers, else null
   int k_real, k_pad, ldw;
   int nchunks, gauss;
-  int one_unit;             // TANH layers: output unit that must evaluate to 1 (the next layer's bias input), else -1
+  int one_unit;             // TANH layers: output units one_unit, one_unit+1 must evaluate to 1 (the next layer's bias inputs), else -1
   float scale, scale2;      // multiplies (W,b) / (W2,b2): log2(e) where the FAST epilogue works in base 2
   int chunk_n[MAX_CHUNKS], chunk_cnt[MAX_CHUNKS], chunk_off[MAX_CHUNKS];
   int64_t chunk_base[MAX_CHUNKS];   // half offset of the chunk's first slab inside the packed buffer
@@ -1067,8 +1067,15 @@ __global__ void pack_layer_kernel(PackLayer pl, __half* __restrict__ out) {
       if (col >= 0) {
         const float sc = (W == pl.W2 && pl.gauss) ? pl.scale2 : pl.scale;
         if (k < pl.k_real) v = sc * W[(int64_t)k * pl.ldw + col];
-        else if (k == pl.k_real) v = sc * b[col];
-      } else if (!pl.gauss && off + n == pl.one_unit && k == pl.k_real) {
+        else if (k == pl.k_real || k == pl.k_real + 1) {
+          // the bias rides on TWO constant-1 activations as an fp16 hi + lo pair (K is padded to a multiple
+          // of 16, the second column is free): ~22 bits instead of 11 - the 784 output biases are logits of
+          // pixel means (|b| up to 7), whose fp16 rounding alone was a 4e-5 relative error on the LLH
+          const float bf = sc * b[col];
+          const float hi = __half2float(__float2half_rn(bf));
+          v = (k == pl.k_real) ? hi : bf - hi;
+        }
+      } else if (!pl.gauss && pl.one_unit >= 0 && (off + n == pl.one_unit || off + n == pl.one_unit + 1) && k == pl.k_real) {
         v = 30.f;           // tanh(30) == 1.0f: the constant-1 activation that carries the next layer's bias
       }
       out[pos] = __float2half_rn(v);
