@@ -147,3 +147,40 @@ def test_golden_fixtures_reproduce(oracle):
         got = run_case(oracle, CASES[name])[1]
         for k, v in want.items():
             assert np.allclose(got[k[4:]], v, rtol=1e-10, atol=1e-10), (name, k)
+
+
+def test_full_model_against_independent_torch_distributions_build(oracle):
+    """The whole two-layer call, rebuilt independently of the oracle's formulas with torch.distributions objects
+    (Normal / Bernoulli log_prob, as the reference builds it with tfd), must agree with the restatement,
+    including the gradient of -iwae_elbo obtained by autograd through the distribution objects."""
+    D = torch.distributions
+    c = make_case(oracle, "iwae2", [200, 100], [100, 50], 3, 7, seed=5, scale=0.5)
+    k = 7
+    p = oracle.to_torch(c["params"], torch.float64, requires_grad=True)
+    x = torch.tensor(c["x"], dtype=torch.float64)
+    e1 = torch.tensor(c["eps1"], dtype=torch.float64)
+    e2 = torch.tensor(c["eps2"], dtype=torch.float64)
+
+    def block(prefix, inp):
+        h = torch.tanh(inp @ p[prefix + ".l1.kernel"] + p[prefix + ".l1.bias"])
+        h = torch.tanh(h @ p[prefix + ".l2.kernel"] + p[prefix + ".l2.bias"])
+        return D.Normal(h @ p[prefix + ".lmu.kernel"] + p[prefix + ".lmu.bias"],
+                        torch.exp(h @ p[prefix + ".lstd.kernel"] + p[prefix + ".lstd.bias"]) + 1e-6)
+
+    qz1 = block("encoder.encode_x_to_z1", x)
+    z1 = qz1.loc + qz1.scale * e1
+    qz2 = block("encoder.encode_z1_to_z2", z1)
+    z2 = qz2.loc + qz2.scale * e2
+    pz1 = block("decoder.decode_z2_to_z1", z2)
+    h = z1
+    for i, act in enumerate((torch.tanh, torch.tanh, lambda t: t)):
+        h = act(h @ p[f"decoder.decode_z1_to_x.dense{i}.kernel"] + p[f"decoder.decode_z1_to_x.dense{i}.bias"])
+    log_w = (D.Bernoulli(logits=h).log_prob(x.expand(k, -1, -1)).sum(-1) + pz1.log_prob(z1).sum(-1)
+             + D.Normal(0.0, 1.0).log_prob(z2).sum(-1) - qz1.log_prob(z1).sum(-1) - qz2.log_prob(z2).sum(-1))
+    iwae = (torch.logsumexp(log_w, 0) - np.log(k)).mean()
+    g_ind = torch.autograd.grad(-iwae, list(p.values()))
+    g_or, res = oracle.grads_objective(oracle.iwae2_call, p, "iwae_elbo", x, k, 1.0, e1, e2)
+    assert torch.allclose(res["log_w"], log_w, rtol=1e-10, atol=1e-9)
+    assert abs(float(res["iwae_elbo"]) - float(iwae)) < 1e-10 * abs(float(iwae))
+    for (name, go), gi in zip(g_or.items(), g_ind):
+        assert torch.allclose(go, gi, rtol=1e-8, atol=1e-12), name
