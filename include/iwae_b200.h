@@ -47,6 +47,14 @@ enum {
  *               throughput mode the bench reports. */
 enum { IWAE_PREC_FP32 = 0, IWAE_PREC_TC_F16 = 1, IWAE_PREC_TC_F16_FAST = 2 };
 
+/* The BasicBlocks of a model (src/iwae1.py:24-44), for iwae_block_forward. */
+enum {
+  IWAE_BLOCK_ENCODER = 0,   /* q(z1|x[,y])  encoder.encode_x_to_z   in: n_x + n_cond */
+  IWAE_BLOCK_ENCODER2 = 1,  /* q(z2|z1)     iwae2.py:53             in: d1 */
+  IWAE_BLOCK_DECODER21 = 2, /* p(z1|z2)     iwae2.py:78             in: d2 */
+  IWAE_BLOCK_PRIOR = 3      /* p(z|y)       task04.py:108           in: n_cond (one-hot rows) */
+};
+
 typedef struct {
   int32_t kind;      /* IWAE_KIND_* */
   int32_t n_x;       /* 784 */
@@ -165,6 +173,12 @@ int iwae_philox_normal(uint64_t seed, int32_t stream_id, int64_t img_offset, int
  * lpxz [R] = sum_j Bernoulli(logits).log_prob(x[r % B]).  Either output may be NULL. */
 int iwae_decode(iwae_ctx* ctx, const float* params, const float* z, const float* x, const float* y,
                 int32_t R, int32_t B, float* logits, float* lpxz, void* stream);
+
+/* One BasicBlock on caller-provided rows: in [R, n_in(block)] -> mu, sd [R, n_out] with sd = exp(.) + 1e-6.
+ * Replaces decoder.decode_z2_to_z1(z2) in IWAE.sample / conditional_sample (src/iwae2.py:184-213) and
+ * conditional_prior_network(y_onehot) in CIWAE.sample (tasks/task04.py:190-196). */
+int iwae_block_forward(iwae_ctx* ctx, const float* params, int32_t block, const float* in, int32_t R,
+                       float* mu, float* sd, void* stream);
 
 /* SIR: numpy.random.RandomState.choice(arange(L), size, replace=False, p=al)
  * (tasks/plot_task01.py:88) bit-exactly, given the float64 uniforms the RandomState would draw.

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libiwae_b200.so")
 KIND_IWAE1, KIND_IWAE2, KIND_CIWAE, KIND_CIWAE_STD = 1, 2, 3, 4
 OBJ = {"vae_elbo": 0, "iwae_elbo": 1, "iwae_eq14": 2, "vae_elbo_kl": 3, "dreg": 4}
 PREC_FP32, PREC_TC_F16, PREC_TC_F16_FAST = 0, 1, 2
+BLOCK_ENCODER, BLOCK_ENCODER2, BLOCK_DECODER21, BLOCK_PRIOR = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "tc_f16": PREC_TC_F16, "tc_f16_fast": PREC_TC_F16_FAST}
 
 
@@ -61,6 +62,7 @@ def _load():
                                       f32, i64, P(Outputs), vp]),
         "iwae_philox_normal": (C.c_int, [u64, i32, i64, i32, i32, i32, vp, vp]),
         "iwae_decode": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
+        "iwae_block_forward": (C.c_int, [vp, vp, i32, vp, i32, vp, vp, vp]),
         "iwae_sir": (C.c_int, [vp, i32, vp, i32, i32, vp, vp, vp]),
         "iwae_softmax_f32": (C.c_int, [vp, i32, vp, vp]),
         "iwae_bernoulli_sample": (C.c_int, [vp, i64, u64, u64, vp, vp]),
@@ -80,7 +82,8 @@ lib = _load()
 EXPORTS = ("iwae_last_error", "iwae_version", "iwae_create", "iwae_destroy", "iwae_param_count",
            "iwae_param_layout", "iwae_layout_for_config", "iwae_forward", "iwae_llh_eval", "iwae_llh_eval_host",
            "iwae_grads", "iwae_adam_step", "iwae_train_step", "iwae_philox_normal", "iwae_decode", "iwae_sir",
-           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_umma_bench", "iwae_monitor_eval")
+           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_umma_bench", "iwae_monitor_eval",
+           "iwae_block_forward")
 
 
 def check(rc: int, what: str = ""):

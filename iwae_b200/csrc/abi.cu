@@ -675,6 +675,29 @@ extern "C" int iwae_decode(iwae_ctx* ctx, const float* params, const float* z, c
   return 0;
 }
 
+// BasicBlock.call (iwae1.py:36-44) of one of the model's four blocks on caller-provided rows: what
+// IWAE.sample / conditional_sample (iwae2.py:184-213) and CIWAE.sample (task04.py:190-209) evaluate outside `call`.
+extern "C" int iwae_block_forward(iwae_ctx* ctx, const float* params, int32_t block, const float* in, int32_t R,
+                                  float* mu, float* sd, void* stream) {
+  IWAE_REQUIRE(ctx && params && in && mu && sd, "iwae_block_forward: null argument");
+  IWAE_REQUIRE(R > 0, "iwae_block_forward: R must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ModelP& m = ctx->model;
+  const BlockP* blk = nullptr;
+  switch (block) {
+    case IWAE_BLOCK_ENCODER: blk = &m.enc1; break;
+    case IWAE_BLOCK_ENCODER2: IWAE_REQUIRE(m.two_layer(), "iwae_block_forward: model has no q(z2|z1) block"); blk = &m.enc2; break;
+    case IWAE_BLOCK_DECODER21: IWAE_REQUIRE(m.two_layer(), "iwae_block_forward: model has no p(z1|z2) block"); blk = &m.dec21; break;
+    case IWAE_BLOCK_PRIOR: IWAE_REQUIRE(m.learned_prior(), "iwae_block_forward: model has no learned prior block"); blk = &m.prior; break;
+    default: IWAE_REQUIRE(false, "iwae_block_forward: unknown block %d", block);
+  }
+  Arena& ar = ctx->arena;
+  ar.reset();
+  float *h1, *h2;
+  IWAE_TRY(ar.get(&h1, (size_t)R * blk->l1.n_out)); IWAE_TRY(ar.get(&h2, (size_t)R * blk->l2.n_out));
+  return block_fwd_f32(params, *blk, in, blk->l1.n_in, R, h1, h2, mu, sd, st);
+}
+
 extern "C" int iwae_sir(const float* al, int32_t L, const double* uniforms, int32_t n_uniforms, int32_t size,
                         int64_t* out_idx, int32_t* out_consumed, void* stream) {
   IWAE_REQUIRE(al && uniforms && out_idx && out_consumed, "iwae_sir: null argument");

@@ -63,3 +63,48 @@ class MyMetric:
 
     def reset_states(self):
         self.VALUES, self.N = [], []
+
+
+class DeviceDataset:
+    """The data step in front of `train_step`, resident on the GPU (main.py:117-120 and
+    utils.bernoullisample, src/utils.py:26-27): pixel intensities [N, n_x] live in HBM once, every epoch is
+    re-binarised by the Philox threshold kernel (`iwae_bernoulli_sample`, keyed on (seed, epoch) so an epoch can
+    be regenerated anywhere) and shuffled on the device; `batch(i)` hands `train_step` a device tensor - no
+    NumPy binomial draws and no host-to-device copy inside the training loop."""
+
+    def __init__(self, intensities, labels=None, batch_size: int = 20, seed: int = 123, device=None):
+        import torch
+        from . import _abi  # noqa: F401  (raises ImportError when the CUDA library is not built: no CPU fallback)
+        self.device = torch.device(device if device is not None else "cuda")
+        self.P = torch.as_tensor(np.asarray(intensities, dtype=np.float32)).to(self.device).contiguous()
+        self.y = None if labels is None else torch.as_tensor(np.asarray(labels, dtype=np.float32)).to(self.device)
+        self.N, self.batch_size, self.seed = self.P.shape[0], int(batch_size), int(seed)
+        self.X = torch.empty_like(self.P)
+        self.perm = torch.arange(self.N, device=self.device)
+        self._gen = torch.Generator(device=self.device)
+        self.epoch = -1
+
+    def __len__(self):
+        return self.N // self.batch_size                    # steps_pr_epoch (main.py:72)
+
+    def start_epoch(self, epoch: int, shuffle: bool = True):
+        """Re-binarise (main.py:117) and reshuffle (tf.data shuffle(Ntrain), main.py:118-119) for `epoch`."""
+        import ctypes as C
+        import torch
+        from ._abi import lib, check
+        with torch.cuda.device(self.device):
+            check(lib.iwae_bernoulli_sample(C.c_void_p(self.P.data_ptr()), self.P.numel(), self.seed, int(epoch),
+                                            C.c_void_p(self.X.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  "iwae_bernoulli_sample")
+        if shuffle:
+            self._gen.manual_seed(self.seed * 1000003 + int(epoch))
+            self.perm = torch.randperm(self.N, device=self.device, generator=self._gen)
+        else:
+            self.perm = torch.arange(self.N, device=self.device)
+        self.epoch = int(epoch)
+        return self
+
+    def batch(self, i: int):
+        """(x [batch, n_x], y [batch] or None) of step i of the current epoch, as device tensors."""
+        idx = self.perm[i * self.batch_size:(i + 1) * self.batch_size]
+        return self.X.index_select(0, idx), (None if self.y is None else self.y.index_select(0, idx))

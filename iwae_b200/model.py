@@ -569,16 +569,56 @@ class IWAE:
         return float(ms.value)
 
     # ---- sampling (iwae1.py:168-178) ------------------------------------------------------------
-    def sample(self, z, y=None, seed=0):
-        """model.sample(z): decode prior samples to Bernoulli probabilities and binary draws."""
-        logits, _ = self._decode(z, y, None, want_logits=True)
-        probs = torch.sigmoid(logits.tensor)
-        n = probs.numel()
+    def _bernoulli(self, logits: torch.Tensor, seed):
+        """(x_sample, probs) of tfd.Bernoulli(logits) - the order every `sample` of the reference returns."""
+        probs = torch.sigmoid(logits)
         out = torch.empty_like(probs)
         with torch.cuda.device(self.device):
-            check(lib.iwae_bernoulli_sample(_ptr(probs), n, int(seed), 0, _ptr(out), _stream_ptr()),
+            check(lib.iwae_bernoulli_sample(_ptr(probs), probs.numel(), int(seed), 0, _ptr(out), _stream_ptr()),
                   "iwae_bernoulli_sample")
-        return DeviceValue(probs), DeviceValue(out)
+        return DeviceValue(out), DeviceValue(probs)
+
+    def _block(self, block_id: int, inp: torch.Tensor, n_out: int):
+        """(loc, scale) of one BasicBlock of the model on rows `inp` (iwae1.py:36-44)."""
+        rows = inp.reshape(-1, inp.shape[-1]).contiguous()
+        mu, sd = self._alloc(rows.shape[0], n_out), self._alloc(rows.shape[0], n_out)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_block_forward(self._ctx, _ptr(self.params), block_id, _ptr(rows), rows.shape[0], _ptr(mu),
+                                         _ptr(sd), _stream_ptr()), "iwae_block_forward")
+        lead = tuple(inp.shape[:-1])
+        return mu.view(*lead, n_out), sd.view(*lead, n_out)
+
+    def _normal(self, seed, stream_id, n, rows, d):
+        """eps [n, rows, d] from the device Philox generator (the noise source of every sampling call)."""
+        eps = self._alloc(n, rows, d)
+        with torch.cuda.device(self.device):
+            check(lib.iwae_philox_normal(int(seed), stream_id, 0, rows, n, d, _ptr(eps), _stream_ptr()), "iwae_philox_normal")
+        return eps
+
+    def sample(self, z, y=None, seed=0):
+        """model.sample(z) -> (x_sample, probs) (iwae1.py:168-178): decode prior samples to Bernoulli
+        probabilities and one binary draw each."""
+        logits, _ = self._decode(z, y, None, want_logits=True)
+        return self._bernoulli(logits.tensor, seed)
+
+    def posterior_grid(self, x, range_x, range_y, n1=200, n2=200):
+        """The true-posterior grid of tasks/plot_task01.py:46-70 for a 2-D latent: log p(z|x) on an n2 x n1 grid
+        (normalised over the grid with logsumexp) and the variational log q(z|x) on the same grid.  Returns
+        (log_posterior [n2,n1], variational_log_posterior [n2,n1], grid [n1*n2, 2])."""
+        if self._d1 != 2 or self._cfg.n_cond:
+            raise ValueError("posterior_grid needs an unconditional model with a 2-D latent (tasks/task01.py:84)")
+        xs = torch.linspace(float(range_x[0]), float(range_x[1]), n1, device=self.device, dtype=_F32)
+        ys = torch.linspace(float(range_y[0]), float(range_y[1]), n2, device=self.device, dtype=_F32)
+        Y1, X1 = torch.meshgrid(ys, xs, indexing="ij")                      # get_grid: np.meshgrid(x, y)
+        grid = torch.stack([X1.reshape(-1), Y1.reshape(-1)], dim=1).contiguous()
+        x1 = self._dev(x).reshape(1, -1)
+        _, lpxz = self._decode(grid, None, x1, want_logits=False)
+        lpz = (-0.5 * grid * grid - 0.5 * float(np.log(2.0 * np.pi))).sum(-1)
+        unnorm = lpxz.tensor + lpz
+        log_post = unnorm - torch.logsumexp(unnorm, 0)
+        mu, sd = self._block(_abi.BLOCK_ENCODER, x1, 2)
+        lq = (-0.5 * ((grid - mu) / sd) ** 2 - (0.5 * float(np.log(2.0 * np.pi)) + torch.log(sd))).sum(-1)
+        return DeviceValue(log_post.view(n2, n1)), DeviceValue(lq.view(n2, n1)), DeviceValue(grid)
 
     @staticmethod
     def write_to_tensorboard(res, step, writer=None):
@@ -646,6 +686,27 @@ class IWAE2(IWAE):
         bufs = self._train(x, None, k, beta, optimizer, oid, eps, eps2, seed)
         return self._result(bufs, k, beta)
 
+
+    def _z1_given_z2(self, z2, n, seed):
+        z2 = self._dev(z2)
+        if z2.shape[-1] != self._d2:
+            raise ValueError(f"z2 must have last dim {self._d2}")
+        mu, sd = self._block(_abi.BLOCK_DECODER21, z2, self._d1)
+        rows = mu.reshape(-1, self._d1).shape[0]
+        eps = self._normal(seed, 1, n, rows, self._d1).view(n, *mu.shape)
+        return mu + sd * eps                                                # pz1z2.sample(n) (A.2)
+
+    def sample(self, z2, seed=0):
+        """iwae2.IWAE.sample (iwae2.py:184-198): z1 ~ p(z1|z2), x ~ Bernoulli(decode(z1)) -> (x_sample, probs)."""
+        z1 = self._z1_given_z2(z2, 1, seed)[0]
+        logits, _ = self._decode(z1, None, None, want_logits=True)
+        return self._bernoulli(logits.tensor, seed)
+
+    def conditional_sample(self, z2, seed=0, n=10):
+        """iwae2.IWAE.conditional_sample (iwae2.py:200-213): ten z1 draws per fixed z2 -> ([10, ..., 784] x2)."""
+        z1 = self._z1_given_z2(z2, n, seed)
+        logits, _ = self._decode(z1, None, None, want_logits=True)
+        return self._bernoulli(logits.tensor, seed)
 
 class IWAEDReG(IWAE):
     """tasks/task02.py:27-101: the doubly-reparameterised gradient estimator.  `call` returns the
@@ -719,6 +780,21 @@ class CIWAE(IWAE):
         bufs = self._train(x, y, k, beta, optimizer, oid, eps, None, seed)
         return self._result(bufs, k, beta)
 
+
+    def sample(self, z, y, seed=0):
+        """CIWAE.sample(z, y) (task04.py:190-209 / task05.py:185-199): every row of z decoded under the single
+        label y; with the learned prior z is first mapped through p(z|y): z_new = loc + scale * z."""
+        z = self._dev(z)
+        rows = z.reshape(-1, self._d1)
+        label = float(np.asarray(y).reshape(-1)[0])
+        if self._learned_prior:
+            onehot = torch.zeros(1, self._cfg.n_cond, device=self.device, dtype=_F32)
+            onehot[0, int(label)] = 1.0
+            mu, sd = self._block(_abi.BLOCK_PRIOR, onehot, self._d1)
+            rows = (mu + sd * rows).contiguous()
+        yv = torch.full((rows.shape[0],), label, device=self.device, dtype=_F32)
+        logits, _ = self._decode(rows, yv, None, want_logits=True)
+        return self._bernoulli(logits.tensor.view(*z.shape[:-1], self._cfg.n_x), seed)
 
 class BasicBlock:
     """iwae1.BasicBlock(n_hidden, n_latent) as tasks/task04.py:108 constructs it directly.  In this

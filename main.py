@@ -35,6 +35,8 @@ parser.add_argument("--n_test", type=int, default=10000)
 parser.add_argument("--eval_samples", type=int, default=5000)
 parser.add_argument("--reference_eval_loop", action="store_true")
 parser.add_argument("--max_steps", type=int, default=-1, help="stop early (smoke runs)")
+parser.add_argument("--device_data", action="store_true",
+                    help="keep the train set in HBM: per-epoch Philox re-binarisation + shuffle on the device, no H2D per step")
 parser.add_argument("--fused_monitor", action="store_true",
                     help="monitor the test set through the fused evaluation kernel (iwae_elbo / vae_elbo only, beta = 1)")
 
@@ -70,9 +72,13 @@ def main(argv=None):
     start = time.time()
     step = 0
     done = False
+    device_data = utils.DeviceDataset(Xtrain, batch_size=batch_size, seed=123) if args.device_data else None
     for epoch in range(epochs):
-        Xtrain_binarized = utils.bernoullisample(Xtrain)
-        perm = np.random.permutation(Ntrain)          # tf.data shuffle(Ntrain).batch(batch_size)
+        if device_data is not None:
+            device_data.start_epoch(epoch)
+        else:
+            Xtrain_binarized = utils.bernoullisample(Xtrain)
+            perm = np.random.permutation(Ntrain)      # tf.data shuffle(Ntrain).batch(batch_size)
         if args.epochs == -1 and epoch in learning_rate_dict:
             new_learning_rate = learning_rate_dict[epoch]
             old_learning_rate = optimizer.learning_rate.numpy()
@@ -80,7 +86,10 @@ def main(argv=None):
             optimizer.learning_rate.assign(new_learning_rate)
         for _step in range(steps_pr_epoch):
             step = _step + steps_pr_epoch * epoch
-            x_batch = Xtrain_binarized[perm[_step * batch_size:(_step + 1) * batch_size]]
+            if device_data is not None:
+                x_batch, _ = device_data.batch(_step)
+            else:
+                x_batch = Xtrain_binarized[perm[_step * batch_size:(_step + 1) * batch_size]]
             beta = 1.0
             res = model.train_step(x_batch, n_samples, beta, optimizer, objective=objective)
             if step % 200 == 0:

@@ -445,3 +445,19 @@ def philox_normal(seed: int, stream: int, img_offset: int, B: int, k: int, d: in
         out[..., 2 * j::4] = rad * np.cos(2.0 * np.pi * u2)
         out[..., 2 * j + 1::4] = rad * np.sin(2.0 * np.pi * u2)
     return out[..., :d].astype(np.float32)
+
+
+def philox_bernoulli(p: np.ndarray, seed: int, epoch: int = 0) -> np.ndarray:
+    """utils.bernoullisample (src/utils.py:26-27) as the CUDA path draws it (kernels_f32.cu,
+    bernoulli_sample_kernel): flat element i uses word i%4 of Philox4x32-10 with counter
+    (i//4 lo, i//4 hi, epoch, 0x42), key = (seed lo, seed hi); u = (r >> 8) * 2^-24 in fp32; x = 1 if u < p."""
+    flat = np.asarray(p, dtype=np.float32).reshape(-1)
+    n = flat.size
+    nq = (n + 3) // 4
+    q = np.arange(nq, dtype=np.uint64)
+    ctr = np.stack([(q & np.uint64(0xFFFFFFFF)).astype(np.uint32), (q >> np.uint64(32)).astype(np.uint32),
+                    np.full(nq, epoch & 0xFFFFFFFF, dtype=np.uint32), np.full(nq, 0x42, dtype=np.uint32)], axis=-1)
+    key = np.broadcast_to(np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32), (nq, 2))
+    r = philox4x32_10(ctr, key).reshape(-1)[:n]
+    u = ((r >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    return (u < flat).astype(np.float32).reshape(np.shape(p))

@@ -5,7 +5,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from iwae_b200.data import bernoullisample, MyMetric, synthetic_mnist  # noqa: E402,F401
+from iwae_b200.data import bernoullisample, MyMetric, synthetic_mnist, DeviceDataset  # noqa: E402,F401
 from iwae_b200 import data as _data  # noqa: E402
 
 

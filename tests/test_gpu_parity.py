@@ -288,7 +288,7 @@ def test_decoder_tools(oracle):
     mu, sd = oracle.basic_block(p, "encoder.encode_x_to_z", torch.tensor(case["x"], dtype=torch.float64))
     assert rel(qzx.loc.numpy(), mu.numpy()) < RTOL and rel(qzx.scale.numpy(), sd.numpy()) < RTOL
     assert zz.shape == (4, 2, 2)
-    probs, xs = m.sample(z[:, 0])
+    xs, probs = m.sample(z[:, 0])               # (x_sample, probs), iwae1.py:178
     assert probs.shape == (9, 784) and set(np.unique(xs.numpy())) <= {0.0, 1.0}
 
 
