@@ -221,13 +221,13 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
 // Micro-benchmark: `reps` back-to-back tcgen05.mma (M=128, K=16, fp16, smem A and B in the fused kernel's
 // no-swizzle K-major layout) of width N into one accumulator; returns cycles from first issue to the
 // commit's mbarrier completion.  Sizes the chunk width of the fused kernel (SS-mode A-operand fetch).
-__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int nctas_dummy, long long* out) {
+__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int mode, long long* out) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2, bar3;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (128 + N) * 16 * 2 * 4 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
-  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_init(&bar3, 1); fence_barrier_init(); }
   __syncwarp();
   if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
   fence_proxy_async();
@@ -240,16 +240,91 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int nc
     const uint32_t idesc = make_idesc((uint32_t)N);
     const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem) + 128 * 16 * 2 * 4;
     t0 = clock64();
-    if (elect_one_sync()) {
-      for (int r = 0; r < reps; ++r) {
+    if (mode == 0) {
+      if (elect_one_sync()) {
+        for (int r = 0; r < reps; ++r) {
+          const uint32_t ks = r & 3;
+          const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
+          umma_f16(tmem_base, ad, bd, idesc, r > 0);
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+    } else if (mode & 32) {
+      // as the fused kernel's slab loop (elect per slab of two MMAs) but unrolled by four, so that consecutive
+      // slabs use different uniform registers for their descriptors
+#pragma unroll 4
+      for (int r = 0; r < reps; r += 2) {
+        if (mode & 2) tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t ks = r & 3;
+          const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
+          umma_f16(tmem_base, ad, bd, idesc, r > 0);
+          if (r + 1 < reps) umma_f16(tmem_base, ad + (uint64_t)(2u * 128u), bd + (uint64_t)(2u * (uint32_t)N), idesc, true);
+          if (mode & 1) umma_commit(&bar2);
+        }
+        if (mode & 4) __syncwarp();
+      }
+      if (elect_one_sync()) umma_commit(&bar);
+      __syncwarp();
+    } else if (mode & 16) {
+      // warp-uniform descriptor arithmetic OUTSIDE the elected region (uniform datapath), only the
+      // tcgen05 instructions inside it
+      for (int r = 0; r < reps; r += 2) {
+        if (mode & 2) tc_fence_after();
         const uint32_t ks = r & 3;
         const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
         const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
-        umma_f16(tmem_base, ad, bd, idesc, r > 0);
+        const uint64_t ad1 = ad + (uint64_t)(2u * 128u), bd1 = bd + (uint64_t)(2u * (uint32_t)N);
+        const bool two = r + 1 < reps;
+        if (elect_one_sync()) {
+          umma_f16(tmem_base, ad, bd, idesc, r > 0);
+          if (two) umma_f16(tmem_base, ad1, bd1, idesc, true);
+          if (mode & 1) umma_commit(&bar2);
+        }
+        if (mode & 4) __syncwarp();
       }
-      umma_commit(&bar);
+      if (elect_one_sync()) umma_commit(&bar);
+      __syncwarp();
+    } else if (mode & 8) {
+      // everything inside ONE elected thread: per slab (bit 0) a commit to a second mbarrier, (bit 1) a
+      // try_wait on an already-completed mbarrier
+      if (elect_one_sync()) {
+        mbar_arrive(&bar3);
+        for (int r = 0; r < reps; r += 2) {
+          if (mode & 2) { while (!mbar_try_wait(&bar3, 0)) {} tc_fence_after(); }
+          for (int rr = r; rr < min(r + 2, reps); ++rr) {
+            const uint32_t ks = rr & 3;
+            const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
+            const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
+            umma_f16(tmem_base, ad, bd, idesc, rr > 0);
+          }
+          if (mode & 1) umma_commit(&bar2);
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+    } else {
+      // the issue pattern of the fused kernel: per slab of two MMAs a warp-uniform iteration with
+      // (mode bit 0) a commit to a second mbarrier, (bit 1) a tcgen05 fence, (bit 2) an elect + __syncwarp
+      for (int r = 0; r < reps; r += 2) {
+        if (mode & 2) tc_fence_after();
+        if (elect_one_sync()) {
+          for (int rr = r; rr < min(r + 2, reps); ++rr) {
+            const uint32_t ks = rr & 3;
+            const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
+            const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
+            umma_f16(tmem_base, ad, bd, idesc, rr > 0);
+          }
+          if (mode & 1) umma_commit(&bar2);
+        }
+        if (mode & 4) __syncwarp();
+      }
+      if (elect_one_sync()) umma_commit(&bar);
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait(&bar, 0, 901);
     const long long t1 = clock64();
     if (tid == 32) out[blockIdx.x] = t1 - t0;
@@ -491,39 +566,35 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-    // Two issue orders per layer:
-    //  * layers whose K fits four slabs (the q(z2|z1) / p(z1|z2) chain and the first decoder layer) run
-    //    SUB-TILE-SEQUENTIAL: all MMAs of sub-tile 0, then all MMAs of sub-tile 1 over the same slabs
-    //    (still resident in the ring).  The two sub-tiles therefore run half a layer apart, and the
-    //    epilogue of one overlaps the MMAs of the other - the dependent layer chain no longer leaves
-    //    the tensor pipe and the MUFU idle in turns.
-    //  * wide layers (K = 208: second decoder layer and the 784-logit layer) interleave the sub-tiles
-    //    per slab so a slab leaves the ring as soon as both have used it; there the double-buffered
-    //    accumulators provide the overlap.
+    // ===================== MMA issuer: ONE elected thread runs the whole role =====================
+    // Per slab of two MMAs the issuing thread executes a dependent chain of ~40-65 instructions (barrier
+    // try-wait, descriptor arithmetic, R2UR moves into the uniform registers tcgen05.mma reads, commit): with an
+    // elect / reconverge / __syncwarp per slab that chain took ~400 cycles per slab - 200 per MMA against the 56
+    // the tensor pipe needs (scripts/umma_bench3.py isolates it).  Running the role inside a single elected
+    // region removes the per-slab warp-convergence instructions; the barrier waits are done by that one thread.
+    // Two issue orders per layer (NSUB = 2 only; with NSUB = 1 they coincide):
+    //  * layers whose K fits the ring run SUB-TILE-SEQUENTIAL (all MMAs of sub-tile 0, then of sub-tile 1 over
+    //    the same resident slabs), so the epilogue of one overlaps the MMAs of the other;
+    //  * wide layers (K = 208) interleave the sub-tiles per slab so a slab leaves the ring as soon as both used it.
+    if (elect_one_sync()) {
     uint32_t stage = 0, phase = 0, cc = 0;
     uint32_t act_phase[NSUB] = {};
     uint32_t empty_phase[NSUB][2] = {};
     const uint32_t ring0 = smem_u32(S.ring[0]);
     const uint32_t z0 = smem_u32(S.sub[0].bufZ), p0 = smem_u32(S.sub[0].bufP);
     const uint32_t sub_stride16 = (uint32_t)sizeof(SubTile) >> 4;
-    int tn = (lane == 0) ? 0 : TRACE_SLOTS, tl = 0;
+    int tn = 0, tl = 0;
 
-    // MMAs of one slab for sub-tile u (one elected lane)
+    // MMAs of one slab for sub-tile u; descriptors: only the 14-bit start-address field changes between MMAs
     auto issue_slab = [&](int u, uint32_t st, uint32_t a_base0, int k0, int k_pad, uint32_t n, uint32_t idesc,
                           uint32_t d_tmem, bool release) {
-      if (elect_one_sync()) {
-        // descriptors: only the 14-bit start-address field changes between MMAs
-        const uint64_t bd0 = make_smem_desc(ring0 + st * SLAB_BYTES, n * 16u, 128);
-        const uint64_t ad0 = make_smem_desc(a_base0 + ((uint32_t)k0 >> 3) * (TILE_M * 16), TILE_M * 16, 128) +
-                             (uint64_t)((uint32_t)u * sub_stride16);
-        const int ksteps = min(SLAB_K, k_pad - k0) / 16;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_f16(d_tmem, ad0 + (uint64_t)((uint32_t)ks * 2u * TILE_M), bd0 + (uint64_t)((uint32_t)ks * 2u * n), idesc,
-                   (k0 | ks) != 0);
-        if (release) umma_commit(&S.empty[st]);     // slab consumed when these MMAs retire
-      }
-      __syncwarp();
+      const uint64_t bd0 = make_smem_desc(ring0 + st * SLAB_BYTES, n * 16u, 128);
+      const uint64_t ad0 = make_smem_desc(a_base0 + ((uint32_t)k0 >> 3) * (TILE_M * 16), TILE_M * 16, 128) +
+                           (uint64_t)((uint32_t)u * sub_stride16);
+      static_assert(SLAB_K == 32, "two MMAs per slab");
+      umma_f16(d_tmem, ad0, bd0, idesc, k0 != 0);
+      if (k_pad - k0 > 16) umma_f16(d_tmem, ad0 + (uint64_t)(2u * TILE_M), bd0 + (uint64_t)(2u * n), idesc, 1u);
+      if (release) umma_commit(&S.empty[st]);     // slab consumed when these MMAs retire
     };
 
     for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
@@ -531,7 +602,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
         const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act;
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
         const int nslabs = (k_pad + SLAB_K - 1) / SLAB_K;
-        const bool sequential = nslabs <= 4;
+        const bool sequential = NSUB > 1 && nslabs <= 4;
         trace_ev(args, 1, tn, tl * 10000 + l * 100 + 0);
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = cc & 1;
@@ -548,12 +619,11 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
               trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2 + 5 * u);
               uint32_t st = stage, ph = phase;
               for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
-                if (u == 0) { mbar_wait(&S.full[st], ph, 202); tc_fence_after(); }
+                if (u == 0) mbar_wait(&S.full[st], ph, 202);
                 issue_slab(u, st, a_base0, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
                 if (++st == NSTAGES) { st = 0; ph ^= 1; }
               }
-              if (elect_one_sync()) umma_commit(&S.acc_full[u][buf]);
-              __syncwarp();
+              umma_commit(&S.acc_full[u][buf]);
               trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3 + 5 * u);
               st_end = st; ph_end = ph;
             }
@@ -569,23 +639,21 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
             trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
             for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
               mbar_wait(&S.full[stage], phase, 202);
-              tc_fence_after();
 #pragma unroll
               for (int u = 0; u < NSUB; ++u)
                 issue_slab(u, stage, a_base0, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
               if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
-            if (elect_one_sync()) {
 #pragma unroll
-              for (int u = 0; u < NSUB; ++u) umma_commit(&S.acc_full[u][buf]);
-            }
-            __syncwarp();
+            for (int u = 0; u < NSUB; ++u) umma_commit(&S.acc_full[u][buf]);
             trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
           }
           ++cc;
         }
       }
     }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue warps =====================
     // Sixteen warps: eight per 128-row sub-tile.  Within a sub-tile, warps e and e+4 share one TMEM
@@ -1280,6 +1348,7 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
     tp.attr_set = true;
   }
   int grid = (int)std::min<int64_t>((a.n_tiles + tc::NSUB - 1) / tc::NSUB, (int64_t)ctx->sm_count * tc::CTAS_PER_SM);
+  if (const char* g = getenv("IWAE_TC_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // diagnostics only
   if (!ctx->ev_k0) { CUDA_TRY(cudaEventCreate(&ctx->ev_k0)); CUDA_TRY(cudaEventCreate(&ctx->ev_k1)); }
   CUDA_TRY(cudaEventRecord(ctx->ev_k0, st));
   kern<<<grid, tc::NUM_THREADS, smem, st>>>(a);
@@ -1311,7 +1380,8 @@ int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream
   IWAE_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && nctas > 0, "umma_bench: bad argument");
   const size_t smem = (size_t)(128 + N) * 16 * 2 * 4;
   CUDA_TRY(cudaFuncSetAttribute(tc::umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::umma_bench_kernel<<<nctas, 128, smem, st>>>(N, reps, nctas, out_cycles_dev);
+  const char* md = getenv("IWAE_UMMA_BENCH_MODE");      // diagnostics: issue-pattern variants, see the kernel
+  tc::umma_bench_kernel<<<nctas, 128, smem, st>>>(N, reps, md ? atoi(md) : 0, out_cycles_dev);
   LAUNCH_CHECK();
   return 0;
 }
