@@ -337,6 +337,9 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int mo
 // ------------------------------------------------------------------------------------------------
 // Fused evaluation kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef IWAE_PRODUCER_SLEEP
+#define IWAE_PRODUCER_SLEEP 32
+#endif
 constexpr int TILE_M = 128;
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_CHUNKS = 7;
@@ -521,6 +524,13 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
   const Program& P = c_prog;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_macro = (args.n_tiles + NSUB - 1) / NSUB;
+  // Each CTA owns a CONTIGUOUS range of tiles: consecutive tiles then belong to the same image (k/128 tiles per
+  // image), so the per-image constants (x, mu, std: ~3k cycles of global-load latency and two CTA barriers per
+  // tile when reloaded) are fetched once per image instead of once per tile.
+  // (tile indices fit 32 bits: n_tiles < 2^31 is checked on the host)
+  const uint32_t per_cta = ((uint32_t)n_macro + gridDim.x - 1u) / gridDim.x;
+  const uint32_t mt_begin = min(blockIdx.x * per_cta, (uint32_t)n_macro);
+  const uint32_t mt_end = min(mt_begin + per_cta, (uint32_t)n_macro);
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
@@ -537,34 +547,31 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
   const uint32_t tmem_base = S.tmem_base;
 
   if (warp == 0) {
-    // ===================== weight producer =====================
-    // One pass over the packed weights per macro-tile; every slab is used by the MMAs of BOTH
-    // sub-tiles, so each weight byte crosses L2 -> smem once per 256 rows.
-    // The whole warp walks the loops convergently and ONE elected lane issues: in warp-uniform code
-    // the compiler feeds UBLKCP / UTCHMMA from uniform registers directly; inside an `if (lane == 0)`
-    // region it wraps every such instruction in an ELECT / R2UR / BRA.U.ANY waterfall loop (v3: ~160
-    // cycles of issue per MMA, three times the tensor-pipe time of the MMA itself).
-    uint32_t stage = 0, phase = 0;
-    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x) {
-      const uint8_t* src = args.wpack;
-      for (int l = 0; l < P.nlayers; ++l) {
-        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad;
-        for (int c = 0; c < nchunks; ++c) {
-          const uint32_t cn = (uint32_t)P.L[l].chunk_n[c];
-          for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
-            const uint32_t bytes = cn * (uint32_t)min(SLAB_K, k_pad - k0) * 2u;
-            mbar_wait(&S.empty[stage], phase ^ 1, 100, 200);
-            if (elect_one_sync()) {
+    // ===================== weight producer: one elected thread =====================
+    // One pass over the packed weights per tile (every slab is used by the MMAs of all NSUB sub-tiles); the ring
+    // keeps NSTAGES slabs in flight ahead of the MMA issuer.  Like the MMA role below, the whole role runs inside
+    // a single elected region (no per-slab elect / reconverge).
+    if (elect_one_sync()) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t mt = mt_begin; mt < mt_end; ++mt) {
+        const uint8_t* src = args.wpack;
+        for (int l = 0; l < P.nlayers; ++l) {
+          const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad;
+          for (int c = 0; c < nchunks; ++c) {
+            const uint32_t cn = (uint32_t)P.L[l].chunk_n[c];
+            for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
+              const uint32_t bytes = cn * (uint32_t)min(SLAB_K, k_pad - k0) * 2u;
+              mbar_wait(&S.empty[stage], phase ^ 1, 100, IWAE_PRODUCER_SLEEP);
               mbar_expect_tx(&S.full[stage], bytes);
               bulk_g2s(S.ring[stage], src, bytes, &S.full[stage]);
+              src += bytes;
+              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            src += bytes;
-            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer: ONE elected thread runs the whole role =====================
     // Per slab of two MMAs the issuing thread executes a dependent chain of ~40-65 instructions (barrier
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     if (elect_one_sync()) {
     uint32_t stage = 0, phase = 0, cc = 0;
     uint32_t act_phase[NSUB] = {};
-    uint32_t empty_phase[NSUB][2] = {};
+    uint32_t empty_bits = 0;     // phase bit of acc_empty[u][buf] at bit u*2+buf (a register, not a dynamically indexed array)
     const uint32_t ring0 = smem_u32(S.ring[0]);
     const uint32_t z0 = smem_u32(S.sub[0].bufZ), p0 = smem_u32(S.sub[0].bufP);
     const uint32_t sub_stride16 = (uint32_t)sizeof(SubTile) >> 4;
@@ -597,7 +604,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       if (release) umma_commit(&S.empty[st]);     // slab consumed when these MMAs retire
     };
 
-    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
+    for (uint32_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
       for (int l = 0; l < P.nlayers; ++l) {
         const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act;
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
@@ -613,8 +620,8 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
 #pragma unroll
             for (int u = 0; u < NSUB; ++u) {
               if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; }
-              mbar_wait(&S.acc_empty[u][buf], empty_phase[u][buf] ^ 1, 201);
-              empty_phase[u][buf] ^= 1;
+              mbar_wait(&S.acc_empty[u][buf], ((empty_bits >> (u * 2 + buf)) & 1u) ^ 1u, 201);
+              empty_bits ^= 1u << (u * 2 + buf);
               tc_fence_after();
               trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2 + 5 * u);
               uint32_t st = stage, ph = phase;
@@ -631,9 +638,9 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           } else {
 #pragma unroll
             for (int u = 0; u < NSUB; ++u) {
-              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; }
-              mbar_wait(&S.acc_empty[u][buf], empty_phase[u][buf] ^ 1, 201);
-              empty_phase[u][buf] ^= 1;
+              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; trace_ev(args, 1, tn, tl * 10000 + l * 100 + 1); }
+              mbar_wait(&S.acc_empty[u][buf], ((empty_bits >> (u * 2 + buf)) & 1u) ^ 1u, 201);
+              empty_bits ^= 1u << (u * 2 + buf);
             }
             tc_fence_after();
             trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
@@ -669,17 +676,19 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     const int et = (e_warp & 7) * 32 + lane; // 0..255 among the sub-tile's epilogue threads
     SubTile& T = S.sub[u];
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t full_phase[2] = {0, 0};
+    uint32_t full_bits = 0;      // phase bit of acc_full[u][buf] at bit buf
     uint32_t cc = 0;
     const int d1 = P.d1, nx = P.nx;
     const int nx_pad = (nx + 15) & ~15;
     const int d1_full = d1 & ~7;             // dims covered by complete 8-wide groups
-    int tn = (e_warp == 0 && lane == 0) ? 0 : TRACE_SLOTS, tl = 0;     // only one thread records
+    int tn = ((e_warp == 0 || e_warp == 7) && lane == 0) ? 0 : TRACE_SLOTS, tl = 0;     // two threads record: one per column half
+    const int trole = (e_warp == 0) ? 2 : 0;
+    uint32_t prev_img = 0xFFFFFFFFu;
 
-    for (int64_t mt = blockIdx.x; mt < n_macro; mt += gridDim.x, ++tl) {
-      trace_ev(args, 2, tn, tl * 10000 + 9000);
+    for (uint32_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
+      trace_ev(args, trole, tn, tl * 10000 + 9000);
       // (tile indices fit 32 bits: n_tiles < 2^31 is checked on the host; 32-bit division is much cheaper)
-      uint32_t tile = (uint32_t)mt * NSUB + u;
+      uint32_t tile = mt * NSUB + u;
       const bool tile_ok = tile < (uint32_t)args.n_tiles;       // the last macro-tile may be half empty
       if (!tile_ok) tile = (uint32_t)args.n_tiles - 1u;
       const uint32_t img32 = tile / (uint32_t)args.tiles_per_img;
@@ -688,7 +697,9 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       const int s = tin * args.rows_per_tile + row;                 // sample index of this row
       const bool valid = tile_ok && (row < args.rows_per_tile) && (s < args.k);
 
-      // ---- per-image constants into smem
+      // ---- per-image constants into smem (only when the image changes)
+      if (img32 != prev_img) {
+      prev_img = img32;
       epi_bar_sync(u);
       for (int j = et; j < nx_pad; j += 256)
         T.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
@@ -716,6 +727,8 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       }
       if (et == 0 && P.cond) T.label = (int)(unsigned char)(int)__ldg(args.y + img);
       epi_bar_sync(u);
+      }
+      trace_ev(args, trole, tn, tl * 10000 + 9050);
 
       // This thread's partial log-weight: log_w = lpxz + lp(prior terms) - lq(terms), all sums over
       // columns.  Precise mode adds log-probabilities term by term in TFP's op order; FAST mode
@@ -820,7 +833,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.act_ready[u]);
-      trace_ev(args, 2, tn, tl * 10000 + 9100);
+      trace_ev(args, trole, tn, tl * 10000 + 9100);
 
       // ---- layers
       float bern_s = 0.f, bern_a = 0.f, bern_lg = 0.f;     // FAST Bernoulli accumulators (log2 units)
@@ -831,18 +844,18 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           // all chunks' MMAs must have retired before the input buffer is overwritten
           for (int c = 0; c < Ly.nchunks; ++c) {
             const uint32_t b = (cc + c) & 1;
-            mbar_wait(&S.acc_full[u][b], full_phase[b], 300);
-            full_phase[b] ^= 1;
+            mbar_wait(&S.acc_full[u][b], (full_bits >> b) & 1u, 300);
+            full_bits ^= 1u << b;
           }
         }
         for (int c = 0; c < Ly.nchunks; ++c) {
           const uint32_t buf = cc & 1;
           if (!(Ly.inplace && Ly.nchunks > 1)) {
-            mbar_wait(&S.acc_full[u][buf], full_phase[buf], 301);
-            full_phase[buf] ^= 1;
+            mbar_wait(&S.acc_full[u][buf], (full_bits >> buf) & 1u, 301);
+            full_bits ^= 1u << buf;
           }
           tc_fence_after();
-          trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 5);
+          trace_ev(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 5);
           const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(u * 2 + buf) * 128u;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
           const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
@@ -1027,13 +1040,16 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.acc_empty[u][buf]);
-          trace_ev(args, 2, tn, tl * 10000 + l * 100 + c * 10 + 6);
+          trace_ev(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 6);
           ++cc;
         }
         if (Ly.signal_act) {
+#ifndef IWAE_EXP_NOFENCE
           fence_proxy_async();
+#endif
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.act_ready[u]);
+          trace_ev(args, trole, tn, tl * 10000 + l * 100 + 7);
         }
       }
       if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
