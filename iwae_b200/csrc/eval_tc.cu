@@ -401,8 +401,9 @@ struct EvalArgs {
 
 #define TRACE_SLOTS 512
 // tag = tile_local*10000 + layer*100 + chunk*10 + phase
+template <bool TRACE>
 __device__ __forceinline__ void trace_ev(const EvalArgs& a, int role, int& n, int tag) {
-  if (a.trace && blockIdx.x < 4 && n < TRACE_SLOTS) {
+  if (TRACE && a.trace && blockIdx.x < 4 && n < TRACE_SLOTS) {
     long long* p = a.trace + (((size_t)blockIdx.x * 3 + role) * TRACE_SLOTS + n) * 2;
     p[0] = tag; p[1] = clock64();
     ++n;
@@ -517,7 +518,8 @@ __device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int
   }
 }
 
-template <bool FAST>
+// TRACE: the timeline instrumentation (IWAE_TC_TRACE) is compiled into a separate instantiation
+template <bool FAST, bool TRACE>
 __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(EvalArgs args) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
         const int nslabs = (k_pad + SLAB_K - 1) / SLAB_K;
         const bool sequential = NSUB > 1 && nslabs <= 4;
-        trace_ev(args, 1, tn, tl * 10000 + l * 100 + 0);
+        trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 0);
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = cc & 1;
           const uint32_t n = (uint32_t)P.L[l].chunk_n[c];
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
               mbar_wait(&S.acc_empty[u][buf], ((empty_bits >> (u * 2 + buf)) & 1u) ^ 1u, 201);
               empty_bits ^= 1u << (u * 2 + buf);
               tc_fence_after();
-              trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2 + 5 * u);
+              trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2 + 5 * u);
               uint32_t st = stage, ph = phase;
               for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
                 if (u == 0) mbar_wait(&S.full[st], ph, 202);
@@ -631,19 +633,19 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                 if (++st == NSTAGES) { st = 0; ph ^= 1; }
               }
               umma_commit(&S.acc_full[u][buf]);
-              trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3 + 5 * u);
+              trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3 + 5 * u);
               st_end = st; ph_end = ph;
             }
             stage = st_end; phase = ph_end;
           } else {
 #pragma unroll
             for (int u = 0; u < NSUB; ++u) {
-              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; trace_ev(args, 1, tn, tl * 10000 + l * 100 + 1); }
+              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 1); }
               mbar_wait(&S.acc_empty[u][buf], ((empty_bits >> (u * 2 + buf)) & 1u) ^ 1u, 201);
               empty_bits ^= 1u << (u * 2 + buf);
             }
             tc_fence_after();
-            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
+            trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
             for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
               mbar_wait(&S.full[stage], phase, 202);
 #pragma unroll
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
             }
 #pragma unroll
             for (int u = 0; u < NSUB; ++u) umma_commit(&S.acc_full[u][buf]);
-            trace_ev(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
+            trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
           }
           ++cc;
         }
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     // keeps one partial log-weight; the two halves of a row are added through shared memory at the
     // end of the tile.
     const int e_warp = warp - 2;             // 0..15
-    const int u = e_warp >> 3;               // sub-tile
+    const int u = (NSUB == 1) ? 0 : (e_warp >> 3);      // sub-tile
     const int half = (e_warp >> 2) & 1;      // which half of the column groups this warp takes
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -686,10 +688,10 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     uint32_t prev_img = 0xFFFFFFFFu;
 
     for (uint32_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
-      trace_ev(args, trole, tn, tl * 10000 + 9000);
+      trace_ev<TRACE>(args, trole, tn, tl * 10000 + 9000);
       // (tile indices fit 32 bits: n_tiles < 2^31 is checked on the host; 32-bit division is much cheaper)
       uint32_t tile = mt * NSUB + u;
-      const bool tile_ok = tile < (uint32_t)args.n_tiles;       // the last macro-tile may be half empty
+      const bool tile_ok = (NSUB == 1) || tile < (uint32_t)args.n_tiles;       // the last macro-tile may be half empty
       if (!tile_ok) tile = (uint32_t)args.n_tiles - 1u;
       const uint32_t img32 = tile / (uint32_t)args.tiles_per_img;
       const int64_t img = img32;
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       if (et == 0 && P.cond) T.label = (int)(unsigned char)(int)__ldg(args.y + img);
       epi_bar_sync(u);
       }
-      trace_ev(args, trole, tn, tl * 10000 + 9050);
+      trace_ev<TRACE>(args, trole, tn, tl * 10000 + 9050);
 
       // This thread's partial log-weight: log_w = lpxz + lp(prior terms) - lq(terms), all sums over
       // columns.  Precise mode adds log-probabilities term by term in TFP's op order; FAST mode
@@ -833,7 +835,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.act_ready[u]);
-      trace_ev(args, trole, tn, tl * 10000 + 9100);
+      trace_ev<TRACE>(args, trole, tn, tl * 10000 + 9100);
 
       // ---- layers
       float bern_s = 0.f, bern_a = 0.f, bern_lg = 0.f;     // FAST Bernoulli accumulators (log2 units)
@@ -855,7 +857,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
             full_bits ^= 1u << buf;
           }
           tc_fence_after();
-          trace_ev(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 5);
+          trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 5);
           const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(u * 2 + buf) * 128u;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
           const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
@@ -1040,7 +1042,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.acc_empty[u][buf]);
-          trace_ev(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 6);
+          trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 6);
           ++cc;
         }
         if (Ly.signal_act) {
@@ -1049,7 +1051,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
 #endif
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.act_ready[u]);
-          trace_ev(args, trole, tn, tl * 10000 + l * 100 + 7);
+          trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + 7);
         }
       }
       if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
@@ -1357,10 +1359,13 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   }
 
   const size_t smem = sizeof(tc::SmemLayout) + 128;
-  auto kern = fast ? tc::iwae_eval_tc_kernel<true> : tc::iwae_eval_tc_kernel<false>;
+  auto kern = a.trace ? (fast ? tc::iwae_eval_tc_kernel<true, true> : tc::iwae_eval_tc_kernel<false, true>)
+                      : (fast ? tc::iwae_eval_tc_kernel<true, false> : tc::iwae_eval_tc_kernel<false, false>);
   if (!tp.attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tp.attr_set = true;
   }
   int grid = (int)std::min<int64_t>((a.n_tiles + tc::NSUB - 1) / tc::NSUB, (int64_t)ctx->sm_count * tc::CTAS_PER_SM);
