@@ -376,6 +376,8 @@ struct Layer {
   int chunk_cnt[MAX_CHUNKS];   // real units / dims / pixels in the chunk
   int chunk_off[MAX_CHUNKS];   // first unit / dim / pixel of the chunk
   int wait_act, signal_act, inplace;
+  int split_dst;               // 1: chunk 0 of this (two-chunk, otherwise in-place) layer is written to the z1 buffer instead
+  int src_split;               // > 0: A columns k < src_split are read from the z1 buffer, the rest from `src`
 };
 struct Program {
   int nlayers, two_layer, cond, learned_prior;
@@ -595,20 +597,22 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     int tn = 0, tl = 0;
 
     // MMAs of one slab for sub-tile u; descriptors: only the 14-bit start-address field changes between MMAs
-    auto issue_slab = [&](int u, uint32_t st, uint32_t a_base0, int k0, int k_pad, uint32_t n, uint32_t idesc,
+    auto issue_slab = [&](int u, uint32_t st, uint32_t a_base0, int split, int k0, int k_pad, uint32_t n, uint32_t idesc,
                           uint32_t d_tmem, bool release) {
       const uint64_t bd0 = make_smem_desc(ring0 + st * SLAB_BYTES, n * 16u, 128);
-      const uint64_t ad0 = make_smem_desc(a_base0 + ((uint32_t)k0 >> 3) * (TILE_M * 16), TILE_M * 16, 128) +
-                           (uint64_t)((uint32_t)u * sub_stride16);
+      // A columns below `split` live in the z1 buffer (see build_program: split destination of the layer before)
+      const uint32_t a0 = (k0 < split ? z0 : a_base0) + ((uint32_t)k0 >> 3) * (TILE_M * 16);
+      const uint32_t a1 = (k0 + 16 < split ? z0 : a_base0) + ((uint32_t)(k0 + 16) >> 3) * (TILE_M * 16);
+      const uint64_t usub = (uint64_t)((uint32_t)u * sub_stride16);
       static_assert(SLAB_K == 32, "two MMAs per slab");
-      umma_f16(d_tmem, ad0, bd0, idesc, k0 != 0);
-      if (k_pad - k0 > 16) umma_f16(d_tmem, ad0 + (uint64_t)(2u * TILE_M), bd0 + (uint64_t)(2u * n), idesc, 1u);
+      umma_f16(d_tmem, make_smem_desc(a0, TILE_M * 16, 128) + usub, bd0, idesc, k0 != 0);
+      if (k_pad - k0 > 16) umma_f16(d_tmem, make_smem_desc(a1, TILE_M * 16, 128) + usub, bd0 + (uint64_t)(2u * n), idesc, 1u);
       if (release) umma_commit(&S.empty[st]);     // slab consumed when these MMAs retire
     };
 
     for (uint32_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
       for (int l = 0; l < P.nlayers; ++l) {
-        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act;
+        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act, split = P.L[l].src_split;
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
         const int nslabs = (k_pad + SLAB_K - 1) / SLAB_K;
         const bool sequential = NSUB > 1 && nslabs <= 4;
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
               uint32_t st = stage, ph = phase;
               for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
                 if (u == 0) mbar_wait(&S.full[st], ph, 202);
-                issue_slab(u, st, a_base0, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
+                issue_slab(u, st, a_base0, split, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
                 if (++st == NSTAGES) { st = 0; ph ^= 1; }
               }
               umma_commit(&S.acc_full[u][buf]);
@@ -650,7 +654,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
               mbar_wait(&S.full[stage], phase, 202);
 #pragma unroll
               for (int u = 0; u < NSUB; ++u)
-                issue_slab(u, stage, a_base0, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
+                issue_slab(u, stage, a_base0, split, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
               if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
 #pragma unroll
@@ -865,11 +869,12 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           if (Ly.kind == EPI_TANH) {
             // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
             // bias 30 (tanh(30) == 1.0f): no per-element special cases
+            uint8_t* dstc = (Ly.split_dst && c == 0) ? T.bufZ : dst;
             for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
-              store16(dst, row, off + g, v);
+              store16(dstc, row, off + g, v);
             });
           } else if (Ly.kind == EPI_GSAMPLE) {
             // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8]
@@ -1267,6 +1272,19 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P, bool fast)
     L.inplace = (L.kind != EPI_BERN && L.kind != EPI_GLOGP && L.src == L.dst) ? 1 : 0;
   }
   for (int l = 0; l < nl; ++l) pr.L[l].signal_act = (l + 1 < nl) ? pr.L[l + 1].wait_act : 0;
+  // The second decoder layer (h1 -> h1 units, two chunks, in place) would have to wait for ALL its MMAs before the
+  // first epilogue may overwrite the input.  The z1 buffer is dead once the first decoder layer's MMAs have retired,
+  // so chunk 0 goes there instead and its epilogue overlaps the MMAs of chunk 1; the logit layer then reads its
+  // first chunk_n[0] K-columns from the z1 buffer.
+  {
+    Layer& D1 = pr.L[nl - 2];
+    Layer& BL = pr.L[nl - 1];
+    if (D1.kind == EPI_TANH && D1.inplace && D1.nchunks == 2 && D1.chunk_n[0] <= KZ_MAX && pr.L[nl - 3].src == 0 &&
+        BL.kind == EPI_BERN && D1.chunk_n[0] % 16 == 0) {
+      D1.split_dst = 1; D1.inplace = 0;
+      BL.src_split = D1.chunk_n[0];
+    }
+  }
   // packed offsets
   int64_t off = 0;
   for (int l = 0; l < nl; ++l) {
