@@ -434,7 +434,7 @@ struct __align__(16) SmemLayout {
 };
 
 // one persistent CTA per SM: the dynamic shared memory of one CTA is at most 227 KB
-static_assert(CTAS_PER_SM * (sizeof(SmemLayout) + 128 + 1024) <= 228 * 1024, "fused eval kernel: shared memory exceeds the SM");
+static_assert(CTAS_PER_SM * (sizeof(SmemLayout) + 1024) <= 228 * 1024, "fused eval kernel: shared memory exceeds the SM");
 
 #define LOG2PI_HALF_F 0.91893853320467274178f
 
@@ -1376,7 +1376,7 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
     CUDA_TRY(cudaMemsetAsync(a.trace, 0, sizeof(long long) * 4 * 3 * TRACE_SLOTS * 2, st));
   }
 
-  const size_t smem = sizeof(tc::SmemLayout) + 128;
+  const size_t smem = sizeof(tc::SmemLayout);     // (the dynamic window is 128-byte aligned: no static shared memory in this kernel)
   auto kern = a.trace ? (fast ? tc::iwae_eval_tc_kernel<true, true> : tc::iwae_eval_tc_kernel<false, true>)
                       : (fast ? tc::iwae_eval_tc_kernel<true, false> : tc::iwae_eval_tc_kernel<false, false>);
   if (!tp.attr_set) {
