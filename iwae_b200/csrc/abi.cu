@@ -473,11 +473,19 @@ static int dense_bwd_w(const DenseP& L, const float* X, int64_t ldx, int64_t M, 
   g.C = grads + L.w; g.ldc = L.n_out;
   g.M = L.n_in; g.N = L.n_out; g.K = (int)M;
   g.small_tile = 1;
-  const int tiles = ((L.n_in + 31) / 32) * ((L.n_out + 31) / 32);
-  int split = std::min<int>(GRAD_SPLITS, (296 + tiles - 1) / tiles);
+  // db = colsum(dY) rides along as a virtual row of ones in X^T: the bias follows its kernel in the flat
+  // parameter layout (add_dense), so row n_in of the [n_in + 1, n_out] product lands on the bias gradient
+  const bool fused_bias = (L.b == L.w + (int64_t)L.n_in * L.n_out);
+  g.ones_row = fused_bias ? 1 : 0;
+  const int tiles = ((L.n_in + g.ones_row + 31) / 32) * ((L.n_out + 31) / 32);
+  // enough slices to fill the SMs AND to keep each CTA's serial K loop short (<= ~128 rows): the slices are summed
+  // by grad_reduce anyway, and a 200 x 784 gradient over 1,000 rows in two slices was a 42 us chain of 32 K-tiles
+  int split = std::max<int>((296 + tiles - 1) / tiles, (int)((M + 127) / 128));
+  split = std::min<int>(GRAD_SPLITS, split);
   split = (int)std::max<int64_t>(1, std::min<int64_t>(split, M / 64));     // at least 64 rows per slice
   g.split_k = split; g.split_stride = g_grad_stride;
   IWAE_TRY(gemm_f32(g, st));
+  if (fused_bias) return 0;
   return colsum_f32(dY, L.n_out, (int)M, L.n_out, grads + L.b, st, GRAD_SPLITS, g_grad_stride);
 }
 // dX = dY W^T, optionally accumulated into dX and/or multiplied by tanh'(H) = 1 - H^2

@@ -106,6 +106,8 @@ struct GemmArgs {
   int small_tile = 0;                                     // 32x32 tiles (more CTAs for skinny outputs)
   int split_k = 1;                                        // >1: gridDim.z partial products, C + z*split_stride (plain products only)
   int64_t split_stride = 0;
+  int ones_row = 0;                                       // A gets a virtual row m = M of ones: C row M = column sums of B
+                                                          // (dW = X^T dY then yields db = colsum(dY) in the same launch)
 };
 int gemm_f32(const GemmArgs& a, cudaStream_t st);
 int gemm_f32_ntiles_n(int N, int small_tile);

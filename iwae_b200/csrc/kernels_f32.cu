@@ -18,9 +18,13 @@ gemm_f32_kernel(GemmArgs a) {
   constexpr int TX = BN / TN;   // threads along n
   constexpr int EA = BM * BK / NT, EB = BN * BK / NT;   // elements of the A / B tile each thread stages
   static_assert(EA * NT == BM * BK && EB * NT == BN * BK, "tile must divide evenly among the threads");
-  // double-buffered tiles: global -> registers (next tile) overlaps the FFMAs on the current tile
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  // NSTG-stage cp.async ring (4-byte copies with zero fill, so any stride / alignment / ragged edge works): with
+  // rows = k*B = 1,000 these GEMMs are a chain of 7-50 K-tiles of a few hundred cycles of FFMAs each, and a
+  // register-staged double buffer (prefetch distance 1) left every tile exposed to the full global-load latency -
+  // ~11 us per launch, 43 launches per train step.  Three tiles in flight hide it.
+  constexpr int NSTG = 4;
+  __shared__ __align__(16) float As[NSTG][BK][BM + 4];
+  __shared__ __align__(16) float Bs[NSTG][BK][BN + 4];
 
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
@@ -39,15 +43,21 @@ gemm_f32_kernel(GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  float ra[EA], rb[EB];
-  auto load_tile = [&](int k0) {
+  auto cp4 = [](float* dst_smem, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int nbytes = valid ? 4 : 0;                       // src-size 0: the 4 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+  };
+  auto issue_tile = [&](int k0, int buf) {
 #pragma unroll
     for (int i = 0; i < EA; ++i) {
       const int e = tid + i * NT;
       int mm, kk;
       if (a_kcontig) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
       const int gm = m0 + mm, gk = k0 + kk;
-      ra[i] = (gm < a.M && gk < k_end) ? __ldg(a.A + (int64_t)gm * a.sa_m + (int64_t)gk * a.sa_k) : 0.f;
+      const bool ok = gm < a.M && gk < k_end;
+      if (a.ones_row && gm == a.M) As[buf][kk][mm] = (gk < k_end) ? 1.f : 0.f;      // virtual row of ones (bias gradient)
+      else cp4(&As[buf][kk][mm], ok ? a.A + (int64_t)gm * a.sa_m + (int64_t)gk * a.sa_k : a.A, ok);
     }
 #pragma unroll
     for (int i = 0; i < EB; ++i) {
@@ -55,34 +65,25 @@ gemm_f32_kernel(GemmArgs a) {
       int nn, kk;
       if (b_ncontig) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
       const int gn = n0 + nn, gk = k0 + kk;
-      rb[i] = (gn < a.N && gk < k_end) ? __ldg(a.B + (int64_t)gk * a.sb_k + (int64_t)gn * a.sb_n) : 0.f;
-    }
-  };
-  auto store_tile = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < EA; ++i) {
-      const int e = tid + i * NT;
-      int mm, kk;
-      if (a_kcontig) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
-      As[buf][kk][mm] = ra[i];
-    }
-#pragma unroll
-    for (int i = 0; i < EB; ++i) {
-      const int e = tid + i * NT;
-      int nn, kk;
-      if (b_ncontig) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
-      Bs[buf][kk][nn] = rb[i];
+      const bool ok = gn < a.N && gk < k_end;
+      cp4(&Bs[buf][kk][nn], ok ? a.B + (int64_t)gk * a.sb_k + (int64_t)gn * a.sb_n : a.B, ok);
     }
   };
 
   if (k_begin < k_end) {
-    load_tile(k_begin);
-    store_tile(0);
-    __syncthreads();
-    int buf = 0;
-    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-      const bool more = k0 + BK < k_end;
-      if (more) load_tile(k0 + BK);
+    const int ntiles = (k_end - k_begin + BK - 1) / BK;
+    // prologue: tiles 0 .. NSTG-2 (one commit group per slot, empty groups keep the count uniform)
+#pragma unroll
+    for (int t = 0; t < NSTG - 1; ++t) {
+      if (t < ntiles) issue_tile(k_begin + t * BK, t);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 2) : "memory");      // tile t has landed (this thread's part)
+      __syncthreads();                                                          // ... everyone's part; tile t-1 is consumed
+      if (t + NSTG - 1 < ntiles) issue_tile(k_begin + (t + NSTG - 1) * BK, (t + NSTG - 1) % NSTG);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const int buf = t % NSTG;
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
         float av[TM], bv[TN];
@@ -95,13 +96,11 @@ gemm_f32_kernel(GemmArgs a) {
 #pragma unroll
           for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
-      if (more) store_tile(buf ^ 1);
-      __syncthreads();
-      buf ^= 1;
     }
   }
 
   // ---- epilogue
+  const int m_rows = a.M + (a.ones_row ? 1 : 0);
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int gm = m0 + ty * TM + i;
@@ -109,7 +108,7 @@ gemm_f32_kernel(GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int gn = n0 + tx * TN + j;
-      if (gm < a.M && gn < a.N) {
+      if (gm < m_rows && gn < a.N) {
         float v = acc[i][j];
         if (a.bias) v += __ldg(a.bias + gn);
         if (a.act == ACT_TANH) v = tanhf(v);
@@ -144,11 +143,19 @@ int gemm_f32(const GemmArgs& a, cudaStream_t st) {
   const int z = a.split_k > 1 ? a.split_k : 1;
   IWAE_REQUIRE(z == 1 || (!a.bias && a.act == ACT_NONE && !a.accumulate && !a.mul_h && !a.bern_x),
                "gemm_f32: split-K supports plain products only");
-  if (a.small_tile) {
-    dim3 grid((a.M + 31) / 32, (a.N + 31) / 32, z);
+  IWAE_REQUIRE(!a.ones_row || (!a.bias && a.act == ACT_NONE && !a.accumulate && !a.mul_h && !a.bern_x),
+               "gemm_f32: ones_row supports plain products only");
+  const int m_rows = a.M + (a.ones_row ? 1 : 0);
+  if (a.small_tile && m_rows >= 256 && a.K >= 512 && z == 1) {
+    // tall, narrow outputs (rows = k*B = 1,000 by <= 200 units): 4x2 register tiles halve the shared-memory loads
+    // per FFMA of the 2x2 kernel, which is LDS-bound on the long-K products (dX of the 784-logit layer: 48 -> ~20 us)
+    dim3 grid((m_rows + 63) / 64, (a.N + 31) / 32, z);
+    gemm_f32_kernel<64, 32, 4, 2><<<grid, 256, 0, st>>>(a);
+  } else if (a.small_tile) {
+    dim3 grid((m_rows + 31) / 32, (a.N + 31) / 32, z);
     gemm_f32_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(a);
   } else {
-    dim3 grid((a.M + 63) / 64, (a.N + 63) / 64, z);
+    dim3 grid((m_rows + 63) / 64, (a.N + 63) / 64, z);
     gemm_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);
   }
   LAUNCH_CHECK();
