@@ -157,7 +157,11 @@ int iwae_adam_step(float* params, const float* grads, float* m, float* v, int64_
 
 /* Replaces model.train_step (src/iwae1.py:153-162; tasks/task02.py:87-101; tasks/task04.py:175-184):
  * forward + backward + Adam on one device in one call.  For data-parallel training call iwae_grads,
- * all-reduce, then iwae_adam_step. */
+ * all-reduce, then iwae_adam_step.
+ * With Philox noise (eps1 == eps2 == NULL) the step is captured into a CUDA graph on the second consecutive call
+ * with one signature (params / m / v pointers, B, k, beta, objective, set of requested outputs) and replayed from
+ * then on - same kernels, bit-identical results; x, y and the outputs may live anywhere (they are staged through
+ * library-owned buffers on the device).  IWAE_NO_GRAPH=1 in the environment keeps every call eager. */
 int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v,
                     const float* x, const float* y, int32_t B, int32_t k, float beta,
                     int32_t objective, const float* eps1, const float* eps2, uint64_t seed,

@@ -113,6 +113,7 @@ extern "C" int iwae_create(const iwae_config* cfg, iwae_ctx** out) {
   return 0;
 }
 
+static void train_graph_release(iwae_ctx* ctx);
 extern "C" int iwae_destroy(iwae_ctx* ctx) {
   if (!ctx) return 0;
   cudaDeviceSynchronize();
@@ -121,6 +122,7 @@ extern "C" int iwae_destroy(iwae_ctx* ctx) {
   if (ctx->per_buf) cudaFree(ctx->per_buf);
   if (ctx->stage_x) cudaFree(ctx->stage_x);
   if (ctx->stage_aux) cudaFree(ctx->stage_aux);
+  train_graph_release(ctx);
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   delete ctx;
@@ -628,16 +630,166 @@ extern "C" int iwae_adam_step(float* params, const float* grads, float* m, float
   return adam_f32(params, grads, m, v, n, lr, beta1, beta2, eps, t, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// train step: eager, or replayed from a CUDA graph
+// ---------------------------------------------------------------------------------------------
+// The k=50 step is ~59 dependent small kernels; launched in stream order they leave ~2 us between kernels that a
+// graph does not (scripts/train_graph_probe.py: 0.62 -> 0.51 ms per step).  The graph is captured inside the
+// library on the SECOND consecutive call with the same signature (the first, eager one has grown the arena, so the
+// capture allocates nothing), on a library-owned stream (the caller's may be the legacy default stream, which cannot
+// be captured), against library-owned copies of x / y and of the requested outputs: the caller's pointers change
+// from call to call.  Per-step scalars (Philox seed, Adam's lr_t) live in a device struct the kernels read.
+// Injected eps (the parity path) and IWAE_NO_GRAPH=1 stay eager.
+static long long out_field_len(int f, const iwae_config& c, int B, int k) {
+  const long long R = (long long)B * k;
+  switch (f) {
+    case 0: case 1: case 2: case 3: case 4: case 5: case 6: return R;             // lpxz .. al
+    case 7: case 8: case 9: case 10: case 11: return B;                           // iwae, vae, eq14, kl, dreg
+    case 12: return (long long)B * c.d1;                                          // snis_z1
+    case 13: return (long long)B * std::max(c.d2, 1);                             // snis_z2
+    case 14: return R * c.d1;                                                     // z1
+    case 15: return R * std::max(c.d2, 1);                                        // z2
+    case 16: return R * c.n_x;                                                    // logits
+    case 17: case 18: return (long long)B * c.d1;                                 // q_mu, q_std
+    default: return 8;                                                            // scalars
+  }
+}
+constexpr int N_OUT_FIELDS = (int)(sizeof(iwae_outputs) / sizeof(float*));
+static_assert(N_OUT_FIELDS == 20, "iwae_outputs changed: update out_field_len");
+
+static void train_graph_release(iwae_ctx* ctx) {
+  TrainGraph& g = ctx->tg;
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (g.x_buf) cudaFree(g.x_buf);
+  if (g.y_buf) cudaFree(g.y_buf);
+  if (g.out_mem) cudaFree(g.out_mem);
+  g = TrainGraph();
+  if (ctx->dyn_dev) { cudaFree(ctx->dyn_dev); ctx->dyn_dev = nullptr; }
+  if (ctx->ev_gin) { cudaEventDestroy(ctx->ev_gin); ctx->ev_gin = nullptr; }
+  if (ctx->ev_gout) { cudaEventDestroy(ctx->ev_gout); ctx->ev_gout = nullptr; }
+  if (ctx->gstream) { cudaStreamDestroy(ctx->gstream); ctx->gstream = nullptr; }
+}
+
+static int train_step_eager(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x, const float* y,
+                            int B, int k, float beta, int objective, const float* eps1, const float* eps2, uint64_t seed,
+                            int64_t img_offset, float lr, float beta1, float beta2, float adam_eps, int64_t t,
+                            const iwae_outputs* outs, cudaStream_t st) {
+  ctx->arena.reset();
+  AdamArgs ad = {params, adam_m, adam_v, lr, beta1, beta2, adam_eps, t};
+  return grads_internal(ctx, params, x, y, B, k, beta, objective, B, eps1, eps2, seed, img_offset, nullptr, outs, st, &ad);
+}
+
+// capture the step for the signature in g.cand; returns 0 and g.valid on success
+static int train_graph_capture(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, bool has_y, int B, int k,
+                               float beta, int objective, const iwae_outputs* outs) {
+  TrainGraph& g = ctx->tg;
+  const iwae_config& c = ctx->model.cfg;
+  if (!ctx->gstream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking));
+  if (!ctx->ev_gin) { CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_gin, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_gout, cudaEventDisableTiming)); }
+  if (!ctx->dyn_dev) CUDA_TRY(cudaMalloc((void**)&ctx->dyn_dev, sizeof(StepDyn)));
+  IWAE_TRY(grow_dev(&g.x_buf, &g.x_cap, (size_t)B * c.n_x * sizeof(float)));
+  IWAE_TRY(grow_dev(&g.y_buf, &g.y_cap, (size_t)B * sizeof(float) + 16));
+  // shadow outputs: one block, each requested field 256-byte aligned
+  size_t need = 0;
+  float* const* user = reinterpret_cast<float* const*>(outs);
+  for (int f = 0; f < N_OUT_FIELDS; ++f)
+    if (outs && user[f]) need += ((size_t)out_field_len(f, c, B, k) * sizeof(float) + 255) & ~(size_t)255;
+  IWAE_TRY(grow_dev(&g.out_mem, &g.out_cap, std::max(need, (size_t)256)));
+  g.shadow = iwae_outputs{};
+  float** sh = reinterpret_cast<float**>(&g.shadow);
+  size_t off = 0;
+  for (int f = 0; f < N_OUT_FIELDS; ++f)
+    if (outs && user[f]) {
+      sh[f] = reinterpret_cast<float*>(reinterpret_cast<char*>(g.out_mem) + off);
+      off += ((size_t)out_field_len(f, c, B, k) * sizeof(float) + 255) & ~(size_t)255;
+    }
+  if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  g.valid = false;
+
+  cudaGraph_t graph = nullptr;
+  const long long launches0 = g_iwae_launches;
+  CUDA_TRY(cudaStreamBeginCapture(ctx->gstream, cudaStreamCaptureModeThreadLocal));
+  g_step_dyn = ctx->dyn_dev;
+  const int rc = train_step_eager(ctx, params, adam_m, adam_v, g.x_buf, has_y ? g.y_buf : nullptr, B, k, beta, objective,
+                                  nullptr, nullptr, 0, 0, 0.f, 0.f, 0.f, 0.f, 1, &g.shadow, ctx->gstream);
+  g_step_dyn = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->gstream, &graph);
+  g.launches = g_iwae_launches - launches0;
+  g_iwae_launches = launches0;
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g.disabled = true;
+    return rc != 0 ? rc : 0;       // the caller falls back to the eager path
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.disabled = true; return 0; }
+  memcpy(g.key, g.cand, sizeof(g.key));
+  g.valid = true;
+  return 0;
+}
+
 extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x,
                                const float* y, int32_t B, int32_t k, float beta, int32_t objective, const float* eps1,
                                const float* eps2, uint64_t seed, int64_t img_offset, float lr, float beta1, float beta2,
                                float adam_eps, int64_t t, const iwae_outputs* outs, void* stream) {
   IWAE_REQUIRE(ctx && params && adam_m && adam_v, "iwae_train_step: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  ctx->arena.reset();
   IWAE_REQUIRE(t >= 1, "iwae_train_step: t is the step count after increment (>= 1)");
-  AdamArgs ad = {params, adam_m, adam_v, lr, beta1, beta2, adam_eps, t};
-  return grads_internal(ctx, params, x, y, B, k, beta, objective, B, eps1, eps2, seed, img_offset, nullptr, outs, st, &ad);
+  TrainGraph& g = ctx->tg;
+  static const bool no_graph = getenv("IWAE_NO_GRAPH") != nullptr;
+  const bool graphable = !no_graph && !g.disabled && !eps1 && !eps2 && x && B > 0 && k > 0;
+  if (!graphable)
+    return train_step_eager(ctx, params, adam_m, adam_v, x, y, B, k, beta, objective, eps1, eps2, seed, img_offset, lr,
+                            beta1, beta2, adam_eps, t, outs, st);
+
+  // signature: everything the captured kernels hold by value or by address
+  unsigned long long key[12] = {};
+  key[0] = (unsigned long long)(uintptr_t)params; key[1] = (unsigned long long)(uintptr_t)adam_m;
+  key[2] = (unsigned long long)(uintptr_t)adam_v; key[3] = (unsigned long long)(unsigned)B;
+  key[4] = (unsigned long long)(unsigned)k; key[5] = (unsigned long long)(unsigned)objective;
+  { unsigned int bb; memcpy(&bb, &beta, 4); key[6] = bb; }
+  key[7] = y ? 1 : 0;
+  float* const* user = reinterpret_cast<float* const*>(outs);
+  unsigned long long mask = 0;
+  for (int f = 0; f < N_OUT_FIELDS; ++f) if (outs && user[f]) mask |= 1ull << f;
+  key[8] = mask;
+
+  if (!(g.valid && memcmp(key, g.key, sizeof(key)) == 0)) {
+    if (g.have_cand && memcmp(key, g.cand, sizeof(key)) == 0) {
+      // second consecutive call with this signature: capture (the eager call before it sized the arena)
+      IWAE_TRY(train_graph_capture(ctx, params, adam_m, adam_v, y != nullptr, B, k, beta, objective, outs));
+    } else {
+      memcpy(g.cand, key, sizeof(key)); g.have_cand = true;
+    }
+    if (!(g.valid && memcmp(key, g.key, sizeof(key)) == 0))
+      return train_step_eager(ctx, params, adam_m, adam_v, x, y, B, k, beta, objective, eps1, eps2, seed, img_offset, lr,
+                              beta1, beta2, adam_eps, t, outs, st);
+  }
+
+  // replay: order the library stream after the caller's, refresh inputs and scalars, launch, hand the outputs back
+  const iwae_config& c = ctx->model.cfg;
+  cudaStream_t gs = ctx->gstream;
+  CUDA_TRY(cudaEventRecord(ctx->ev_gin, st));
+  CUDA_TRY(cudaStreamWaitEvent(gs, ctx->ev_gin, 0));
+  CUDA_TRY(cudaMemcpyAsync(g.x_buf, x, (size_t)B * c.n_x * sizeof(float), cudaMemcpyDeviceToDevice, gs));
+  if (y) CUDA_TRY(cudaMemcpyAsync(g.y_buf, y, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, gs));
+  StepDyn d;
+  d.seed = seed; d.img_offset = img_offset;
+  d.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t)));
+  d.b1 = beta1; d.b2 = beta2; d.eps = adam_eps;
+  IWAE_TRY(set_step_dyn(ctx->dyn_dev, d, gs));
+  CUDA_TRY(cudaGraphLaunch(g.exec, gs));
+  g_iwae_launches += g.launches;
+  CopyTable tb; tb.count = 0;
+  float* const* sh = reinterpret_cast<float* const*>(&g.shadow);
+  for (int f = 0; f < N_OUT_FIELDS; ++f)
+    if (outs && user[f]) { tb.src[tb.count] = sh[f]; tb.dst[tb.count] = user[f]; tb.n[tb.count] = out_field_len(f, c, B, k); ++tb.count; }
+  IWAE_TRY(copy_table(tb, gs));
+  CUDA_TRY(cudaEventRecord(ctx->ev_gout, gs));
+  CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_gout, 0));
+  return 0;
 }
 
 extern "C" int iwae_philox_normal(uint64_t seed, int32_t stream_id, int64_t img_offset, int32_t B, int32_t k, int32_t d,

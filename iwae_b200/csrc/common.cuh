@@ -76,6 +76,30 @@ struct Arena {
 
 struct TcPack;   // packed fp16 weights + program for the fused tcgen05 evaluation (eval_tc.cu)
 
+// Per-step scalars of a train step, device-resident so that a captured CUDA graph of the step can be replayed with
+// new values (kernels read them through g_step_dyn when it is non-null, else from their by-value arguments).
+struct StepDyn {
+  unsigned long long seed;
+  long long img_offset;
+  float lr_t, b1, b2, eps;
+};
+extern const StepDyn* g_step_dyn;
+
+// One cached CUDA graph of iwae_train_step (see abi.cu): signature it was captured for, library-owned input and
+// output buffers (the caller's pointers change from call to call), and the captured launch count.
+struct TrainGraph {
+  bool valid = false;
+  unsigned long long key[12] = {};          // signature of the captured step
+  unsigned long long cand[12] = {};         // signature seen on the previous (eager) call
+  bool have_cand = false;
+  bool disabled = false;                    // capture failed once: stay eager
+  cudaGraphExec_t exec = nullptr;
+  float* x_buf = nullptr; float* y_buf = nullptr; size_t x_cap = 0, y_cap = 0;
+  float* out_mem = nullptr; size_t out_cap = 0;
+  iwae_outputs shadow{};                    // the graph writes here; a gather kernel copies to the caller's pointers
+  long long launches = 0;
+};
+
 struct iwae_ctx {
   ModelP model;
   Arena arena;
@@ -87,6 +111,11 @@ struct iwae_ctx {
   float* stage_x = nullptr; size_t stage_x_cap = 0;   // x (and y) copied from the host
   float* stage_aux = nullptr; size_t stage_aux_cap = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr; bool ev_valid = false;   // around the fused eval kernel
+  // train-step graph replay
+  TrainGraph tg;
+  StepDyn* dyn_dev = nullptr;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
 };
 
 // ---- fp32 kernels (kernels_f32.cu) ----
@@ -183,6 +212,10 @@ int adam_from_partials(float* p, const float* ws, int splits, float* m, float* v
 int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
              float eps, int64_t t, cudaStream_t st);
 int bernoulli_sample_f32(const float* p, int64_t n, uint64_t seed, uint64_t epoch, float* out, cudaStream_t st);
+// graph replay helpers: write the per-step scalars / copy up to 24 (src, dst, n) float ranges in one launch
+struct CopyTable { const float* src[24]; float* dst[24]; long long n[24]; int count; };
+int set_step_dyn(StepDyn* dev, const StepDyn& v, cudaStream_t st);
+int copy_table(const CopyTable& t, cudaStream_t st);
 int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64_t* out_idx,
                int32_t* out_consumed, cudaStream_t st);
 int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st);

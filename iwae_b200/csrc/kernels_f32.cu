@@ -225,7 +225,8 @@ int onehot_f32(const float* y, int B, int nc, float* out, cudaStream_t st) {
 __global__ void sample_latent_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int bcast,
                                      const float* __restrict__ eps_in, float* __restrict__ eps_out,
                                      float* __restrict__ z, int B, int k, int d, uint64_t seed, int stream_id,
-                                     int64_t img_offset) {
+                                     int64_t img_offset, const StepDyn* __restrict__ dyn) {
+  if (dyn) { seed = dyn->seed; img_offset = dyn->img_offset; }      // graph replay: per-step values live on the device
   const int nq = (d + 3) / 4;
   const int64_t total = (int64_t)k * B * nq;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -259,7 +260,8 @@ int sample_latent(const float* mu, const float* sd, int bcast, const float* eps_
   const int64_t total = (int64_t)k * B * ((d + 3) / 4);
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  sample_latent_kernel<<<blocks, 256, 0, st>>>(mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset);
+  sample_latent_kernel<<<blocks, 256, 0, st>>>(mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset,
+                                               eps_in ? nullptr : g_step_dyn);
   LAUNCH_CHECK();
   return 0;
 }
@@ -720,7 +722,8 @@ int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
 // ---- split-K gradient partials: fixed-order reduction, optionally fused with the Keras-Adam update ----
 __global__ void grad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t n, float* __restrict__ g,
                                    float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float lr_t,
-                                   float b1, float b2, float eps) {
+                                   float b1, float b2, float eps, const StepDyn* __restrict__ dyn) {
+  if (dyn) { lr_t = dyn->lr_t; b1 = dyn->b1; b2 = dyn->b2; eps = dyn->eps; }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
     float gg = 0.f;
@@ -737,7 +740,7 @@ __global__ void grad_reduce_kernel(const float* __restrict__ ws, int splits, int
 int grad_reduce(const float* ws, int splits, int64_t n, float* grads, cudaStream_t st) {
   if (n == 0) return 0;
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, grads, nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f);
+  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, grads, nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, nullptr);
   LAUNCH_CHECK();
   return 0;
 }
@@ -746,7 +749,7 @@ int adam_from_partials(float* p, const float* ws, int splits, float* m, float* v
   if (n == 0) return 0;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, nullptr, p, m, v, (float)lr_t, b1, b2, eps);
+  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, nullptr, p, m, v, (float)lr_t, b1, b2, eps, g_step_dyn);
   LAUNCH_CHECK();
   return 0;
 }
@@ -861,5 +864,32 @@ int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64
                                reinterpret_cast<int32_t*>(scratch + 2 * (size_t)L));
   LAUNCH_CHECK();
   CUDA_TRY(cudaFreeAsync(scratch, st));
+  return 0;
+}
+
+
+// ---- train-step graph replay helpers ----
+const StepDyn* g_step_dyn = nullptr;
+
+__global__ void set_step_dyn_kernel(StepDyn* d, StepDyn v) { *d = v; }
+int set_step_dyn(StepDyn* dev, const StepDyn& v, cudaStream_t st) {
+  set_step_dyn_kernel<<<1, 1, 0, st>>>(dev, v);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void copy_table_kernel(CopyTable t) {
+  const float* __restrict__ src = t.src[blockIdx.y];
+  float* __restrict__ dst = t.dst[blockIdx.y];
+  const long long n = t.n[blockIdx.y];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int copy_table(const CopyTable& t, cudaStream_t st) {
+  if (t.count == 0) return 0;
+  long long nmax = 0;
+  for (int i = 0; i < t.count; ++i) nmax = std::max(nmax, t.n[i]);
+  const int bx = (int)std::min<long long>((nmax + 255) / 256, 296);
+  copy_table_kernel<<<dim3(bx, t.count), 256, 0, st>>>(t);
+  LAUNCH_CHECK();
   return 0;
 }
