@@ -48,25 +48,43 @@ gemm_f32_kernel(GemmArgs a) {
     const int nbytes = valid ? 4 : 0;                       // src-size 0: the 4 bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
   };
-  auto issue_tile = [&](int k0, int buf) {
+  // per-thread element slots of the A / B tiles: base pointer at k = k_begin, validity of the row / column and the
+  // k offset inside a tile are fixed for the whole K loop, so a tile issue is one add + compare + cp.async per element
+  const float* pa[EA]; float* sa[EA]; int ka[EA]; bool oka[EA]; bool onea[EA];
+  const float* pb[EB]; float* sb[EB]; int kb[EB]; bool okb[EB];
+#pragma unroll
+  for (int i = 0; i < EA; ++i) {
+    const int e = tid + i * NT;
+    int mm, kk;
+    if (a_kcontig) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
+    const int gm = m0 + mm;
+    oka[i] = gm < a.M; onea[i] = a.ones_row && gm == a.M; ka[i] = kk;
+    pa[i] = a.A + (oka[i] ? (int64_t)gm * a.sa_m + (int64_t)(k_begin + kk) * a.sa_k : 0);
+    sa[i] = &As[0][kk][mm];
+  }
+#pragma unroll
+  for (int i = 0; i < EB; ++i) {
+    const int e = tid + i * NT;
+    int nn, kk;
+    if (b_ncontig) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
+    const int gn = n0 + nn;
+    okb[i] = gn < a.N; kb[i] = kk;
+    pb[i] = a.B + (okb[i] ? (int64_t)(k_begin + kk) * a.sb_k + (int64_t)gn * a.sb_n : 0);
+    sb[i] = &Bs[0][kk][nn];
+  }
+  constexpr int A_STAGE = BK * (BM + 4), B_STAGE = BK * (BN + 4);      // floats per ring stage
+  auto issue_tile = [&](int t, int buf) {                               // tile t covers k_begin + t*BK ...
+    const int krem = k_end - (k_begin + t * BK);                       // valid k offsets of this tile: kk < krem
 #pragma unroll
     for (int i = 0; i < EA; ++i) {
-      const int e = tid + i * NT;
-      int mm, kk;
-      if (a_kcontig) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
-      const int gm = m0 + mm, gk = k0 + kk;
-      const bool ok = gm < a.M && gk < k_end;
-      if (a.ones_row && gm == a.M) As[buf][kk][mm] = (gk < k_end) ? 1.f : 0.f;      // virtual row of ones (bias gradient)
-      else cp4(&As[buf][kk][mm], ok ? a.A + (int64_t)gm * a.sa_m + (int64_t)gk * a.sa_k : a.A, ok);
+      const bool ok = oka[i] && ka[i] < krem;
+      if (onea[i]) sa[i][buf * A_STAGE] = (ka[i] < krem) ? 1.f : 0.f;  // virtual row of ones (bias gradient)
+      else cp4(sa[i] + buf * A_STAGE, ok ? pa[i] + (int64_t)t * BK * a.sa_k : a.A, ok);
     }
 #pragma unroll
     for (int i = 0; i < EB; ++i) {
-      const int e = tid + i * NT;
-      int nn, kk;
-      if (b_ncontig) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
-      const int gn = n0 + nn, gk = k0 + kk;
-      const bool ok = gn < a.N && gk < k_end;
-      cp4(&Bs[buf][kk][nn], ok ? a.B + (int64_t)gk * a.sb_k + (int64_t)gn * a.sb_n : a.B, ok);
+      const bool ok = okb[i] && kb[i] < krem;
+      cp4(sb[i] + buf * B_STAGE, ok ? pb[i] + (int64_t)t * BK * a.sb_k : a.B, ok);
     }
   };
 
@@ -75,13 +93,13 @@ gemm_f32_kernel(GemmArgs a) {
     // prologue: tiles 0 .. NSTG-2 (one commit group per slot, empty groups keep the count uniform)
 #pragma unroll
     for (int t = 0; t < NSTG - 1; ++t) {
-      if (t < ntiles) issue_tile(k_begin + t * BK, t);
+      if (t < ntiles) issue_tile(t, t);
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int t = 0; t < ntiles; ++t) {
       asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 2) : "memory");      // tile t has landed (this thread's part)
       __syncthreads();                                                          // ... everyone's part; tile t-1 is consumed
-      if (t + NSTG - 1 < ntiles) issue_tile(k_begin + (t + NSTG - 1) * BK, (t + NSTG - 1) % NSTG);
+      if (t + NSTG - 1 < ntiles) issue_tile(t + NSTG - 1, (t + NSTG - 1) % NSTG);
       asm volatile("cp.async.commit_group;" ::: "memory");
       const int buf = t % NSTG;
 #pragma unroll
