@@ -345,7 +345,7 @@ def bench_train(ib, torch, X, bias, steps=300, warmup=30):
     ms = e0.elapsed_time(e1)
     return {"metric": "k=50 train steps/s", "value": steps / (ms * 1e-3), "unit": "steps/s", "batch": 20, "k": 50,
             "stochastic_layers": 2, "objective": "iwae_elbo", "launches_per_step": (_abi.lib.iwae_launch_count() - l0) / steps,
-            "note": "latency-bound: ~1.7 GFLOP per step; fp32 FFMA kernels", "last_iwae_elbo": float(res["iwae_elbo"])}
+            "note": "latency-bound: ~1.7 GFLOP per step; fp32 FFMA kernels, the step replayed from a CUDA graph inside iwae_train_step", "last_iwae_elbo": float(res["iwae_elbo"])}
 
 
 def main():

@@ -484,16 +484,35 @@ int logw_reduce(const LogwArgs& a0, cudaStream_t st) {
 
 // Batch-mean scalars of the result dict (iwae1.py:119-134): one CTA, fixed order -> deterministic.
 __global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
-  __shared__ float red[8];
-  auto mean_of = [&](const float* v, int64_t n) -> float {
-    if (!v || n == 0) return 0.f;
-    float s = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
-    return block_reduce(s, red, false) / (float)n;
-  };
-  const float m_vae = mean_of(a.vae, a.B), m_iwae = mean_of(a.iwae, a.B), m_eq14 = mean_of(a.eq14, a.B);
-  const float m_kl = mean_of(a.kl, a.B), m_dreg = mean_of(a.dreg, a.B);
-  const float m_lpxz = mean_of(a.lpxz, a.R), m_lpz = mean_of(a.lpz, a.R), m_lq1 = mean_of(a.lq1, a.R);
+  // eight means in ONE pass: all loads are issued before the first reduction (eight serial block reductions, each
+  // waiting for its own global loads, were a 12 us kernel on the train step's critical path)
+  __shared__ float red[8][8];
+  const float* src[8] = {a.vae, a.iwae, a.eq14, a.kl, a.dreg, a.lpxz, a.lpz, a.lq1};
+  const int64_t len[8] = {a.B, a.B, a.B, a.B, a.B, a.R, a.R, a.R};
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] = 0.f;
+    if (src[j]) for (int64_t i = threadIdx.x; i < len[j]; i += blockDim.x) s[j] += src[j][i];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[j][threadIdx.x >> 5] = s[j];
+  __syncthreads();
+  float mean[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[j][w];
+    mean[j] = (src[j] && len[j] > 0) ? t / (float)len[j] : 0.f;
+  }
+  const float m_vae = mean[0], m_iwae = mean[1], m_eq14 = mean[2], m_kl = mean[3], m_dreg = mean[4];
+  const float m_lpxz = mean[5], m_lpz = mean[6], m_lq1 = mean[7];
   if (threadIdx.x == 0) {
     a.out[0] = m_vae;
     a.out[1] = m_lpxz - a.beta * m_kl;      // vae_elbo_kl (iwae1.py:121)
@@ -588,6 +607,9 @@ __global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
   float mu = 0.f, sd = 1.f;
   if (active) {
     mu = a.mu[idx]; sd = a.std[idx];
+    // (unrolled: the ~7 global loads of different samples are independent; one CTA per image leaves most SMs idle,
+    //  so this kernel's time is its serial load-latency chain)
+#pragma unroll 5
     for (int s = ks; s < a.k; s += KS) {
       const int64_t r = (int64_t)s * a.B + b;
       const float g = a.g[r];
