@@ -187,8 +187,23 @@ struct FwdOpts {
   bool want_dreg = false;
 };
 
+// Training forward of the encoder's first layer: 20 rows x 784 inputs -> 200 units is 7 CTAs walking 49 K-tiles each
+// (22-32 us).  With `scratch` the product is split over K into partial sums that one small kernel reduces with the
+// bias and activation.  Only the train step passes a scratch buffer: the evaluation paths must round identically for
+// any number of rows (per-example results are bit-identical across shards).
+constexpr int FWD_SPLITS = 7;
 static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ldx, int64_t M, int act, float* Y,
-                     cudaStream_t st) {
+                     cudaStream_t st, float* scratch = nullptr) {
+  if (scratch && M <= 64 && L.n_in >= 400) {
+    GemmArgs g;
+    g.A = X; g.sa_m = ldx; g.sa_k = 1;
+    g.B = P + L.w; g.sb_k = L.n_out; g.sb_n = 1;
+    g.C = scratch; g.ldc = L.n_out;
+    g.M = (int)M; g.N = L.n_out; g.K = L.n_in;
+    g.small_tile = 1; g.split_k = FWD_SPLITS; g.split_stride = (int64_t)M * L.n_out;
+    IWAE_TRY(gemm_f32(g, st));
+    return splitk_bias_act(scratch, FWD_SPLITS, (int)M, L.n_out, P + L.b, act, Y, st);
+  }
   GemmArgs g;
   g.A = X; g.sa_m = ldx; g.sa_k = 1;
   g.B = P + L.w; g.sb_k = L.n_out; g.sb_n = 1;
@@ -200,8 +215,8 @@ static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ld
 }
 
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
-                     float* mu, float* sd, cudaStream_t st) {
-  IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st));
+                     float* mu, float* sd, cudaStream_t st, float* l1_scratch) {
+  IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st, l1_scratch));
   IWAE_TRY(dense_fwd(P, blk.l2, h1, blk.l1.n_out, M, ACT_TANH, h2, st));
   IWAE_TRY(dense_fwd(P, blk.lmu, h2, blk.l2.n_out, M, ACT_NONE, mu, st));
   IWAE_TRY(dense_fwd(P, blk.lstd, h2, blk.l2.n_out, M, ACT_EXP_EPS, sd, st));   // exp(a) + 1e-6 (iwae1.py:34,42)
@@ -238,7 +253,9 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   } else { f.xin = x; f.ld_xin = nx; }
   IWAE_TRY(ar.get(&f.h1, (size_t)B * h1)); IWAE_TRY(ar.get(&f.h2, (size_t)B * h1));
   IWAE_TRY(pick(ar, o->q_mu, (size_t)B * d1, &f.mu1)); IWAE_TRY(pick(ar, o->q_std, (size_t)B * d1, &f.std1));
-  IWAE_TRY(block_fwd_f32(P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, f.mu1, f.std1, st));
+  float* l1_scratch = nullptr;       // split-K partial sums of the encoder's first layer (train step only, see dense_fwd)
+  if (opt.keep_for_bwd && B <= 64) IWAE_TRY(ar.get(&l1_scratch, (size_t)FWD_SPLITS * B * h1));
+  IWAE_TRY(block_fwd_f32(P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, f.mu1, f.std1, st, l1_scratch));
 
   // ---- z1 = mu + std*eps, k samples                                        iwae1.py:59
   IWAE_TRY(pick(ar, o->z1, (size_t)R * d1, &f.z1));

@@ -225,7 +225,9 @@ int tc_pack_weights(iwae_ctx* ctx, const float* params, bool fast, cudaStream_t 
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k,
                 uint64_t seed, int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st);
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
-                  float* mu, float* sd, cudaStream_t st);
+                  float* mu, float* sd, cudaStream_t st, float* l1_scratch = nullptr);
+// out[m, n] = act(sum_s partial[s][m, n] + bias[n])   (split-K forward, see dense_fwd in abi.cu)
+int splitk_bias_act(const float* partial, int splits, int M, int N, const float* bias, int act, float* out, cudaStream_t st);
 void tc_release(iwae_ctx* ctx);
 int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream_t st);
 int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st);

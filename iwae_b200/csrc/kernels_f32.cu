@@ -908,6 +908,26 @@ int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64
 }
 
 
+// ---- split-K forward epilogue ----
+__global__ void splitk_bias_act_kernel(const float* __restrict__ partial, int splits, int M, int N,
+                                       const float* __restrict__ bias, int act, float* __restrict__ out) {
+  const int total = M * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += partial[(size_t)s * total + i];
+    v += bias[i % N];
+    if (act == ACT_TANH) v = tanhf(v);
+    else if (act == ACT_EXP_EPS) v = expf(v) + 1e-6f;
+    out[i] = v;
+  }
+}
+int splitk_bias_act(const float* partial, int splits, int M, int N, const float* bias, int act, float* out, cudaStream_t st) {
+  if (M * N == 0) return 0;
+  splitk_bias_act_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(partial, splits, M, N, bias, act, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- train-step graph replay helpers ----
 const StepDyn* g_step_dyn = nullptr;
 
