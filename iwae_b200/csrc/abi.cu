@@ -508,8 +508,20 @@ static int dense_bwd_w(const DenseP& L, const float* X, int64_t ldx, int64_t M, 
   return colsum_f32(dY, L.n_out, (int)M, L.n_out, grads + L.b, st, GRAD_SPLITS, g_grad_stride);
 }
 // dX = dY W^T, optionally accumulated into dX and/or multiplied by tanh'(H) = 1 - H^2
+constexpr int BWDX_SPLITS = 4;
 static int dense_bwd_x(const float* P, const DenseP& L, const float* dY, int64_t M, float* dX, int64_t ld_dx,
-                       int accumulate, const float* H, int64_t ld_h, cudaStream_t st) {
+                       int accumulate, const float* H, int64_t ld_h, cudaStream_t st, float* scratch = nullptr) {
+  if (scratch && L.n_out >= 400) {
+    // long reduction (the 784 logits of the output layer): K split into partial products, one epilogue kernel
+    GemmArgs g;
+    g.A = dY; g.sa_m = L.n_out; g.sa_k = 1;
+    g.B = P + L.w; g.sb_k = 1; g.sb_n = L.n_out;
+    g.C = scratch; g.ldc = L.n_in;
+    g.M = (int)M; g.N = L.n_in; g.K = L.n_out;
+    g.small_tile = 1; g.split_k = BWDX_SPLITS; g.split_stride = M * L.n_in;
+    IWAE_TRY(gemm_f32(g, st));
+    return splitk_mul_h(scratch, BWDX_SPLITS, (int)M, L.n_in, H, ld_h, accumulate, dX, ld_dx, st);
+  }
   GemmArgs g;
   g.A = dY; g.sa_m = L.n_out; g.sa_k = 1;
   g.B = P + L.w; g.sb_k = 1; g.sb_n = L.n_out;       // B(o, i) = W[i, o]
@@ -557,7 +569,9 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
   IWAE_TRY(ar.get(&da2, (size_t)R * h1)); IWAE_TRY(ar.get(&da1, (size_t)R * h1));
   IWAE_TRY(ar.get(&dzin, (size_t)R * m.dec_in()));
   IWAE_TRY(dense_bwd_w(m.dec.d2, f.a2, h1, R, dl, grads, st));
-  IWAE_TRY(dense_bwd_x(P, m.dec.d2, dl, R, da2, h1, 0, f.a2, h1, st));
+  float* dx_scratch = nullptr;       // split-K partial sums of the output layer's dX (training shapes only)
+  if (R <= 4096) IWAE_TRY(ar.get(&dx_scratch, (size_t)BWDX_SPLITS * R * h1));
+  IWAE_TRY(dense_bwd_x(P, m.dec.d2, dl, R, da2, h1, 0, f.a2, h1, st, dx_scratch));
   IWAE_TRY(dense_bwd_w(m.dec.d1, f.a1, h1, R, da2, grads, st));
   IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, st));
   IWAE_TRY(dense_bwd_w(m.dec.d0, f.zin, f.ld_zin, R, da1, grads, st));

@@ -228,6 +228,9 @@ int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx
                   float* mu, float* sd, cudaStream_t st, float* l1_scratch = nullptr);
 // out[m, n] = act(sum_s partial[s][m, n] + bias[n])   (split-K forward, see dense_fwd in abi.cu)
 int splitk_bias_act(const float* partial, int splits, int M, int N, const float* bias, int act, float* out, cudaStream_t st);
+// dX[m, n] = (sum_s partial[s][m, n] (+ dX[m, n])) * (1 - H[m, n]^2 if H)   (split-K backward through tanh)
+int splitk_mul_h(const float* partial, int splits, int M, int N, const float* H, int64_t ld_h, int accumulate, float* dX,
+                 int64_t ld_dx, cudaStream_t st);
 void tc_release(iwae_ctx* ctx);
 int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream_t st);
 int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st);

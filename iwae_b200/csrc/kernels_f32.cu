@@ -928,6 +928,27 @@ int splitk_bias_act(const float* partial, int splits, int M, int N, const float*
   return 0;
 }
 
+__global__ void splitk_mul_h_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ H,
+                                    int64_t ld_h, int accumulate, float* __restrict__ dX, int64_t ld_dx) {
+  const int total = M * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int m = i / N, n = i % N;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += partial[(size_t)s * total + i];
+    if (accumulate) v += dX[(int64_t)m * ld_dx + n];
+    if (H) { const float h = H[(int64_t)m * ld_h + n]; v *= (1.f - h * h); }
+    dX[(int64_t)m * ld_dx + n] = v;
+  }
+}
+int splitk_mul_h(const float* partial, int splits, int M, int N, const float* H, int64_t ld_h, int accumulate, float* dX,
+                 int64_t ld_dx, cudaStream_t st) {
+  if (M * N == 0) return 0;
+  const int blocks = std::min((M * N + 255) / 256, 148 * 8);
+  splitk_mul_h_kernel<<<blocks, 256, 0, st>>>(partial, splits, M, N, H, ld_h, accumulate, dX, ld_dx);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- train-step graph replay helpers ----
 const StepDyn* g_step_dyn = nullptr;
 
