@@ -184,3 +184,23 @@ def test_full_model_against_independent_torch_distributions_build(oracle):
     assert abs(float(res["iwae_elbo"]) - float(iwae)) < 1e-10 * abs(float(iwae))
     for (name, go), gi in zip(g_or.items(), g_ind):
         assert torch.allclose(go, gi, rtol=1e-8, atol=1e-12), name
+
+
+def test_philox_bernoulli_restatement(oracle):
+    """The device re-binarisation rule (utils.bernoullisample on the GPU): p = 0 / 1 are never / always drawn, the mean
+    follows p, an epoch is a pure function of (seed, epoch), and the four draws of one Philox call are the call's four
+    words in order (checked against the Philox restatement that the Random123 known-answer tests pin)."""
+    rs = np.random.RandomState(3)
+    p = rs.rand(50, 784).astype(np.float32) ** 4
+    p[0, :10] = 0.0
+    p[0, 10:20] = 1.0
+    a = oracle.philox_bernoulli(p, 123, 0)
+    assert a.shape == p.shape and set(np.unique(a)) <= {0.0, 1.0}
+    assert not a[0, :10].any() and a[0, 10:20].all()
+    assert abs(a.mean() - p.mean()) < 0.01
+    assert np.array_equal(a, oracle.philox_bernoulli(p, 123, 0))
+    assert not np.array_equal(a, oracle.philox_bernoulli(p, 123, 1)) and not np.array_equal(a, oracle.philox_bernoulli(p, 124, 0))
+    words = oracle.philox4x32_10(np.array([[1, 0, 7, 0x42]], dtype=np.uint32), np.array([[9, 0]], dtype=np.uint32))[0]
+    u = (words >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    probe = np.full(8, 0.5, dtype=np.float32)                   # elements 4..7 use Philox call q = 1
+    assert np.array_equal(oracle.philox_bernoulli(probe, 9, 7)[4:], (u < 0.5).astype(np.float32))
