@@ -7,12 +7,14 @@
 //   p(x|z1): tanh, tanh, 784 logits -> Bernoulli log-lik reduced in the epilogue (logits never leave TMEM)
 // Roles (320 threads with the default NSUB=1): warp 0 = weight producer (cp.async.bulk slabs through an mbarrier
 // ring; weights are fp16, pre-packed in the exact smem image, ~0.62 MB per tile from L2), warp 1 = MMA issuer
-// (tcgen05.mma, kind::f16, M=128, fp32 accumulators in TMEM, two 128-column accumulator buffers; warp-uniform
-// control flow, one elect.sync lane issues), warps 2-9 = epilogue (tcgen05.ld -> the bias is already folded into
+// (tcgen05.mma, kind::f16, M=128, fp32 accumulators in TMEM, two 128-column accumulator buffers; both of these
+// roles run inside ONE elected thread each), warps 2-9 = epilogue (tcgen05.ld -> the bias is already folded into
 // the GEMM through a constant-1 column -> tanh / exp / softplus -> fp16 back to smem for the next layer; warps e
 // and e+4 share a TMEM lane quarter and split the accumulator columns; log-density terms accumulate per row in
 // registers).  Two CTAs are resident per SM (<=113 KB smem, 256 TMEM columns each) so one CTA's epilogue overlaps
-// the other CTA's MMAs.  `make NSUB=2` builds the alternative schedule: one persistent CTA per SM on a 256-row
+// the other CTA's MMAs.  Every CTA owns a contiguous range of tiles (consecutive tiles share the image, whose
+// constants are loaded once); the second decoder layer parks its first output chunk in the by then dead z1 buffer so
+// that its epilogue overlaps the MMAs of its second chunk.  `make NSUB=2` builds the alternative schedule: one persistent CTA per SM on a 256-row
 // macro-tile whose two sub-tiles share every weight slab (measured slower, kept for reference).
 // Operand layout: no-swizzle K-major core matrices, element (row,k) at (k/8)*rows*16 + row*16 + (k%8)*2 bytes,
 // i.e. LBO = rows*16 (K direction), SBO = 128 (M/N direction).  DESIGN.md section 4.1 has the roofline and the
