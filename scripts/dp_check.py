@@ -26,7 +26,14 @@ for t in range(3):
 diff = float((m.params - m1.params).abs().max())
 flag = torch.tensor([1.0 if (ok_eval and diff < 2e-5) else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+# throughput of the data-parallel step (latency-bound: one ~2 MB all-reduce per step)
+import time
+for t in range(20): dp_train_step(m, X[:20], 50, 1.0, o, "iwae_elbo", seed=500 + t)
+torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+for t in range(300): dp_train_step(m, X[:20], 50, 1.0, o, "iwae_elbo", seed=600 + t)
+torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) / 300
 if rank == 0:
+    print(f"world={world} data-parallel train step (k=50, global batch 20): {1e3*dt:.3f} ms/step = {1/dt:.0f} steps/s")
     print(f"world={world} eval bit-exact={ok_eval} dp-vs-single max |dparam|={diff:.2e} ->", "OK" if flag.item() == 1 else "FAIL")
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)
