@@ -964,22 +964,34 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                 // <= (1e-6*inv)^2).  Branch-free over the group; a warp vote re-does the group exactly in
                 // the rare case that some sd is < ~1e-3.
                 float inv[8];
-                bool small = false;
+                float invmax = 0.f;                       // padded dims have a' = 0 -> inv = 1: never "small"
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   inv[i] = ex2_approx(-__uint_as_float(r[8 + i]));
-                  small |= (i < nv) && !(inv[i] < 1024.f);
+                  invmax = fmaxf(invmax, inv[i]);
                 }
-                if (!__any_sync(0xffffffffu, small)) {
+                if (!__any_sync(0xffffffffu, !(invmax < 1024.f))) {
+                  if (nv == 8) {                          // complete group (warp-uniform): no per-dim masks
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
-                    const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
-                    const float isd = fmaf(-1e-6f * inv[i], inv[i], inv[i]);
-                    const float ls = fmaf(__uint_as_float(r[8 + i]), LN2_F, 1e-6f * inv[i]);
-                    const float t = (i < nv) ? (z - __uint_as_float(r[i])) * isd : 0.f;
-                    t2sum = fmaf(t, t, t2sum);
-                    lssum += (i < nv) ? ls : 0.f;
+                    for (int i = 0; i < 8; ++i) {
+                      const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
+                      const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                      const float c = 1e-6f * inv[i];
+                      const float t = (z - __uint_as_float(r[i])) * fmaf(-c, inv[i], inv[i]);
+                      t2sum = fmaf(t, t, t2sum);
+                      lssum += fmaf(__uint_as_float(r[8 + i]), LN2_F, c);
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
+                      const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                      const float isd = fmaf(-1e-6f * inv[i], inv[i], inv[i]);
+                      const float ls = fmaf(__uint_as_float(r[8 + i]), LN2_F, 1e-6f * inv[i]);
+                      const float t = (i < nv) ? (z - __uint_as_float(r[i])) * isd : 0.f;
+                      t2sum = fmaf(t, t, t2sum);
+                      lssum += (i < nv) ? ls : 0.f;
+                    }
                   }
                 } else {
 #pragma unroll
