@@ -847,18 +847,21 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       float bern_s = 0.f, bern_a = 0.f, bern_lg = 0.f;     // FAST Bernoulli accumulators (log2 units)
       for (int l = 0; l < P.nlayers; ++l) {
         const Layer& Ly = P.L[l];
+        // layer constants once per layer (the asm statements' memory clobbers otherwise force re-reads per chunk)
+        const int kind = Ly.kind, nchunks = Ly.nchunks;
+        const bool wait_all = Ly.inplace && nchunks > 1, split_dst = Ly.split_dst != 0, signal_act = Ly.signal_act != 0;
         uint8_t* dst = Ly.dst ? T.bufP : T.bufZ;
-        if (Ly.inplace && Ly.nchunks > 1) {
+        if (wait_all) {
           // all chunks' MMAs must have retired before the input buffer is overwritten
-          for (int c = 0; c < Ly.nchunks; ++c) {
+          for (int c = 0; c < nchunks; ++c) {
             const uint32_t b = (cc + c) & 1;
             mbar_wait(&S.acc_full[u][b], (full_bits >> b) & 1u, 300);
             full_bits ^= 1u << b;
           }
         }
-        for (int c = 0; c < Ly.nchunks; ++c) {
+        for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = cc & 1;
-          if (!(Ly.inplace && Ly.nchunks > 1)) {
+          if (!wait_all) {
             mbar_wait(&S.acc_full[u][buf], (full_bits >> buf) & 1u, 301);
             full_bits ^= 1u << buf;
           }
@@ -868,17 +871,17 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
           const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
 
-          if (Ly.kind == EPI_TANH) {
+          if (kind == EPI_TANH) {
             // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
             // bias 30 (tanh(30) == 1.0f): no per-element special cases
-            uint8_t* dstc = (Ly.split_dst && c == 0) ? T.bufZ : dst;
+            uint8_t* dstc = (split_dst && c == 0) ? T.bufZ : dst;
             for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
               store16(dstc, row, off + g, v);
             });
-          } else if (Ly.kind == EPI_GSAMPLE) {
+          } else if (kind == EPI_GSAMPLE) {
             // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8]
             // (FAST: the log-std head is pre-scaled by log2(e) at pack time).
             // z2 = mu2 + std2*eps2 (iwae2.py:65); one 16-byte A-operand row segment per group.
@@ -946,7 +949,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
             }
             // -lq2 + lpz2: the two log(2 pi)/2 constants cancel
             if (FAST) lw += 0.5f * e2sum + LN2_F * lgsum - 0.5f * z2sum;
-          } else if (Ly.kind == EPI_GLOGP) {
+          } else if (kind == EPI_GLOGP) {
             // same column layout; log p(z1|z2) over dims off..off+cnt (iwae2.py:120), z1 re-read from bufZ
             float t2sum = 0.f, lssum = 0.f;
             int n_mine = 0;
@@ -1064,7 +1067,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 6);
           ++cc;
         }
-        if (Ly.signal_act) {
+        if (signal_act) {
 #ifndef IWAE_EXP_NOFENCE
           fence_proxy_async();
 #endif
