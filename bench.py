@@ -325,7 +325,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_train(ib, torch, X, bias, steps=300, warmup=30):
+def bench_train(ib, torch, X, bias, steps=1000, warmup=50):
     """Second half of BASELINE.json's metric: k=50 train steps/s, batch 20, 2 stochastic layers
     (configs[1]); batch already on the device, forward + backward + Keras-Adam per step."""
     from iwae_b200 import _abi
