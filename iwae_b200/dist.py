@@ -54,7 +54,7 @@ def llh_eval_sharded(local_eval: Callable, n_images: int, device=None, gather: b
     return (total / max(n_images, 1)).reshape(()), per
 
 
-def model_llh_sharded(model, x_all, n_samples: int = 5000, y_all=None, precision: str = "tc_f16_fast",
+def model_llh_sharded(model, x_all, n_samples: int = 5000, y_all=None, precision: str = "auto",
                       seed: int = 123, gather: bool = False):
     """The k=5000 test-set log-likelihood of main.py:170-184 over all ranks.  `x_all` [N,784] (host or
     device; every rank passes the same array and evaluates its own slice)."""

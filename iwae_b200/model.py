@@ -513,9 +513,25 @@ class IWAE:
         return g
 
     # ---- k-sample test log-likelihood (main.py:170-184) ------------------------------------------
-    def llh(self, x, n_samples=5000, y=None, precision="tc_f16_fast", seed=None, img_offset=0):
+    def tc_supported(self) -> bool:
+        """Whether the fused tcgen05 evaluation kernel covers this architecture (the limits `build_program` in
+        csrc/eval_tc.cu enforces: one 208-column activation buffer, one 112-column z1 buffer, <= 7 logit chunks)."""
+        c = self._cfg
+        ok = c.h1 + 1 <= 208 and c.d1 <= 100 and c.n_x <= 784 and c.d1 + (c.n_cond if self._cfg.n_cond else 0) + 1 <= 112
+        if c.kind == _abi.KIND_IWAE2:
+            ok = ok and c.h2 + 1 <= 208 and c.d2 <= 56
+        return bool(ok)
+
+    def _precision(self, precision):
+        """None / "auto": the fused tensor-core kernel when the architecture fits it, else the fp32 CUDA kernels."""
+        if precision in (None, "auto"):
+            return "tc_f16_fast" if self.tc_supported() else "fp32"
+        return precision
+
+    def llh(self, x, n_samples=5000, y=None, precision="auto", seed=None, img_offset=0):
         """Per-example log-mean-exp of `n_samples` importance weights for every row of x (device
         resident), and their fp64 sum: returns (per_example [N] tensor, sum as 0-dim fp64 tensor)."""
+        precision = self._precision(precision)
         x, y = self._check_x(x, y)
         N = x.shape[0]
         per = self._alloc(max(N, 1))[:N]
@@ -526,10 +542,11 @@ class IWAE:
                                     _ptr(total), _stream_ptr()), "iwae_llh_eval")
         return per, total
 
-    def monitor(self, x, n_samples, y=None, precision="tc_f16_fast", seed=None):
+    def monitor(self, x, n_samples, y=None, precision="auto", seed=None):
         """The monitoring numbers of `val_step` on a whole test set (main.py:152) at beta = 1 through the fused
         evaluation kernel: {'iwae_elbo', 'vae_elbo'} as batch means plus the per-example vectors, without
         materialising any [k,B,.] tensor."""
+        precision = self._precision(precision)
         x, y = self._check_x(x, y)
         N = x.shape[0]
         per_i, per_v = self._alloc(max(N, 1))[:N], self._alloc(max(N, 1))[:N]
@@ -545,10 +562,11 @@ class IWAE:
         res["vae_elbo_per_example"] = DeviceValue(per_v)
         return res
 
-    def llh_host(self, x_host: np.ndarray, n_samples=5000, y_host=None, precision="tc_f16_fast", seed=None,
+    def llh_host(self, x_host: np.ndarray, n_samples=5000, y_host=None, precision="auto", seed=None,
                  img_offset=0):
         """Same through the reference-facing HOST-buffer entry point (iwae_llh_eval_host): x (and y) are
         host arrays, copied to the device, evaluated, results copied back; synchronous."""
+        precision = self._precision(precision)
         x_host = np.ascontiguousarray(x_host, dtype=np.float32)
         N = x_host.shape[0]
         per = np.empty(N, dtype=np.float32)

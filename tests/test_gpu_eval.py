@@ -186,3 +186,20 @@ def test_random_architectures_both_paths(oracle, seed):
     for prec, tol in (("fp32", RTOL), ("tc_f16", TC_RTOL), ("tc_f16_fast", TC_RTOL)):
         per, _ = m.llh(case["x"], k, precision=prec, seed=SEED, img_offset=5)
         assert rel(per.cpu().numpy(), ref) < tol, (kind, h, d, N, k, prec, rel(per.cpu().numpy(), ref))
+
+
+def test_auto_precision_falls_back_to_fp32_kernels_outside_the_fused_kernels_limits(oracle):
+    """precision="auto" (the default) uses the fused tensor-core kernel when the architecture fits it and the fp32
+    CUDA kernels otherwise (h = 300 here) - never an error, never the CPU."""
+    case = make_case(oracle, "iwae1", 300, 20, 3, 1, seed=77, scale=0.7)
+    case["d"], case["h"] = 20, 300
+    m = build("iwae1", case, case)
+    assert not m.tc_supported()
+    per, _ = m.llh(case["x"], 64, seed=SEED)
+    per32, _ = m.llh(case["x"], 64, precision="fp32", seed=SEED)
+    assert torch.equal(per, per32)
+    assert rel(per.cpu().numpy(), oracle_llh(oracle, "iwae1", case, 64)) < RTOL
+    with pytest.raises(Exception):
+        m.llh(case["x"], 64, precision="tc_f16_fast", seed=SEED)
+    small = _case(oracle, "iwae2", 2)
+    assert build("iwae2", small, small).tc_supported()
