@@ -311,22 +311,29 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   // ---- Gaussian terms                                                      iwae1.py:107-109, iwae2.py:116-122
   IWAE_TRY(pick(ar, o->lpz, (size_t)R, &f.lpz));
   IWAE_TRY(pick(ar, o->lq1, (size_t)R, &f.lq1));
-  IWAE_TRY(normal_logp_rows(f.z1, f.mu1, f.std1, 1, 0.f, B, k, d1, f.lq1, st));
+  // all Gaussian log-density row sums of the call in ONE launch (they are independent; up to four kernels before)
+  NlpJobs jobs;
+  auto add_job = [&](const float* z, const float* mu, const float* sd, int bcast, float std_extra, int d, float* out) {
+    NlpJob& j = jobs.job[jobs.count++];
+    j.z = z; j.mu = mu; j.sd = sd; j.bcast = bcast; j.std_extra = std_extra; j.d = d; j.out = out;
+  };
+  add_job(f.z1, f.mu1, f.std1, 1, 0.f, d1, f.lq1);
   if (m.two_layer()) {
     IWAE_TRY(pick(ar, o->lq2, (size_t)R, &f.lq2));
     IWAE_TRY(pick(ar, o->lp12, (size_t)R, &f.lp12));
-    IWAE_TRY(normal_logp_rows(f.z2, nullptr, nullptr, 0, 0.f, B, k, d2, f.lpz, st));        // lpz2
-    IWAE_TRY(normal_logp_rows(f.z2, f.mu2, f.std2, 0, 0.f, B, k, d2, f.lq2, st));           // lqz2z1
-    IWAE_TRY(normal_logp_rows(f.z1, f.pmu, f.pstd, 0, 0.f, B, k, d1, f.lp12, st));          // lpz1z2
+    add_job(f.z2, nullptr, nullptr, 0, 0.f, d2, f.lpz);        // lpz2
+    add_job(f.z2, f.mu2, f.std2, 0, 0.f, d2, f.lq2);           // lqz2z1
+    add_job(f.z1, f.pmu, f.pstd, 0, 0.f, d1, f.lp12);          // lpz1z2
   } else if (m.learned_prior()) {
-    IWAE_TRY(normal_logp_rows(f.z1, f.pmu, f.pstd, 1, 0.f, B, k, d1, f.lpz, st));           // lpzy
+    add_job(f.z1, f.pmu, f.pstd, 1, 0.f, d1, f.lpz);           // lpzy
   } else {
-    IWAE_TRY(normal_logp_rows(f.z1, nullptr, nullptr, 0, 0.f, B, k, d1, f.lpz, st));        // lpz
+    add_job(f.z1, nullptr, nullptr, 0, 0.f, d1, f.lpz);        // lpz
   }
   if (opt.want_dreg || o->dreg) {
     IWAE_TRY(ar.get(&f.lqst, (size_t)R));
-    IWAE_TRY(normal_logp_rows(f.z1, f.mu1, f.std1, 1, 1e-6f, B, k, d1, f.lqst, st));        // task02.py:61-65
+    add_job(f.z1, f.mu1, f.std1, 1, 1e-6f, d1, f.lqst);        // task02.py:61-65
   }
+  IWAE_TRY(normal_logp_rows_multi(jobs, B, k, st));
   if ((o->kl || o->scalars) && !m.two_layer()) {
     IWAE_TRY(pick(ar, o->kl, (size_t)B, &f.kl));
     IWAE_TRY(kl_rows(f.mu1, f.std1, B, d1, f.kl, st));                                      // iwae1.py:116

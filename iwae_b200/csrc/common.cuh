@@ -159,6 +159,10 @@ int philox_fill(uint64_t seed, int stream_id, int64_t img_offset, int B, int k, 
 // std_extra is added to std (DReG's second +1e-6, task02.py:61-63).
 int normal_logp_rows(const float* z, const float* mu, const float* std, int bcast, float std_extra,
                      int B, int k, int d, float* out, cudaStream_t st);
+// several independent normal_logp_rows jobs in one launch (blockIdx.y = job)
+struct NlpJob { const float* z; const float* mu; const float* sd; int bcast; float std_extra; int d; float* out; };
+struct NlpJobs { NlpJob job[6]; int count = 0; };
+int normal_logp_rows_multi(const NlpJobs& jobs, int B, int k, cudaStream_t st);
 int kl_rows(const float* mu, const float* std, int B, int d, float* out, cudaStream_t st);
 int bern_reduce_partials(const float* partial, int R, int nt, float* lpxz, cudaStream_t st);
 int bern_logp_rows(const float* logits, const float* x, int R, int B, int n, float* lpxz, cudaStream_t st);

@@ -324,6 +324,41 @@ int normal_logp_rows(const float* z, const float* mu, const float* sd, int bcast
   return 0;
 }
 
+__global__ void normal_logp_rows_multi_kernel(NlpJobs jobs, int B, int64_t R) {
+  const NlpJob& jb = jobs.job[blockIdx.y];
+  const float* __restrict__ z = jb.z; const float* __restrict__ mu = jb.mu; const float* __restrict__ sd = jb.sd;
+  const int d = jb.d, bcast = jb.bcast; const float std_extra = jb.std_extra;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {      // the same per-row arithmetic as normal_logp_rows_kernel
+    const int64_t prow = bcast ? (r % B) : r;
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      const float zz = z[r * d + j];
+      if (mu) {
+        const float sc = sd[prow * d + j] + std_extra;
+        const float t = zz / sc - mu[prow * d + j] / sc;
+        s += -0.5f * t * t - (LOG2PI_HALF + logf(sc));
+      } else {
+        s += -0.5f * zz * zz - LOG2PI_HALF;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) jb.out[r] = s;
+  }
+}
+int normal_logp_rows_multi(const NlpJobs& jobs, int B, int k, cudaStream_t st) {
+  const int64_t R = (int64_t)B * k;
+  if (R == 0 || jobs.count == 0) return 0;
+  int64_t blocks = (R + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  normal_logp_rows_multi_kernel<<<dim3((unsigned)blocks, (unsigned)jobs.count), 256, 0, st>>>(jobs, B, R);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void kl_rows_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int B, int d,
                                float* __restrict__ out) {
   // tfd.kl_divergence(N(mu,sd), N(0,1)) = 0.5 mu^2 + 0.5 expm1(2 log sd) - log sd   (A.2)
