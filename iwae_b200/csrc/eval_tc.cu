@@ -477,25 +477,26 @@ __device__ __forceinline__ float cos_approx(float v) { float r; asm("cos.approx.
 #define LN2_F 0.69314718055994530942f
 #define LOG2E_F 1.44269504088896340736f
 
-// Four N(0,1) for dims 4q..4q+3: Philox4x32-10 + Box-Muller (rng.cuh defines the mapping).  FAST uses the
-// MUFU approximations (lg2, sqrt, sin, cos on [-pi,pi)): same uniforms, normals equal to ~1e-6.
+// Eight N(0,1) for dims 8g..8g+7: Philox4x32-10 + Box-Muller on 16-bit uniforms (rng.cuh defines the mapping).
+// FAST builds the uniforms with two ALU ops each (no integer->float conversion, which would share the XU pipe
+// with the transcendentals) and uses the MUFU approximations (lg2, sqrt, sin, cos on (-pi,pi)): same uniforms,
+// normals equal to ~1e-6.
 template <bool FAST>
-__device__ __forceinline__ float4 normal4(uint64_t seed, uint32_t stream_id, uint32_t img, uint32_t s, uint32_t q) {
-  if (!FAST) return philox_normal4(seed, stream_id, img, s, q);
-  const uint4 r = philox4x32_10(make_uint4(s, q, img, stream_id), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  float o[4];
-  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+__device__ __forceinline__ void normal8(uint64_t seed, uint32_t stream_id, uint32_t img, uint32_t s, uint32_t g, float (&o)[8]) {
+  if (!FAST) { philox_normal8(seed, stream_id, img, s, g, o); return; }
+  const uint4 r = philox4x32_10(make_uint4(s, g, img, stream_id), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float u1 = (float)((rr[2 * h] >> 8) + 1u) * 5.9604644775390625e-8f;
-    const float u2 = (float)(rr[2 * h + 1] >> 8) * 5.9604644775390625e-8f;
+  for (int h = 0; h < 4; ++h) {
+    const float f1 = __uint_as_float(((w[h] >> 9) & 0x007FFF80u) | 0x3F800000u);     // 1 + hi16/65536
+    const float f2 = __uint_as_float(((w[h] << 7) & 0x007FFF80u) | 0x3F800000u);     // 1 + lo16/65536
+    const float u1 = f1 - 0.99999237060546875f;                                      // (hi16 + 0.5)/65536, exact
     const float rad = sqrt_approx(-2.0f * LN2_F * lg2_approx(u1));
-    // cos(2 pi u) = -cos(2 pi u - pi), sin likewise: keeps the MUFU argument inside [-pi, pi)
-    const float th = fmaf(u2, 6.283185307179586f, -3.14159265358979f);
+    // theta = 2 pi u2 - pi in (-pi, pi), u2 = (lo16 + 0.5)/65536;  cos(2 pi u2) = -cos(theta), sin likewise
+    const float th = fmaf(f2, 6.283185307179586f, -9.4247300721120986f);             // -(3 pi - 2 pi 2^-17)
     o[2 * h] = -rad * cos_approx(th);
     o[2 * h + 1] = -rad * sin_approx(th);
   }
-  return make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // TMEM -> registers, 16 columns at a time, software-pipelined: the load of this warp's next group is
@@ -750,8 +751,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
         const int one_col = d1 + P.nc;
         float e1sum = 0.f, z1sum = 0.f;
         // complete group of 8 latent dims (FAST): no per-element predicates, vector constant loads
-        auto full_group = [&](int k0, const float4 na, const float4 nb, float (&v)[8]) {
-          const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+        auto full_group = [&](int k0, const float (&e)[8], float (&v)[8]) {
           const float4 m0 = *reinterpret_cast<const float4*>(&T.mu[k0]), m1 = *reinterpret_cast<const float4*>(&T.mu[k0 + 4]);
           const float4 s0 = *reinterpret_cast<const float4*>(&T.sd[k0]), s1 = *reinterpret_cast<const float4*>(&T.sd[k0 + 4]);
           const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
@@ -772,66 +772,57 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
         };
         int k0 = 8 * half;
         if (FAST) {
-          // two groups per iteration: four independent Philox / Box-Muller chains in flight per thread (the
+          // two groups per iteration: two independent Philox / Box-Muller chains in flight per thread (the
           // generator is a long dependent chain - 10 rounds - so one chain alone issues at ~0.25 IPC)
           for (; k0 + 24 <= d1_full; k0 += 32) {
-            const float4 na = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2));
-            const float4 nb = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 1u);
-            const float4 nc = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 4u);
-            const float4 nd = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 5u);
-            float va[8], vb[8];
-            full_group(k0, na, nb, va);
-            full_group(k0 + 16, nc, nd, vb);
+            float ea[8], eb[8], va[8], vb[8];
+            normal8<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3), ea);
+            normal8<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3) + 2u, eb);
+            full_group(k0, ea, va);
+            full_group(k0 + 16, eb, vb);
           }
         }
         for (; k0 < P.kz_pad; k0 += 16) {
           float v[8];
           if (FAST && k0 < d1_full) {
-            const float4 na = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2));
-            const float4 nb = normal4<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 2) + 1u);
-            full_group(k0, na, nb, v);
+            float ea[8];
+            normal8<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3), ea);
+            full_group(k0, ea, v);
             continue;
           } else {
+            float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (k0 < d1) normal8<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3), e);
 #pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-              const int j0 = k0 + 4 * qq;
-              float e[4] = {0.f, 0.f, 0.f, 0.f};
-              if (j0 < d1) {
-                const float4 n4 = normal4<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(j0 >> 2));
-                e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int j = j0 + i;
-                float val = 0.f;
-                if (j < d1) {
-                  const float sd = T.sd[j], m = T.mu[j];
-                  const float z = fmaf(e[i], sd, m);
-                  if (FAST) {
-                    e1sum = fmaf(e[i], e[i], e1sum);
-                    if (P.learned_prior) { const float tp = (z - T.pmu[j]) * T.psd[j]; z1sum = fmaf(tp, tp, z1sum); }
-                    else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
-                  } else {
-                    const float t = z / sd - m / sd;                         // TFP op order
-                    lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));       // - lq(z1|x)
-                    if (!P.two_layer) {
-                      if (P.learned_prior) {
-                        const float ps = T.psd[j];
-                        const float tp = z / ps - T.pmu[j] / ps;
-                        lw += -0.5f * tp * tp - (LOG2PI_HALF_F + logf(ps));
-                      } else {
-                        lw += -0.5f * z * z - LOG2PI_HALF_F;
-                      }
+            for (int i = 0; i < 8; ++i) {
+              const int j = k0 + i;
+              float val = 0.f;
+              if (j < d1) {
+                const float sd = T.sd[j], m = T.mu[j];
+                const float z = fmaf(e[i], sd, m);
+                if (FAST) {
+                  e1sum = fmaf(e[i], e[i], e1sum);
+                  if (P.learned_prior) { const float tp = (z - T.pmu[j]) * T.psd[j]; z1sum = fmaf(tp, tp, z1sum); }
+                  else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
+                } else {
+                  const float t = z / sd - m / sd;                         // TFP op order
+                  lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));       // - lq(z1|x)
+                  if (!P.two_layer) {
+                    if (P.learned_prior) {
+                      const float ps = T.psd[j];
+                      const float tp = z / ps - T.pmu[j] / ps;
+                      lw += -0.5f * tp * tp - (LOG2PI_HALF_F + logf(ps));
+                    } else {
+                      lw += -0.5f * z * z - LOG2PI_HALF_F;
                     }
                   }
-                  val = z;
-                } else if (j < one_col) {
-                  val = (T.label == j - d1) ? 1.f : 0.f;
-                } else if (j == one_col || j == one_col + 1) {      // two constant-1 columns: bias hi + lo
-                  val = 1.f;
                 }
-                v[4 * qq + i] = val;
+                val = z;
+              } else if (j < one_col) {
+                val = (T.label == j - d1) ? 1.f : 0.f;
+              } else if (j == one_col || j == one_col + 1) {      // two constant-1 columns: bias hi + lo
+                val = 1.f;
               }
+              v[i] = val;
             }
           }
           store8(T.bufZ, row, k0, v);
@@ -893,9 +884,8 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                 // complete group of 8 latent dims: branch-free
                 uint32_t r[16];
                 tmem_ld16(tbase + 2 * g8, r);
-                const float4 na = normal4<true>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2));
-                const float4 nb = normal4<true>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2) + 1u);
-                const float e[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+                float e[8];
+                normal8<true>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 3), e);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -909,37 +899,34 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
                 uint32_t r[16];
                 tmem_ld16(tbase + 2 * g8, r);
                 tmem_ld_wait();
+                float e[8];
+                normal8<FAST>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 3), e);
 #pragma unroll
-                for (int qq = 0; qq < 2; ++qq) {
-                  const float4 n4 = normal4<FAST>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 2) + qq);
-                  const float e[4] = {n4.x, n4.y, n4.z, n4.w};
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const int j = g8 + 4 * qq + i;
-                    float val = 0.f;
-                    if (j < cnt) {
-                      const float m = __uint_as_float(r[4 * qq + i]);
-                      const float a = __uint_as_float(r[8 + 4 * qq + i]);
-                      if (FAST) {
-                        const float sd = ex2_approx(a) + 1e-6f;
-                        const float z = fmaf(e[i], sd, m);
-                        e2sum = fmaf(e[i], e[i], e2sum);
-                        z2sum = fmaf(z, z, z2sum);
-                        lgsum += lg2_approx(sd);
-                        val = z;
-                      } else {
-                        const float sd = expf(a) + 1e-6f;
-                        const float z = e[i] * sd + m;
-                        const float t = z / sd - m / sd;
-                        lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                // - lqz2z1 (iwae2.py:118)
-                        lw += -0.5f * z * z - LOG2PI_HALF_F;                              // + lpz2   (iwae2.py:116)
-                        val = z;
-                      }
-                    } else if (j == cnt || j == cnt + 1) {
-                      val = 1.f;
+                for (int i = 0; i < 8; ++i) {
+                  const int j = g8 + i;
+                  float val = 0.f;
+                  if (j < cnt) {
+                    const float m = __uint_as_float(r[i]);
+                    const float a = __uint_as_float(r[8 + i]);
+                    if (FAST) {
+                      const float sd = ex2_approx(a) + 1e-6f;
+                      const float z = fmaf(e[i], sd, m);
+                      e2sum = fmaf(e[i], e[i], e2sum);
+                      z2sum = fmaf(z, z, z2sum);
+                      lgsum += lg2_approx(sd);
+                      val = z;
+                    } else {
+                      const float sd = expf(a) + 1e-6f;
+                      const float z = e[i] * sd + m;
+                      const float t = z / sd - m / sd;
+                      lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                // - lqz2z1 (iwae2.py:118)
+                      lw += -0.5f * z * z - LOG2PI_HALF_F;                              // + lpz2   (iwae2.py:116)
+                      val = z;
                     }
-                    v[4 * qq + i] = val;
+                  } else if (j == cnt || j == cnt + 1) {
+                    val = 1.f;
                   }
+                  v[i] = val;
                 }
               } else {
 #pragma unroll

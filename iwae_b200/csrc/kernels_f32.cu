@@ -245,25 +245,24 @@ __global__ void sample_latent_kernel(const float* __restrict__ mu, const float* 
                                      float* __restrict__ z, int B, int k, int d, uint64_t seed, int stream_id,
                                      int64_t img_offset, const StepDyn* __restrict__ dyn) {
   if (dyn) { seed = dyn->seed; img_offset = dyn->img_offset; }      // graph replay: per-step values live on the device
-  const int nq = (d + 3) / 4;
+  const int nq = (d + 7) / 8;                // one Philox call per dim-octet (rng.cuh)
   const int64_t total = (int64_t)k * B * nq;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(i % nq);
     const int64_t r = i / nq;
     const int b = (int)(r % B);
     const int s = (int)(r / B);
-    float e[4];
+    float e[8];
     if (eps_in) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) e[j] = (4 * q + j < d) ? eps_in[r * d + 4 * q + j] : 0.f;
+      for (int j = 0; j < 8; ++j) e[j] = (8 * q + j < d) ? eps_in[r * d + 8 * q + j] : 0.f;
     } else {
-      const float4 n4 = philox_normal4(seed, (uint32_t)stream_id, (uint32_t)(img_offset + b), (uint32_t)s, (uint32_t)q);
-      e[0] = n4.x; e[1] = n4.y; e[2] = n4.z; e[3] = n4.w;
+      philox_normal8(seed, (uint32_t)stream_id, (uint32_t)(img_offset + b), (uint32_t)s, (uint32_t)q, e);
     }
     const int64_t prow = bcast ? b : r;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = 4 * q + j;
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * q + j;
       if (c < d) {
         const float m = mu ? mu[prow * d + c] : 0.f;
         const float sdev = sd ? sd[prow * d + c] : 1.f;
@@ -275,7 +274,7 @@ __global__ void sample_latent_kernel(const float* __restrict__ mu, const float* 
 }
 int sample_latent(const float* mu, const float* sd, int bcast, const float* eps_in, float* eps_out, float* z,
                   int B, int k, int d, uint64_t seed, int stream_id, int64_t img_offset, cudaStream_t st) {
-  const int64_t total = (int64_t)k * B * ((d + 3) / 4);
+  const int64_t total = (int64_t)k * B * ((d + 7) / 8);
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
   sample_latent_kernel<<<blocks, 256, 0, st>>>(mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset,

@@ -426,24 +426,26 @@ def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
 
 def philox_normal(seed: int, stream: int, img_offset: int, B: int, k: int, d: int) -> np.ndarray:
     """eps [k,B,d] float32 as generated by the CUDA path (iwae_b200/csrc/rng.cuh):
-    counter = (sample s, dim-quad q, global image index, stream id), key = (seed lo, seed hi);
-    each Philox call gives 4 uint32 -> two Box-Muller pairs -> 4 normals for dims 4q..4q+3.
-    u1 = ((r>>8)+1)*2^-24 in (0,1], u2 = (r>>8)*2^-24; n0 = sqrt(-2 ln u1) cos(2 pi u2), n1 = ... sin(...)."""
-    nq = (d + 3) // 4
+    counter = (sample s, dim-octet g, global image index, stream id), key = (seed lo, seed hi);
+    each Philox call gives 4 uint32; word h -> one Box-Muller pair for dims 8g+2h, 8g+2h+1 from two 16-bit
+    uniforms: u1 = (hi16 + 0.5) / 65536, u2 = (lo16 + 0.5) / 65536;
+    n0 = sqrt(-2 ln u1) cos(2 pi u2), n1 = sqrt(-2 ln u1) sin(2 pi u2)."""
+    ng = (d + 7) // 8
     s = np.arange(k, dtype=np.uint32)[:, None, None]
     b = (np.arange(B, dtype=np.uint64) + np.uint64(img_offset)).astype(np.uint32)[None, :, None]
-    q = np.arange(nq, dtype=np.uint32)[None, None, :]
-    ctr = np.stack(np.broadcast_arrays(s, q, b, np.uint32(stream)), axis=-1)
+    g = np.arange(ng, dtype=np.uint32)[None, None, :]
+    ctr = np.stack(np.broadcast_arrays(s, g, b, np.uint32(stream)), axis=-1)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
     key = np.broadcast_to(key, ctr.shape[:-1] + (2,))
-    r = (philox4x32_10(ctr, key) >> np.uint32(8)).astype(np.float64)   # top 24 bits
-    out = np.empty((k, B, nq * 4), dtype=np.float64)
-    for j in range(2):
-        u1 = (r[..., 2 * j] + 1.0) * 2.0 ** -24
-        u2 = r[..., 2 * j + 1] * 2.0 ** -24
+    r = philox4x32_10(ctr, key)
+    out = np.empty((k, B, ng * 8), dtype=np.float64)
+    for h in range(4):
+        w = r[..., h]
+        u1 = ((w >> np.uint32(16)).astype(np.float64) + 0.5) * 2.0 ** -16
+        u2 = ((w & np.uint32(0xFFFF)).astype(np.float64) + 0.5) * 2.0 ** -16
         rad = np.sqrt(-2.0 * np.log(u1))
-        out[..., 2 * j::4] = rad * np.cos(2.0 * np.pi * u2)
-        out[..., 2 * j + 1::4] = rad * np.sin(2.0 * np.pi * u2)
+        out[..., 2 * h::8] = rad * np.cos(2.0 * np.pi * u2)
+        out[..., 2 * h + 1::8] = rad * np.sin(2.0 * np.pi * u2)
     return out[..., :d].astype(np.float32)
 
 
