@@ -5,17 +5,21 @@
 //   z1 = mu1(x) + std1(x)*eps   (Philox in registers)              -> fp16 A operand in smem
 //   [IWAE2]  q(z2|z1): tanh,tanh,(mu2|log-std2) -> z2 ; p(z1|z2): tanh,tanh,(mu|log-std) -> log p(z1|z2)
 //   p(x|z1): tanh, tanh, 784 logits -> Bernoulli log-lik reduced in the epilogue (logits never leave TMEM)
-// Roles (320 threads with the default NSUB=1): warp 0 = weight producer (cp.async.bulk slabs through an mbarrier
-// ring; weights are fp16, pre-packed in the exact smem image, ~0.62 MB per tile from L2), warp 1 = MMA issuer
-// (tcgen05.mma, kind::f16, M=128, fp32 accumulators in TMEM, two 128-column accumulator buffers; both of these
-// roles run inside ONE elected thread each), warps 2-9 = epilogue (tcgen05.ld -> the bias is already folded into
-// the GEMM through a constant-1 column -> tanh / exp / softplus -> fp16 back to smem for the next layer; warps e
-// and e+4 share a TMEM lane quarter and split the accumulator columns; log-density terms accumulate per row in
-// registers).  Two CTAs are resident per SM (<=113 KB smem, 256 TMEM columns each) so one CTA's epilogue overlaps
-// the other CTA's MMAs.  Every CTA owns a contiguous range of tiles (consecutive tiles share the image, whose
+// The kernel runs as CTA PAIRS (clusters of two CTAs on the two SMs of a TPC): every tcgen05.mma is a cta_group::2
+// instruction with M = 256 - rows 0..127 are the tile of the even (leader) CTA, rows 128..255 the tile of its peer -
+// and each CTA stores only its half (N/2 columns) of every weight slab.
+// Roles (320 threads): warp 0 = weight producer (cp.async.bulk half-slabs through an mbarrier ring; weights are fp16,
+// pre-packed in the exact smem image, ~0.31 MB per tile and CTA from L2), warp 1 = MMA issuer in the leader (tcgen05.mma,
+// kind::f16, fp32 accumulators in TMEM, two 128-column accumulator buffers; completion multicast to both CTAs' mbarriers)
+// and slab-arrival relay in the peer (both of these roles run inside ONE elected thread each), warps 2-9 = epilogue
+// (tcgen05.ld -> the bias is already folded into the GEMM through a constant-1 column -> tanh / exp / softplus -> fp16
+// back to smem for the next layer; warps e and e+4 share a TMEM lane quarter and split the accumulator columns;
+// log-density terms accumulate per row in registers; they arrive on the LEADER's mbarriers).  Two CTAs (of two
+// different pairs) are resident per SM (<=113 KB smem, 256 TMEM columns each) so one CTA's epilogue overlaps the other
+// CTA's MMAs.  Every pair owns a contiguous range of tile pairs (consecutive tiles share the image, whose
 // constants are loaded once); the second decoder layer parks its first output chunk in the by then dead z1 buffer so
-// that its epilogue overlaps the MMAs of its second chunk.  `make NSUB=2` builds the alternative schedule: one persistent CTA per SM on a 256-row
-// macro-tile whose two sub-tiles share every weight slab (measured slower, kept for reference).
+// that its epilogue overlaps the MMAs of its second chunk.  -DIWAE_PAIR=0 builds the round-1 schedule (independent
+// CTAs, cta_group::1).
 // Operand layout: no-swizzle K-major core matrices, element (row,k) at (k/8)*rows*16 + row*16 + (k%8)*2 bytes,
 // i.e. LBO = rows*16 (K direction), SBO = 128 (M/N direction).  DESIGN.md section 4.1 has the roofline and the
 // measured timeline.
@@ -26,6 +30,7 @@
 #include <stdio.h>
 #include <algorithm>
 #include <stdlib.h>
+#include <stddef.h>
 #include <vector>
 
 namespace tc {
@@ -342,29 +347,123 @@ __global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int mo
 #ifndef IWAE_PRODUCER_SLEEP
 #define IWAE_PRODUCER_SLEEP 32
 #endif
+// IWAE_PAIR = 1 (default): the kernel runs as CTA PAIRS (clusters of two CTAs on the two SMs of a TPC) and every
+// tcgen05.mma is a cta_group::2 instruction with M = 256: rows 0..127 are the tile of the even ("leader") CTA, rows
+// 128..255 the tile of its peer; each CTA keeps only HALF of every weight slab (N/2 columns of B) in its shared
+// memory, so the L2 -> shared-memory weight stream, the shared-memory operand reads of B and the number of MMA
+// instructions per row are all halved.  Only the leader issues MMAs; completion is multicast to both CTAs' mbarriers.
+// IWAE_PAIR = 0 builds the round-1 schedule (independent CTAs, cta_group::1) for A/B measurements.
+#ifndef IWAE_PAIR
+#define IWAE_PAIR 1
+#endif
+#if IWAE_PAIR
+#define IWAE_CG "cta_group::2"
+#else
+#define IWAE_CG "cta_group::1"
+#endif
+constexpr int PAIR = IWAE_PAIR ? 2 : 1;               // CTAs that share one MMA (and split every weight slab)
 constexpr int TILE_M = 128;
 constexpr int MAX_LAYERS = 9;
 constexpr int MAX_CHUNKS = 7;
 constexpr int CHUNK_N_MAX = 112;
-#ifndef IWAE_NSUB
-#define IWAE_NSUB 1
-#endif
-constexpr int NSUB = IWAE_NSUB;                       // 128-row sub-tiles per CTA: 1 = two independent CTAs per SM (default,
-                                                      // fastest measured), 2 = one persistent CTA per SM on a 256-row macro-tile
-                                                      // whose sub-tiles share every weight slab
-constexpr int CTAS_PER_SM = (NSUB == 2) ? 1 : 2;
-constexpr int NSTAGES = (NSUB == 2) ? 7 : 4;          // weight-slab ring depth (7 KB slabs)
-constexpr int SLAB_K = 32;
-constexpr int SLAB_BYTES = CHUNK_N_MAX * SLAB_K * 2;   // 7168
+constexpr int CTAS_PER_SM = 2;                        // two resident CTAs per SM: one CTA's epilogue overlaps the other's MMAs
+constexpr int NSTAGES = 4;                            // weight-slab ring depth
+constexpr int SLAB_K = 32 * PAIR;                     // K rows per slab: the ring holds NSTAGES * SLAB_K rows of B ahead of the MMAs
+constexpr int SLAB_BYTES = (CHUNK_N_MAX / PAIR) * SLAB_K * 2;   // 7168: this CTA's share of a slab
 constexpr int KZ_MAX = 112;                            // K capacity of the z1 buffer
 constexpr int KP_MAX = 208;                            // K capacity of the activation buffer
 constexpr int BUFZ_BYTES = TILE_M * KZ_MAX * 2;        // 28672
 constexpr int BUFP_BYTES = TILE_M * KP_MAX * 2;        // 53248
 constexpr int NX_MAX = 784;
 constexpr int D_MAX = 100;
-constexpr int NUM_EPI_WARPS = 8 * NSUB;               // 8 epilogue warps per sub-tile
+constexpr int NUM_EPI_WARPS = 8;                      // epilogue warps per CTA
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // producer warp, MMA warp, epilogue warps
-constexpr int TMEM_COLS = 256 * NSUB;                 // per sub-tile: 2 accumulator buffers x 128 columns
+constexpr int TMEM_COLS = 256;                        // 2 accumulator buffers x 128 columns
+
+// ---- cluster / cta_group-dependent PTX wrappers of the fused kernel (all tcgen05 instructions of one kernel must use
+// ---- the same cta_group; the self-test and micro-benchmark kernels above stay cta_group::1) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) inside the CTA of rank `rank`
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// Arrive on an mbarrier of any CTA of the cluster.  Default semantics (.release.cta), like CUTLASS's
+// ClusterBarrier::arrive(cta_id): an explicit .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front
+// of every arrive (~1,000 cycles each; the first pair-mode build was 20 % SLOWER than independent CTAs because of it).
+// What the arrive publishes is either "my tcgen05.ld of this accumulator have completed" (ordered by
+// tcgen05.fence::before_thread_sync) or shared-memory stores that a fence.proxy.async has already made visible to the
+// tensor core of the SM that owns that shared memory - neither needs a cluster-scope memory fence.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier that CTAs of the whole pair arrive on
+__device__ __forceinline__ void mbar_wait_pair(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns = 32) {
+  mbar_wait(bar, parity, tag, sleep_ns);
+}
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc." IWAE_CG ".sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg() {
+  asm volatile("tcgen05.relinquish_alloc_permit." IWAE_CG ".sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc." IWAE_CG ".sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate; M = 128 per CTA of the group
+__device__ __forceinline__ void umma_f16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma." IWAE_CG ".kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+// mbarrier arrive when all MMAs issued so far have retired; in pair mode the arrive is multicast to the barrier at
+// the same shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+#if IWAE_PAIR
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+#else
+  umma_commit(bar);
+#endif
+}
+// Predicated forms for the warp-convergent MMA role: all 32 lanes run the (warp-uniform) control flow and descriptor
+// arithmetic - which the compiler then keeps in UNIFORM registers, the operand form tcgen05.mma wants - and only the
+// elected lane (issue != 0) executes the tcgen05 instruction.
+__device__ __forceinline__ void umma_f16_cg_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma." IWAE_CG
+      ".kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg_pred(uint64_t* bar, uint32_t issue) {
+#if IWAE_PAIR
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3), "r"(issue)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+#endif
+}
+// instruction descriptor of the group MMA: M = 128 * PAIR
+__device__ __forceinline__ uint32_t make_idesc_cg(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | (((128u * PAIR) >> 4) << 24); }
 
 enum { EPI_TANH = 0, EPI_GSAMPLE = 1, EPI_GLOGP = 2, EPI_BERN = 3 };
 
@@ -378,8 +477,10 @@ struct Layer {
   int chunk_cnt[MAX_CHUNKS];   // real units / dims / pixels in the chunk
   int chunk_off[MAX_CHUNKS];   // first unit / dim / pixel of the chunk
   int wait_act, signal_act, inplace;
-  int split_dst;               // 1: chunk 0 of this (two-chunk, otherwise in-place) layer is written to the z1 buffer instead
-  int src_split;               // > 0: A columns k < src_split are read from the z1 buffer, the rest from `src`
+  int split_dst;               // 1: chunk 0 of this (two-chunk, otherwise in-place) layer fills the z1 buffer completely (KZ_MAX columns)
+                               //    and the later chunks go to the START of the activation buffer, which follows the z1 buffer in
+                               //    shared memory: the output is then ONE contiguous K-major operand that begins at the z1 buffer
+  int src_split;               // 1: this layer reads that contiguous operand (src == 0, k_pad > KZ_MAX)
 };
 struct Program {
   int nlayers, two_layer, cond, learned_prior;
@@ -416,10 +517,10 @@ __device__ __forceinline__ void trace_ev(const EvalArgs& a, int role, int& n, in
 
 __constant__ Program c_prog;
 
-struct __align__(16) SubTile {       // per 128-row sub-tile
+struct __align__(16) SubTile {       // the CTA's 128-row tile
   uint8_t bufZ[BUFZ_BYTES];
   uint8_t bufP[BUFP_BYTES];
-  float sgn[NX_MAX];           // 1 - 2x per pixel of the sub-tile's image (0 for padded columns); 16-byte aligned
+  float sgn[NX_MAX];           // 1 - 2x per pixel of the tile's image (0 for padded columns); 16-byte aligned
   float mu[D_MAX], sd[D_MAX], pmu[D_MAX];
   float psd[D_MAX];            // learned prior: 1/std in FAST mode, std in precise mode
   float red[16];               // [0,4) max, [4,8) sum-exp, [8,16) per-warp constant partials
@@ -428,20 +529,24 @@ struct __align__(16) SubTile {       // per 128-row sub-tile
   //  once the last layer's MMAs have retired: a 4th weight slab fits in the shared memory this frees)
   int label; int pad_[3];
 };
+// Both CTAs of a pair use the SAME layout: cta_group::2 descriptors and multicast commits address the two CTAs'
+// shared memories by one common offset.
 struct __align__(16) SmemLayout {
-  SubTile sub[NSUB];
+  SubTile sub;
   uint8_t ring[NSTAGES][SLAB_BYTES];
-  uint64_t full[NSTAGES], empty[NSTAGES], acc_full[NSUB][2], acc_empty[NSUB][2], act_ready[NSUB];
+  // full / empty: weight ring.  acc_full[b]: accumulator buffer b complete (commit, multicast).  acc_empty[b],
+  // act_ready: arrived on by the epilogue warps of BOTH CTAs, in the leader's shared memory (the MMA issuer waits there)
+  uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready;
   uint32_t tmem_base;
 };
 
-// one persistent CTA per SM: the dynamic shared memory of one CTA is at most 227 KB
+// two resident CTAs per SM: the dynamic shared memory of one CTA is at most ~113 KB
 static_assert(CTAS_PER_SM * (sizeof(SmemLayout) + 1024) <= 228 * 1024, "fused eval kernel: shared memory exceeds the SM");
 
 #define LOG2PI_HALF_F 0.91893853320467274178f
 
-// named barrier of one sub-tile's 8 epilogue warps
-__device__ __forceinline__ void epi_bar_sync(int u) { asm volatile("bar.sync %0, 256;" ::"r"(1 + u) : "memory"); }
+// named barrier of the CTA's 8 epilogue warps
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <bool FAST>
 __device__ __forceinline__ float act_tanh(float v) {
@@ -525,39 +630,50 @@ __device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int
 
 // TRACE: the timeline instrumentation (IWAE_TC_TRACE) is compiled into a separate instantiation
 template <bool FAST, bool TRACE>
-__global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(EvalArgs args) {
+__global__ void
+#if IWAE_PAIR
+__cluster_dims__(2, 1, 1)
+#endif
+__launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(EvalArgs args) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
   const Program& P = c_prog;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t n_macro = (args.n_tiles + NSUB - 1) / NSUB;
-  // Each CTA owns a CONTIGUOUS range of tiles: consecutive tiles then belong to the same image (k/128 tiles per
-  // image), so the per-image constants (x, mu, std: ~3k cycles of global-load latency and two CTA barriers per
-  // tile when reloaded) are fetched once per image instead of once per tile.
+  const uint32_t rank = IWAE_PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs), 1 = peer
+  // Work unit of a CTA group: PAIR consecutive tiles (one per CTA).  Each group owns a CONTIGUOUS range of units:
+  // consecutive tiles then belong to the same image (k/128 tiles per image), so the per-image constants (x, mu, std:
+  // ~3k cycles of global-load latency and two CTA barriers per tile when reloaded) are fetched once per image.
   // (tile indices fit 32 bits: n_tiles < 2^31 is checked on the host)
-  const uint32_t per_cta = ((uint32_t)n_macro + gridDim.x - 1u) / gridDim.x;
-  const uint32_t mt_begin = min(blockIdx.x * per_cta, (uint32_t)n_macro);
-  const uint32_t mt_end = min(mt_begin + per_cta, (uint32_t)n_macro);
+  const uint32_t n_units = (uint32_t)((args.n_tiles + PAIR - 1) / PAIR);
+  const uint32_t n_groups = gridDim.x / PAIR, group = blockIdx.x / PAIR;
+  const uint32_t per_group = (n_units + n_groups - 1u) / n_groups;
+  const uint32_t mt_begin = min(group * per_group, n_units);
+  const uint32_t mt_end = min(mt_begin + per_group, n_units);
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
-    for (int u = 0; u < NSUB; ++u) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[u][i], 1); mbar_init(&S.acc_empty[u][i], 8); }
-      mbar_init(&S.act_ready[u], 8);
+    for (int i = 0; i < NSTAGES; ++i) {
+      // the leader's MMA thread must see BOTH halves of a slab: its own producer's expect_tx + the peer's relay
+      mbar_init(&S.full[i], (IWAE_PAIR && rank == 0) ? 2 : 1);
+      mbar_init(&S.empty[i], 1);
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], NUM_EPI_WARPS * PAIR); }
+    mbar_init(&S.act_ready, NUM_EPI_WARPS * PAIR);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(&S.tmem_base, TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc_cg(&S.tmem_base, TMEM_COLS); tmem_relinquish_cg(); }
   tc_fence_before();
   __syncthreads();
+#if IWAE_PAIR
+  cluster_sync_all();           // the peer's mbarriers must be initialised before anything arrives on them remotely
+#endif
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
 
   if (warp == 0) {
     // ===================== weight producer: one elected thread =====================
-    // One pass over the packed weights per tile (every slab is used by the MMAs of all NSUB sub-tiles); the ring
-    // keeps NSTAGES slabs in flight ahead of the MMA issuer.  Like the MMA role below, the whole role runs inside
-    // a single elected region (no per-slab elect / reconverge).
+    // One pass over the packed weights per tile; this CTA copies ITS share (N / PAIR columns) of every slab.  The
+    // ring keeps NSTAGES slabs in flight ahead of the MMA issuer.  Like the MMA role below, the whole role runs
+    // inside a single elected region (no per-slab elect / reconverge).
     if (elect_one_sync()) {
       uint32_t stage = 0, phase = 0;
       for (uint32_t mt = mt_begin; mt < mt_end; ++mt) {
@@ -567,11 +683,11 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t cn = (uint32_t)P.L[l].chunk_n[c];
             for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
-              const uint32_t bytes = cn * (uint32_t)min(SLAB_K, k_pad - k0) * 2u;
+              const uint32_t share = (cn / PAIR) * (uint32_t)min(SLAB_K, k_pad - k0) * 2u;   // bytes of one CTA's share
               mbar_wait(&S.empty[stage], phase ^ 1, 100, IWAE_PRODUCER_SLEEP);
-              mbar_expect_tx(&S.full[stage], bytes);
-              bulk_g2s(S.ring[stage], src, bytes, &S.full[stage]);
-              src += bytes;
+              mbar_expect_tx(&S.full[stage], share);
+              bulk_g2s(S.ring[stage], src + rank * share, share, &S.full[stage]);
+              src += share * PAIR;
               if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -579,91 +695,82 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer: ONE elected thread runs the whole role =====================
-    // Per slab of two MMAs the issuing thread executes a dependent chain of ~40-65 instructions (barrier
-    // try-wait, descriptor arithmetic, R2UR moves into the uniform registers tcgen05.mma reads, commit): with an
-    // elect / reconverge / __syncwarp per slab that chain took ~400 cycles per slab - 200 per MMA against the 56
-    // the tensor pipe needs (scripts/umma_bench3.py isolates it).  Running the role inside a single elected
-    // region removes the per-slab warp-convergence instructions; the barrier waits are done by that one thread.
-    // Two issue orders per layer (NSUB = 2 only; with NSUB = 1 they coincide):
-    //  * layers whose K fits the ring run SUB-TILE-SEQUENTIAL (all MMAs of sub-tile 0, then of sub-tile 1 over
-    //    the same resident slabs), so the epilogue of one overlaps the MMAs of the other;
-    //  * wide layers (K = 208) interleave the sub-tiles per slab so a slab leaves the ring as soon as both used it.
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer CTA: relay "my half of slab s has landed" to the leader =====================
+    // (a bulk copy signals the mbarrier of the CTA it writes to; the leader's full[s] needs the peer's arrival too)
     if (elect_one_sync()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t full0 = map_to_rank(smem_u32(&S.full[0]), 0);
+      for (uint32_t mt = mt_begin; mt < mt_end; ++mt)
+        for (int l = 0; l < P.nlayers; ++l) {
+          const int nslabs = (P.L[l].k_pad + SLAB_K - 1) / SLAB_K * P.L[l].nchunks;
+          for (int i = 0; i < nslabs; ++i) {
+            mbar_wait(&S.full[stage], phase, 150, IWAE_PRODUCER_SLEEP);
+            mbar_arrive_cluster(full0 + stage * 8u);
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    // The whole warp runs the role CONVERGED: control flow, barrier waits and descriptor arithmetic are warp-uniform,
+    // so the compiler keeps them in uniform registers (the operand form tcgen05.mma reads); only the tcgen05
+    // instructions themselves are predicated on the elected lane.  (Round 1 ran the role inside one elected thread:
+    // every MMA then cost ~20 instructions of a dependent chain incl. 4 R2UR moves, ~130 cycles per MMA against the
+    // 56 the tensor pipe needs; with an elect / reconverge per slab it was ~200, scripts/umma_bench3.py.)
+    if (elect_one_sync()) {
+    const uint32_t issue = 1u;
     uint32_t stage = 0, phase = 0, cc = 0;
-    uint32_t act_phase[NSUB] = {};
-    uint32_t empty_bits = 0;     // phase bit of acc_empty[u][buf] at bit u*2+buf (a register, not a dynamically indexed array)
+    uint32_t act_phase = 0;
+    uint32_t empty_bits = 0;     // phase bit of acc_empty[buf] at bit buf (a register, not a dynamically indexed array)
     const uint32_t ring0 = smem_u32(S.ring[0]);
-    const uint32_t z0 = smem_u32(S.sub[0].bufZ), p0 = smem_u32(S.sub[0].bufP);
-    const uint32_t sub_stride16 = (uint32_t)sizeof(SubTile) >> 4;
+    const uint32_t z0 = smem_u32(S.sub.bufZ), p0 = smem_u32(S.sub.bufP);
     int tn = 0, tl = 0;
-
-    // MMAs of one slab for sub-tile u; descriptors: only the 14-bit start-address field changes between MMAs
-    auto issue_slab = [&](int u, uint32_t st, uint32_t a_base0, int split, int k0, int k_pad, uint32_t n, uint32_t idesc,
-                          uint32_t d_tmem, bool release) {
-      const uint64_t bd0 = make_smem_desc(ring0 + st * SLAB_BYTES, n * 16u, 128);
-      // A columns below `split` live in the z1 buffer (see build_program: split destination of the layer before)
-      const uint32_t a0 = (k0 < split ? z0 : a_base0) + ((uint32_t)k0 >> 3) * (TILE_M * 16);
-      const uint32_t a1 = (k0 + 16 < split ? z0 : a_base0) + ((uint32_t)(k0 + 16) >> 3) * (TILE_M * 16);
-      const uint64_t usub = (uint64_t)((uint32_t)u * sub_stride16);
-      static_assert(SLAB_K == 32, "two MMAs per slab");
-      umma_f16(d_tmem, make_smem_desc(a0, TILE_M * 16, 128) + usub, bd0, idesc, k0 != 0);
-      if (k_pad - k0 > 16) umma_f16(d_tmem, make_smem_desc(a1, TILE_M * 16, 128) + usub, bd0 + (uint64_t)(2u * n), idesc, 1u);
-      if (release) umma_commit(&S.empty[st]);     // slab consumed when these MMAs retire
-    };
 
     for (uint32_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
       for (int l = 0; l < P.nlayers; ++l) {
-        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act, split = P.L[l].src_split;
+        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act;
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
-        const int nslabs = (k_pad + SLAB_K - 1) / SLAB_K;
-        const bool sequential = NSUB > 1 && nslabs <= 4;
         trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 0);
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = cc & 1;
           const uint32_t n = (uint32_t)P.L[l].chunk_n[c];
-          const uint32_t idesc = make_idesc(n);
-          if (sequential) {
-            uint32_t st_end = stage, ph_end = phase;
-#pragma unroll
-            for (int u = 0; u < NSUB; ++u) {
-              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; }
-              mbar_wait(&S.acc_empty[u][buf], ((empty_bits >> (u * 2 + buf)) & 1u) ^ 1u, 201);
-              empty_bits ^= 1u << (u * 2 + buf);
-              tc_fence_after();
-              trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2 + 5 * u);
-              uint32_t st = stage, ph = phase;
-              for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
-                if (u == 0) mbar_wait(&S.full[st], ph, 202);
-                issue_slab(u, st, a_base0, split, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
-                if (++st == NSTAGES) { st = 0; ph ^= 1; }
-              }
-              umma_commit(&S.acc_full[u][buf]);
-              trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3 + 5 * u);
-              st_end = st; ph_end = ph;
-            }
-            stage = st_end; phase = ph_end;
-          } else {
-#pragma unroll
-            for (int u = 0; u < NSUB; ++u) {
-              if (c == 0 && wait_act) { mbar_wait(&S.act_ready[u], act_phase[u], 200); act_phase[u] ^= 1; trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 1); }
-              mbar_wait(&S.acc_empty[u][buf], ((empty_bits >> (u * 2 + buf)) & 1u) ^ 1u, 201);
-              empty_bits ^= 1u << (u * 2 + buf);
-            }
-            tc_fence_after();
-            trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
-            for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
-              mbar_wait(&S.full[stage], phase, 202);
-#pragma unroll
-              for (int u = 0; u < NSUB; ++u)
-                issue_slab(u, stage, a_base0, split, k0, k_pad, n, idesc, tmem_base + (uint32_t)(u * 2 + buf) * 128u, u == NSUB - 1);
-              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
-            }
-#pragma unroll
-            for (int u = 0; u < NSUB; ++u) umma_commit(&S.acc_full[u][buf]);
-            trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
+          const uint32_t idesc = make_idesc_cg(n);
+          if (wait_act && c == 0) {
+            mbar_wait_pair(&S.act_ready, act_phase, 200); act_phase ^= 1;
+            trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 1);
           }
+          // Every epilogue warp signals act_ready only AFTER it has drained (and signalled acc_empty for) all chunks of
+          // the layer before: once act_ready has completed, both accumulator buffers are known to be free, so the first
+          // two chunks of such a layer skip the acc_empty wait (a try_wait on a completed barrier still costs ~100
+          // cycles of the issuing warp's dependent chain); the phase bookkeeping advances either way.
+          if (!(wait_act && c < 2)) mbar_wait_pair(&S.acc_empty[buf], ((empty_bits >> buf) & 1u) ^ 1u, 201);
+          empty_bits ^= 1u << buf;
+          tc_fence_after();
+          trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
+          const uint32_t d_tmem = tmem_base + buf * 128u;
+          const uint32_t n_share = n / PAIR;               // columns of this CTA's share of B; K groups of 8 rows are n_share*16 bytes apart
+          // descriptors: only the 14-bit start-address field (16-byte units) changes between MMAs
+          uint64_t ad = make_smem_desc(a_base0, TILE_M * 16, 128);
+          for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
+            mbar_wait_pair(&S.full[stage], phase, 202);
+            tc_fence_after();
+            uint64_t bd = make_smem_desc(ring0 + stage * SLAB_BYTES, n_share * 16u, 128);
+            const int ksteps = min(SLAB_K, k_pad - k0) >> 4;
+#pragma unroll
+            for (int j = 0; j < SLAB_K / 16; ++j) {
+              if (j < ksteps) {
+                umma_f16_cg_pred(d_tmem, ad, bd, idesc, (k0 | j) != 0, issue);
+                ad += 2u * TILE_M;            // 16 K columns = two 8-column groups of TILE_M*16 bytes
+                bd += 2u * n_share;
+              }
+            }
+            umma_commit_cg_pred(&S.empty[stage], issue);     // slab consumed (in both CTAs) when these MMAs retire
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_cg_pred(&S.acc_full[buf], issue);
+          trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 3);
           ++cc;
         }
       }
@@ -672,21 +779,25 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
-    // Sixteen warps: eight per 128-row sub-tile.  Within a sub-tile, warps e and e+4 share one TMEM
-    // lane quarter (one row per lane) and split the COLUMNS of every accumulator chunk between them
-    // (alternating 16-column groups).  Every log-density term is a sum over columns, so each thread
-    // keeps one partial log-weight; the two halves of a row are added through shared memory at the
+    // Eight warps.  Warps e and e+4 share one TMEM lane quarter (one row per lane) and split the COLUMNS of every
+    // accumulator chunk between them (alternating 16-column groups).  Every log-density term is a sum over columns,
+    // so each thread keeps one partial log-weight; the two halves of a row are added through shared memory at the
     // end of the tile.
-    const int e_warp = warp - 2;             // 0..15
-    const int u = (NSUB == 1) ? 0 : (e_warp >> 3);      // sub-tile
+    const int e_warp = warp - 2;             // 0..7
     const int half = (e_warp >> 2) & 1;      // which half of the column groups this warp takes
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int et = (e_warp & 7) * 32 + lane; // 0..255 among the sub-tile's epilogue threads
-    SubTile& T = S.sub[u];
+    const int et = e_warp * 32 + lane;       // 0..255 among the epilogue threads
+    SubTile& T = S.sub;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t full_bits = 0;      // phase bit of acc_full[u][buf] at bit buf
+    uint32_t full_bits = 0;      // phase bit of acc_full[buf] at bit buf
     uint32_t cc = 0;
+    // the barriers the MMA issuer waits on live in the leader CTA
+#if IWAE_PAIR
+    const uint32_t act_ready_l = map_to_rank(smem_u32(&S.act_ready), 0), acc_empty_l = map_to_rank(smem_u32(&S.acc_empty[0]), 0);
+#else
+    const uint32_t act_ready_l = smem_u32(&S.act_ready), acc_empty_l = smem_u32(&S.acc_empty[0]);
+#endif
     const int d1 = P.d1, nx = P.nx;
     const int nx_pad = (nx + 15) & ~15;
     const int d1_full = d1 & ~7;             // dims covered by complete 8-wide groups
@@ -697,8 +808,8 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
     for (uint32_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
       trace_ev<TRACE>(args, trole, tn, tl * 10000 + 9000);
       // (tile indices fit 32 bits: n_tiles < 2^31 is checked on the host; 32-bit division is much cheaper)
-      uint32_t tile = mt * NSUB + u;
-      const bool tile_ok = (NSUB == 1) || tile < (uint32_t)args.n_tiles;       // the last macro-tile may be half empty
+      uint32_t tile = mt * PAIR + rank;
+      const bool tile_ok = tile < (uint32_t)args.n_tiles;       // the last unit of a pair may be half empty
       if (!tile_ok) tile = (uint32_t)args.n_tiles - 1u;
       const uint32_t img32 = tile / (uint32_t)args.tiles_per_img;
       const int64_t img = img32;
@@ -709,7 +820,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       // ---- per-image constants into smem (only when the image changes)
       if (img32 != prev_img) {
       prev_img = img32;
-      epi_bar_sync(u);
+      epi_bar_sync();
       for (int j = et; j < nx_pad; j += 256)
         T.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
       float csum = 0.f;
@@ -735,7 +846,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
         if (lane == 0) T.red[8 + (e_warp & 7)] = csum;
       }
       if (et == 0 && P.cond) T.label = (int)(unsigned char)(int)__ldg(args.y + img);
-      epi_bar_sync(u);
+      epi_bar_sync();
       }
       trace_ev<TRACE>(args, trole, tn, tl * 10000 + 9050);
 
@@ -831,7 +942,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.act_ready[u]);
+      if (lane == 0) mbar_arrive_cluster(act_ready_l);
       trace_ev<TRACE>(args, trole, tn, tl * 10000 + 9100);
 
       // ---- layers
@@ -846,26 +957,28 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           // all chunks' MMAs must have retired before the input buffer is overwritten
           for (int c = 0; c < nchunks; ++c) {
             const uint32_t b = (cc + c) & 1;
-            mbar_wait(&S.acc_full[u][b], (full_bits >> b) & 1u, 300);
+            mbar_wait(&S.acc_full[b], (full_bits >> b) & 1u, 300);
             full_bits ^= 1u << b;
           }
         }
         for (int c = 0; c < nchunks; ++c) {
           const uint32_t buf = cc & 1;
           if (!wait_all) {
-            mbar_wait(&S.acc_full[u][buf], (full_bits >> buf) & 1u, 301);
+            mbar_wait(&S.acc_full[buf], (full_bits >> buf) & 1u, 301);
             full_bits ^= 1u << buf;
           }
           tc_fence_after();
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 5);
-          const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(u * 2 + buf) * 128u;
+          const uint32_t tbase = tmem_base + lane_addr + buf * 128u;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
           const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
 
           if (kind == EPI_TANH) {
             // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
             // bias 30 (tanh(30) == 1.0f): no per-element special cases
-            uint8_t* dstc = (split_dst && c == 0) ? T.bufZ : dst;
+            // split destination: unit j of the layer lands at K column j of the contiguous operand that starts at the z1
+            // buffer (the activation buffer follows it in shared memory; bufZ holds exactly KZ_MAX columns)
+            uint8_t* dstc = split_dst ? T.bufZ : dst;
             for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
               float v[16];
 #pragma unroll
@@ -1050,7 +1163,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&S.acc_empty[u][buf]);
+          if (lane == 0) mbar_arrive_cluster(acc_empty_l + buf * 8u);
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 6);
           ++cc;
         }
@@ -1059,7 +1172,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
           fence_proxy_async();
 #endif
           __syncwarp();
-          if (lane == 0) mbar_arrive(&S.act_ready[u]);
+          if (lane == 0) mbar_arrive_cluster(act_ready_l);
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + 7);
         }
       }
@@ -1068,7 +1181,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
       // ---- combine the two column halves of each row, then the tile's (max, sum exp) partial
       float* lwpart = reinterpret_cast<float*>(T.bufP);
       if (half == 1) lwpart[row] = lw;
-      epi_bar_sync(u);
+      epi_bar_sync();
       if (half == 0) {
         lw += lwpart[row];
         if (FAST) {
@@ -1083,7 +1196,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (lane == 0 && half == 0) T.red[q] = mx;
-      epi_bar_sync(u);
+      epi_bar_sync();
       mx = fmaxf(fmaxf(T.red[0], T.red[1]), fmaxf(T.red[2], T.red[3]));
       float se = (half == 0 && valid) ? expf(lw - mx) : 0.f;
       float sl = (half == 0 && valid) ? lw : 0.f;          // for vae_elbo = mean_k log_w (iwae1.py:119)
@@ -1093,7 +1206,7 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
         sl += __shfl_xor_sync(0xffffffffu, sl, o);
       }
       if (lane == 0 && half == 0) { T.red[4 + q] = se; T.red_lw[q] = sl; }
-      epi_bar_sync(u);
+      epi_bar_sync();
       if (et == 0 && tile_ok) {
         args.partial[tile] = make_float2(mx, T.red[4] + T.red[5] + T.red[6] + T.red[7]);
         if (args.partial_lw) args.partial_lw[tile] = T.red_lw[0] + T.red_lw[1] + T.red_lw[2] + T.red_lw[3];
@@ -1103,7 +1216,10 @@ __global__ void __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+#if IWAE_PAIR
+  cluster_sync_all();           // neither CTA may exit (or free TMEM) while its peer can still arrive on its barriers
+#endif
+  if (warp == 1) tmem_dealloc_cg(tmem_base, TMEM_COLS);
 }
 
 // per image: logmeanexp over its tiles' partials (utils.logmeanexp, utils.py:6-8)
@@ -1149,8 +1265,10 @@ __global__ void pack_layer_kernel(PackLayer pl, __half* __restrict__ out) {
       // i enumerates (k, n); locate the slab and the position inside it
       const int k = i / cn, n = i % cn;
       const int slab = k / SLAB_K, kin = k % SLAB_K;
+      const int rows = min(SLAB_K, pl.k_pad - slab * SLAB_K);                     // K rows of this slab
+      const int cs = cn / PAIR, rk = n / cs, nn = n % cs;                         // CTA `rk` of the pair holds columns [rk*cs, rk*cs + cs)
       const int64_t slab_base = pl.chunk_base[c] + (int64_t)slab * cn * SLAB_K;   // full slabs precede
-      const int64_t pos = slab_base + ((int64_t)(kin >> 3) * cn + n) * 8 + (kin & 7);
+      const int64_t pos = slab_base + (int64_t)rk * rows * cs + ((int64_t)(kin >> 3) * cs + nn) * 8 + (kin & 7);
       float v = 0.f;
       const float* W = pl.W; const float* b = pl.b; int col = -1;
       if (!pl.gauss) { if (n < cnt) col = off + n; }
@@ -1278,15 +1396,18 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P, bool fast)
   for (int l = 0; l < nl; ++l) pr.L[l].signal_act = (l + 1 < nl) ? pr.L[l + 1].wait_act : 0;
   // The second decoder layer (h1 -> h1 units, two chunks, in place) would have to wait for ALL its MMAs before the
   // first epilogue may overwrite the input.  The z1 buffer is dead once the first decoder layer's MMAs have retired,
-  // so chunk 0 goes there instead and its epilogue overlaps the MMAs of chunk 1; the logit layer then reads its
-  // first chunk_n[0] K-columns from the z1 buffer.
+  // so chunk 0 (exactly KZ_MAX columns) goes there instead and its epilogue overlaps the MMAs of chunk 1; chunk 1 is
+  // written after ALL MMAs of the layer have retired, to the START of the activation buffer.  The activation buffer
+  // follows the z1 buffer in shared memory and a K group of 8 columns is TILE_M*16 bytes in both, so the logit layer
+  // reads ONE contiguous operand that begins at the z1 buffer (no per-MMA address select in the issue loop).
   {
     Layer& D1 = pr.L[nl - 2];
     Layer& BL = pr.L[nl - 1];
-    if (D1.kind == EPI_TANH && D1.inplace && D1.nchunks == 2 && D1.chunk_n[0] <= KZ_MAX && pr.L[nl - 3].src == 0 &&
-        BL.kind == EPI_BERN && D1.chunk_n[0] % 16 == 0) {
+    static_assert(offsetof(SubTile, bufP) == offsetof(SubTile, bufZ) + BUFZ_BYTES, "bufP must follow bufZ");
+    if (D1.kind == EPI_TANH && D1.inplace && D1.nchunks == 2 && D1.chunk_n[0] == KZ_MAX && pr.L[nl - 3].src == 0 &&
+        BL.kind == EPI_BERN) {
       D1.split_dst = 1; D1.inplace = 0;
-      BL.src_split = D1.chunk_n[0];
+      BL.src_split = 1; BL.src = 0;
     }
   }
   // packed offsets
@@ -1390,8 +1511,9 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
     CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tp.attr_set = true;
   }
-  int grid = (int)std::min<int64_t>((a.n_tiles + tc::NSUB - 1) / tc::NSUB, (int64_t)ctx->sm_count * tc::CTAS_PER_SM);
-  if (const char* g = getenv("IWAE_TC_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // diagnostics only
+  // one CTA group (a pair of CTAs on the two SMs of a TPC) per unit of PAIR tiles, at most CTAS_PER_SM CTAs per SM
+  int grid = tc::PAIR * (int)std::min<int64_t>((a.n_tiles + tc::PAIR - 1) / tc::PAIR, (int64_t)ctx->sm_count * tc::CTAS_PER_SM / tc::PAIR);
+  if (const char* g = getenv("IWAE_TC_GRID")) { const int v = atoi(g) / tc::PAIR * tc::PAIR; if (v > 0 && v < grid) grid = v; }   // diagnostics only
   if (!ctx->ev_k0) { CUDA_TRY(cudaEventCreate(&ctx->ev_k0)); CUDA_TRY(cudaEventCreate(&ctx->ev_k1)); }
   CUDA_TRY(cudaEventRecord(ctx->ev_k0, st));
   kern<<<grid, tc::NUM_THREADS, smem, st>>>(a);
