@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libiwae_b200.so")
+# IWAE_B200_LIB: an alternative build of the SAME library (A/B measurements of kernel variants, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("IWAE_B200_LIB") or os.path.join(_HERE, "lib", "libiwae_b200.so")
 
 KIND_IWAE1, KIND_IWAE2, KIND_CIWAE, KIND_CIWAE_STD = 1, 2, 3, 4
 OBJ = {"vae_elbo": 0, "iwae_elbo": 1, "iwae_eq14": 2, "vae_elbo_kl": 3, "dreg": 4}

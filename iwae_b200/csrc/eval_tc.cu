@@ -579,6 +579,24 @@ __device__ __forceinline__ float rcp_approx(float v) { float r; asm("rcp.approx.
 __device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float sin_approx(float v) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float cos_approx(float v) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-4 minimax
+// polynomial for 2^f (max relative error 2.7e-6 incl. fp32 evaluation), exponent inserted with one integer add.  The
+// Bernoulli epilogue evaluates a compile-time share of its exponentials this way: the XU pipe (16 MUFU/clk/SM) is the
+// most contended unit of the kernel while the FMA pipe is under 20 % busy (the FlashAttention-4 trick).
+__device__ __forceinline__ float ex2_poly_neg(float x) {
+  x = fmaxf(x, -125.f);
+  const float r = x + 12582912.f;            // 1.5 * 2^23: the low mantissa bits of r hold round(x)
+  const float f = x - (r - 12582912.f);
+  float p = 0.009570102207362652f;
+  p = fmaf(p, f, 0.05591785907745361f);
+  p = fmaf(p, f, 0.240247443318367f);
+  p = fmaf(p, f, 0.6931217908859253f);
+  p = fmaf(p, f, 0.9999992847442627f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+#ifndef IWAE_EX2_POLY
+#define IWAE_EX2_POLY 0                       // of every 4 groups of 4 pixels, how many use ex2_poly_neg instead of MUFU.EX2
+#endif
 #define LN2_F 0.69314718055994530942f
 #define LOG2E_F 1.44269504088896340736f
 
@@ -1141,8 +1159,13 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(EvalArgs args) {
                   const float l2 = __uint_as_float(r[4 * i4 + 2]), l3 = __uint_as_float(r[4 * i4 + 3]);
                   s0 = fmaf(sg.x, l0, s0); s1 = fmaf(sg.y, l1, s1); s0 = fmaf(sg.z, l2, s0); s1 = fmaf(sg.w, l3, s1);
                   a0 += fabsf(l0); a1 += fabsf(l1); a0 += fabsf(l2); a1 += fabsf(l3);
-                  p0 = fmaf(p0, ex2_approx(-fabsf(l0)), p0); p1 = fmaf(p1, ex2_approx(-fabsf(l1)), p1);
-                  p2 = fmaf(p2, ex2_approx(-fabsf(l2)), p2); p3 = fmaf(p3, ex2_approx(-fabsf(l3)), p3);
+                  if (i4 < 4 - IWAE_EX2_POLY) {
+                    p0 = fmaf(p0, ex2_approx(-fabsf(l0)), p0); p1 = fmaf(p1, ex2_approx(-fabsf(l1)), p1);
+                    p2 = fmaf(p2, ex2_approx(-fabsf(l2)), p2); p3 = fmaf(p3, ex2_approx(-fabsf(l3)), p3);
+                  } else {
+                    p0 = fmaf(p0, ex2_poly_neg(-fabsf(l0)), p0); p1 = fmaf(p1, ex2_poly_neg(-fabsf(l1)), p1);
+                    p2 = fmaf(p2, ex2_poly_neg(-fabsf(l2)), p2); p3 = fmaf(p3, ex2_poly_neg(-fabsf(l3)), p3);
+                  }
                 }
               });
               bern_s += s0 + s1; bern_a += a0 + a1;
