@@ -130,6 +130,13 @@ int iwae_monitor_eval(iwae_ctx* ctx, const float* params, const float* x, const 
                       int32_t k, uint64_t seed, int64_t img_offset, int32_t precision, float* out_iwae,
                       float* out_vae, double* out_sums, void* stream);
 
+/* Declares the CONTENT version of the parameter buffer the caller passes to iwae_llh_eval / iwae_monitor_eval (the
+ * Python shim bumps it in set_weights / load_weights / train_step / Variable.assign, i.e. whenever
+ * model.trainable_weights change, src/iwae1.py:160).  While (pointer, version) stay the same the fused evaluation
+ * reuses its packed fp16 weight image instead of re-packing it on every call.  version 0 (the default) = unknown:
+ * always re-pack. */
+int iwae_set_params_version(iwae_ctx* ctx, uint64_t version);
+
 /* Device time (ms) of the fused tensor-core evaluation kernel in the most recent iwae_llh_eval /
  * iwae_llh_eval_host call with a TC precision on this context (CUDA events recorded around that one
  * launch on the caller's stream); synchronises on the second event.  bench.py's roofline uses it. */
@@ -167,6 +174,30 @@ int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v,
                     int32_t objective, const float* eps1, const float* eps2, uint64_t seed,
                     int64_t img_offset, float lr, float beta1, float beta2, float adam_eps,
                     int64_t t, const iwae_outputs* outs, void* stream);
+
+/* ---- multi-GPU (the reference is single-device: main.py:32) -------------------------------------
+ * One process per GPU.  The library owns an NCCL communicator per context (NCCL is bound at run time with
+ * dlopen("libnccl.so.2"), i.e. the copy PyTorch has already loaded when there is one).
+ *   iwae_comm_unique_id : rank 0 creates the 128-byte ncclUniqueId, the host side broadcasts it (torch.distributed).
+ *   iwae_comm_init      : every rank joins (collective).   iwae_comm_destroy: leave.
+ *   iwae_allreduce_sum_*: in-place sum all-reduce of a device buffer on `stream` (the fp64 LLH sum of the sharded
+ *                         k-sample evaluation, main.py:181). */
+int iwae_comm_unique_id(uint8_t* out128);
+int iwae_comm_init(iwae_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);
+int iwae_comm_destroy(iwae_ctx* ctx);
+int iwae_comm_info(const iwae_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version);
+int iwae_allreduce_sum_f32(iwae_ctx* ctx, float* buf, int64_t n, void* stream);
+int iwae_allreduce_sum_f64(iwae_ctx* ctx, double* buf, int64_t n, void* stream);
+
+/* Data-parallel model.train_step (src/iwae1.py:153-162 / tasks/task02.py:87-101 over image shards): this rank's
+ * B_local images (global indices img_offset .. img_offset + B_local of a batch of B_global; B_local may be 0), local
+ * gradient divided by B_global, ONE ncclAllReduce(sum) of the flat gradient, the same Keras-Adam update on every
+ * rank.  Like iwae_train_step the whole step - including the all-reduce - is captured into a CUDA graph on the second
+ * consecutive call with one signature and replayed afterwards.  `outs` describe the LOCAL shard. */
+int iwae_dp_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x_local,
+                       const float* y_local, int32_t B_local, int32_t B_global, int32_t k, float beta,
+                       int32_t objective, uint64_t seed, int64_t img_offset, float lr, float beta1, float beta2,
+                       float adam_eps, int64_t t, const iwae_outputs* outs, void* stream);
 
 /* The device noise source by itself: eps [k,B,d] for stream_id 1 (first latent) or 2 (second). */
 int iwae_philox_normal(uint64_t seed, int32_t stream_id, int64_t img_offset, int32_t B, int32_t k,

@@ -71,6 +71,15 @@ def _load():
         "iwae_launch_count": (i64, []),
         "iwae_umma_bench": (C.c_int, [i32, i32, i32, vp, vp]),
         "iwae_llh_kernel_ms": (C.c_int, [vp, P(C.c_float)]),
+        "iwae_set_params_version": (C.c_int, [vp, C.c_uint64]),
+        "iwae_comm_unique_id": (C.c_int, [vp]),
+        "iwae_comm_init": (C.c_int, [vp, vp, i32, i32]),
+        "iwae_comm_destroy": (C.c_int, [vp]),
+        "iwae_comm_info": (C.c_int, [vp, P(i32), P(i32), P(i32)]),
+        "iwae_allreduce_sum_f32": (C.c_int, [vp, vp, i64, vp]),
+        "iwae_allreduce_sum_f64": (C.c_int, [vp, vp, i64, vp]),
+        "iwae_dp_train_step": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, u64, i64, f32, f32, f32,
+                                         f32, i64, P(Outputs), vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)      # AttributeError here = the library does not export the header's symbol
@@ -83,7 +92,8 @@ lib = _load()
 EXPORTS = ("iwae_last_error", "iwae_version", "iwae_create", "iwae_destroy", "iwae_param_count",
            "iwae_param_layout", "iwae_layout_for_config", "iwae_forward", "iwae_llh_eval", "iwae_llh_eval_host",
            "iwae_grads", "iwae_adam_step", "iwae_train_step", "iwae_philox_normal", "iwae_decode", "iwae_sir",
-           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_umma_bench", "iwae_monitor_eval",
+           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_set_params_version", "iwae_comm_unique_id", "iwae_comm_init", "iwae_comm_destroy", "iwae_comm_info",
+           "iwae_allreduce_sum_f32", "iwae_allreduce_sum_f64", "iwae_dp_train_step", "iwae_umma_bench", "iwae_monitor_eval",
            "iwae_block_forward")
 
 

@@ -123,6 +123,7 @@ extern "C" int iwae_destroy(iwae_ctx* ctx) {
   if (ctx->stage_x) cudaFree(ctx->stage_x);
   if (ctx->stage_aux) cudaFree(ctx->stage_aux);
   train_graph_release(ctx);
+  comm_release(ctx);
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   delete ctx;
@@ -447,6 +448,12 @@ static int llh_eval_impl(iwae_ctx* ctx, const float* params, const float* x, con
   return 0;
 }
 
+extern "C" int iwae_set_params_version(iwae_ctx* ctx, uint64_t version) {
+  IWAE_REQUIRE(ctx, "iwae_set_params_version: null context");
+  ctx->params_version = version;
+  return 0;
+}
+
 extern "C" int iwae_llh_kernel_ms(iwae_ctx* ctx, float* ms) {
   IWAE_REQUIRE(ctx && ms, "iwae_llh_kernel_ms: null argument");
   IWAE_REQUIRE(ctx->ev_valid, "iwae_llh_kernel_ms: no tensor-core evaluation has run on this context");
@@ -488,7 +495,7 @@ extern "C" int iwae_llh_eval_host(iwae_ctx* ctx, const float* params, const floa
 // row range is split over gridDim.z to fill the SMs.  `grads` points to slice 0 of a zeroed
 // [GRAD_SPLITS][n_params] workspace; grad_reduce / adam_from_partials sum the slices in a fixed order.
 constexpr int GRAD_SPLITS = 8;
-static int g_grad_stride = 0;      // n_params of the model whose backward is running (slice stride)
+static thread_local int g_grad_stride = 0;      // n_params of the model whose backward is running on this host thread (slice stride)
 
 // dW = X^T dY, db = colsum(dY)
 static int dense_bwd_w(const DenseP& L, const float* X, int64_t ldx, int64_t M, const float* dY, float* grads,
@@ -708,18 +715,33 @@ static void train_graph_release(iwae_ctx* ctx) {
   if (ctx->gstream) { cudaStreamDestroy(ctx->gstream); ctx->gstream = nullptr; }
 }
 
+// B_norm: the batch size the objective's mean_b divides by (B, or the GLOBAL batch of a data-parallel step).
+// dp: data-parallel step - local gradient (already divided by the global batch) -> ONE NCCL sum all-reduce on the
+// step's own stream (so it is captured inside the step's CUDA graph) -> the same fused reduce + Keras-Adam kernel.
 static int train_step_eager(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x, const float* y,
                             int B, int k, float beta, int objective, const float* eps1, const float* eps2, uint64_t seed,
                             int64_t img_offset, float lr, float beta1, float beta2, float adam_eps, int64_t t,
-                            const iwae_outputs* outs, cudaStream_t st) {
+                            const iwae_outputs* outs, cudaStream_t st, int B_norm = 0, bool dp = false) {
   ctx->arena.reset();
-  AdamArgs ad = {params, adam_m, adam_v, lr, beta1, beta2, adam_eps, t};
-  return grads_internal(ctx, params, x, y, B, k, beta, objective, B, eps1, eps2, seed, img_offset, nullptr, outs, st, &ad);
+  if (!dp) {
+    AdamArgs ad = {params, adam_m, adam_v, lr, beta1, beta2, adam_eps, t};
+    return grads_internal(ctx, params, x, y, B, k, beta, objective, B_norm > 0 ? B_norm : B, eps1, eps2, seed, img_offset,
+                          nullptr, outs, st, &ad);
+  }
+  float* g = comm_grad_buffer(ctx);
+  IWAE_REQUIRE(g, "iwae_dp_train_step: no communicator (iwae_comm_init)");
+  const int64_t n = ctx->model.n_params;
+  if (B > 0)
+    IWAE_TRY(grads_internal(ctx, params, x, y, B, k, beta, objective, B_norm, eps1, eps2, seed, img_offset, g, outs, st));
+  else
+    CUDA_TRY(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)n, st));      // a rank without images still joins the all-reduce
+  IWAE_TRY(comm_allreduce_f32(ctx, g, n, st));
+  return adam_from_partials(params, g, 1, adam_m, adam_v, n, lr, beta1, beta2, adam_eps, t, st);
 }
 
 // capture the step for the signature in g.cand; returns 0 and g.valid on success
 static int train_graph_capture(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, bool has_y, int B, int k,
-                               float beta, int objective, const iwae_outputs* outs) {
+                               float beta, int objective, const iwae_outputs* outs, int B_norm, bool dp) {
   TrainGraph& g = ctx->tg;
   const iwae_config& c = ctx->model.cfg;
   if (!ctx->gstream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking));
@@ -749,7 +771,7 @@ static int train_graph_capture(iwae_ctx* ctx, float* params, float* adam_m, floa
   CUDA_TRY(cudaStreamBeginCapture(ctx->gstream, cudaStreamCaptureModeThreadLocal));
   g_step_dyn = ctx->dyn_dev;
   const int rc = train_step_eager(ctx, params, adam_m, adam_v, g.x_buf, has_y ? g.y_buf : nullptr, B, k, beta, objective,
-                                  nullptr, nullptr, 0, 0, 0.f, 0.f, 0.f, 0.f, 1, &g.shadow, ctx->gstream);
+                                  nullptr, nullptr, 0, 0, 0.f, 0.f, 0.f, 0.f, 1, &g.shadow, ctx->gstream, B_norm, dp);
   g_step_dyn = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(ctx->gstream, &graph);
   g.launches = g_iwae_launches - launches0;
@@ -758,7 +780,7 @@ static int train_graph_capture(iwae_ctx* ctx, float* params, float* adam_m, floa
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     g.disabled = true;
-    return rc != 0 ? rc : 0;       // the caller falls back to the eager path
+    return 0;       // not an error: the caller sees !g.valid and runs this (and every later) step eagerly
   }
   const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -768,10 +790,10 @@ static int train_graph_capture(iwae_ctx* ctx, float* params, float* adam_m, floa
   return 0;
 }
 
-extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x,
-                               const float* y, int32_t B, int32_t k, float beta, int32_t objective, const float* eps1,
-                               const float* eps2, uint64_t seed, int64_t img_offset, float lr, float beta1, float beta2,
-                               float adam_eps, int64_t t, const iwae_outputs* outs, void* stream) {
+static int train_step_impl(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x,
+                           const float* y, int32_t B, int32_t k, float beta, int32_t objective, const float* eps1,
+                           const float* eps2, uint64_t seed, int64_t img_offset, float lr, float beta1, float beta2,
+                           float adam_eps, int64_t t, const iwae_outputs* outs, void* stream, int B_norm, bool dp) {
   IWAE_REQUIRE(ctx && params && adam_m && adam_v, "iwae_train_step: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   IWAE_REQUIRE(t >= 1, "iwae_train_step: t is the step count after increment (>= 1)");
@@ -780,7 +802,7 @@ extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, floa
   const bool graphable = !no_graph && !g.disabled && !eps1 && !eps2 && x && B > 0 && k > 0;
   if (!graphable)
     return train_step_eager(ctx, params, adam_m, adam_v, x, y, B, k, beta, objective, eps1, eps2, seed, img_offset, lr,
-                            beta1, beta2, adam_eps, t, outs, st);
+                            beta1, beta2, adam_eps, t, outs, st, B_norm, dp);
 
   // signature: everything the captured kernels hold by value or by address
   unsigned long long key[12] = {};
@@ -793,17 +815,18 @@ extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, floa
   unsigned long long mask = 0;
   for (int f = 0; f < N_OUT_FIELDS; ++f) if (outs && user[f]) mask |= 1ull << f;
   key[8] = mask;
+  key[9] = (unsigned long long)(unsigned)B_norm; key[10] = dp ? 1 : 0;
 
   if (!(g.valid && memcmp(key, g.key, sizeof(key)) == 0)) {
     if (g.have_cand && memcmp(key, g.cand, sizeof(key)) == 0) {
       // second consecutive call with this signature: capture (the eager call before it sized the arena)
-      IWAE_TRY(train_graph_capture(ctx, params, adam_m, adam_v, y != nullptr, B, k, beta, objective, outs));
+      IWAE_TRY(train_graph_capture(ctx, params, adam_m, adam_v, y != nullptr, B, k, beta, objective, outs, B_norm, dp));
     } else {
       memcpy(g.cand, key, sizeof(key)); g.have_cand = true;
     }
     if (!(g.valid && memcmp(key, g.key, sizeof(key)) == 0))
       return train_step_eager(ctx, params, adam_m, adam_v, x, y, B, k, beta, objective, eps1, eps2, seed, img_offset, lr,
-                              beta1, beta2, adam_eps, t, outs, st);
+                              beta1, beta2, adam_eps, t, outs, st, B_norm, dp);
   }
 
   // replay: order the library stream after the caller's, refresh inputs and scalars, launch, hand the outputs back
@@ -828,6 +851,25 @@ extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, floa
   CUDA_TRY(cudaEventRecord(ctx->ev_gout, gs));
   CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_gout, 0));
   return 0;
+}
+
+extern "C" int iwae_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x,
+                               const float* y, int32_t B, int32_t k, float beta, int32_t objective, const float* eps1,
+                               const float* eps2, uint64_t seed, int64_t img_offset, float lr, float beta1, float beta2,
+                               float adam_eps, int64_t t, const iwae_outputs* outs, void* stream) {
+  return train_step_impl(ctx, params, adam_m, adam_v, x, y, B, k, beta, objective, eps1, eps2, seed, img_offset, lr, beta1,
+                         beta2, adam_eps, t, outs, stream, 0, false);
+}
+
+extern "C" int iwae_dp_train_step(iwae_ctx* ctx, float* params, float* adam_m, float* adam_v, const float* x_local,
+                                  const float* y_local, int32_t B_local, int32_t B_global, int32_t k, float beta,
+                                  int32_t objective, uint64_t seed, int64_t img_offset, float lr, float beta1, float beta2,
+                                  float adam_eps, int64_t t, const iwae_outputs* outs, void* stream) {
+  IWAE_REQUIRE(ctx && comm_grad_buffer(ctx), "iwae_dp_train_step: no communicator (iwae_comm_init)");
+  IWAE_REQUIRE(B_local >= 0 && B_global >= B_local && B_global > 0, "iwae_dp_train_step: bad batch sizes %d / %d", B_local,
+               B_global);
+  return train_step_impl(ctx, params, adam_m, adam_v, x_local, y_local, B_local, k, beta, objective, nullptr, nullptr, seed,
+                         img_offset, lr, beta1, beta2, adam_eps, t, outs, stream, B_global, true);
 }
 
 extern "C" int iwae_philox_normal(uint64_t seed, int32_t stream_id, int64_t img_offset, int32_t B, int32_t k, int32_t d,

@@ -75,6 +75,7 @@ struct Arena {
 };
 
 struct TcPack;   // packed fp16 weights + program for the fused tcgen05 evaluation (eval_tc.cu)
+struct DpComm;   // library-owned NCCL communicator + reduced-gradient buffer (comm.cu)
 
 // Per-step scalars of a train step, device-resident so that a captured CUDA graph of the step can be replayed with
 // new values (kernels read them through g_step_dyn when it is non-null, else from their by-value arguments).
@@ -83,7 +84,7 @@ struct StepDyn {
   long long img_offset;
   float lr_t, b1, b2, eps;
 };
-extern const StepDyn* g_step_dyn;
+extern thread_local const StepDyn* g_step_dyn;
 
 // One cached CUDA graph of iwae_train_step (see abi.cu): signature it was captured for, library-owned input and
 // output buffers (the caller's pointers change from call to call), and the captured launch count.
@@ -106,6 +107,8 @@ struct iwae_ctx {
   int device = 0;
   int sm_count = 148;
   TcPack* tc = nullptr;
+  DpComm* dp = nullptr;
+  uint64_t params_version = 0;     // iwae_set_params_version: content version of the caller's parameter buffer (0 = unknown)
   // persistent device staging for iwae_llh_eval / iwae_llh_eval_host (outlives arena resets)
   float* per_buf = nullptr; size_t per_cap = 0;       // per-example results
   float* stage_x = nullptr; size_t stage_x_cap = 0;   // x (and y) copied from the host
@@ -236,5 +239,10 @@ int splitk_bias_act(const float* partial, int splits, int M, int N, const float*
 int splitk_mul_h(const float* partial, int splits, int M, int N, const float* H, int64_t ld_h, int accumulate, float* dX,
                  int64_t ld_dx, cudaStream_t st);
 void tc_release(iwae_ctx* ctx);
+// ---- communicator (comm.cu) ----
+int comm_allreduce_f32(iwae_ctx* ctx, float* buf, int64_t n, cudaStream_t st);
+float* comm_grad_buffer(iwae_ctx* ctx);
+int comm_world(const iwae_ctx* ctx);
+void comm_release(iwae_ctx* ctx);
 int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream_t st);
 int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st);

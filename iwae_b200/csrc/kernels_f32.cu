@@ -984,7 +984,7 @@ int splitk_mul_h(const float* partial, int splits, int M, int N, const float* H,
 }
 
 // ---- train-step graph replay helpers ----
-const StepDyn* g_step_dyn = nullptr;
+thread_local const StepDyn* g_step_dyn = nullptr;   // per host thread: one context per thread may capture a train-step graph
 
 __global__ void set_step_dyn_kernel(StepDyn* d, StepDyn v) { *d = v; }
 int set_step_dyn(StepDyn* dev, const StepDyn& v, cudaStream_t st) {

@@ -70,16 +70,58 @@ def model_llh_sharded(model, x_all, n_samples: int = 5000, y_all=None, precision
     return llh_eval_sharded(local_eval, n, gather=gather)
 
 
+def init_comm(model) -> Tuple[int, int]:
+    """Give `model`'s context a library-owned NCCL communicator spanning the torch.distributed world
+    (iwae_comm_unique_id on rank 0 -> broadcast of the 128-byte id -> iwae_comm_init on every rank).
+    `dp_train_step` then runs the whole data-parallel step - gradient all-reduce included - inside the library
+    (one CUDA graph per step).  Returns (rank, world)."""
+    import ctypes as C
+    from ._abi import check, lib
+    rank, world = _world()
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        check(lib.iwae_comm_unique_id(buf), "iwae_comm_unique_id")
+    box = [bytes(buf)]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+    with torch.cuda.device(model.device):
+        check(lib.iwae_comm_init(model._ctx, ident, rank, world), "iwae_comm_init")
+    model._comm = (rank, world)
+    return rank, world
+
+
 def dp_train_step(model, x, n_samples: int, beta: float, optimizer, objective: str = "iwae_elbo", y=None,
                   seed: Optional[int] = None):
     """Data-parallel train step: local gradients of this rank's image shard (already divided by the
     GLOBAL batch size), one SUM all-reduce of the flat gradient, replicated Adam update.
-    Every rank passes the same global batch x [B,784]."""
+    Every rank passes the same global batch x [B,784].
+
+    With a library communicator (`init_comm(model)`) the step is ONE call into the library: forward, backward,
+    ncclAllReduce and Keras-Adam on one stream, replayed from a CUDA graph (iwae_dp_train_step); returns None.
+    Without one (the gloo CPU tests of the host logic, or no NCCL) it falls back to iwae_grads ->
+    torch.distributed.all_reduce -> iwae_adam_step and returns the reduced gradient."""
     rank, world = _world()
     B = x.shape[0]
     a, b = shard_range(B, rank, world)
     if seed is None:
         seed = model._next_seed()
+    if getattr(model, "_comm", None) == (rank, world):
+        import ctypes as C
+        from ._abi import OBJ, check, lib
+        xs, ys = model._check_x(x[a:b], None if y is None else y[a:b]) if b > a else (None, None)
+        m, v = optimizer._state_for(model)
+        stream = torch.cuda.current_stream().cuda_stream
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        with torch.cuda.device(model.device):
+            check(lib.iwae_dp_train_step(model._ctx, ptr(model.params), ptr(m), ptr(v), ptr(xs), ptr(ys), b - a, B,
+                                         int(n_samples), float(beta), OBJ[objective], int(seed), a,
+                                         float(optimizer.learning_rate.value), optimizer.beta_1, optimizer.beta_2,
+                                         optimizer.epsilon, optimizer.iterations + 1, None, stream),
+                  "iwae_dp_train_step")
+        optimizer.iterations += 1
+        model.mark_params_modified()
+        return None
     if b > a:
         ys = None if y is None else y[a:b]
         g = model.grads(x[a:b], n_samples, beta, objective, seed=seed, y=ys, B_norm=B, img_offset=a)
@@ -88,6 +130,7 @@ def dp_train_step(model, x, n_samples: int, beta: float, optimizer, objective: s
     if world > 1:
         dist.all_reduce(g, op=dist.ReduceOp.SUM)
     optimizer.apply_gradients([(g, _FlatVar(model))])
+    model.mark_params_modified()
     return g
 
 

@@ -226,6 +226,7 @@ class IWAE:
             self.trainable_weights.append(Variable(name, view, off))
         self._seed = int(seed)
         self._calls = 0
+        self._native_writes = 0        # bumped whenever the library writes self.params through a raw pointer
         self._build_submodels()
         self.init_weights(np.random.RandomState(seed), out_bias)
 
@@ -291,6 +292,18 @@ class IWAE:
             self.set_weights({k: f[k] for k in f.files})
 
     # ---- plumbing -------------------------------------------------------------------------------
+    def mark_params_modified(self):
+        """Tell the model that `self.params` was written through its raw pointer (the library's Adam kernels do that;
+        torch-side writes are tracked by the tensor's own version counter)."""
+        self._native_writes += 1
+
+    def _declare_params_version(self):
+        """iwae_set_params_version: lets the fused evaluation reuse its packed fp16 weight image while the parameters
+        are unchanged.  Version = torch's in-place version counter of the flat buffer (every torch write to it or to a
+        Variable view bumps it) combined with the count of native writes."""
+        ver = (((self.params._version + 1) & 0xFFFFFFFF) << 32) | (self._native_writes & 0xFFFFFFFF)
+        check(lib.iwae_set_params_version(self._ctx, C.c_uint64(ver)), "iwae_set_params_version")
+
     def _dev(self, a, dtype=_F32) -> Optional[torch.Tensor]:
         if a is None:
             return None
@@ -478,13 +491,14 @@ class IWAE:
         o, bufs = self._outputs(B, k, want or self._WANT)
         seed = self._next_seed(seed)
         m, v = optimizer._state_for(self)
-        optimizer.iterations += 1
         with torch.cuda.device(self.device):
             check(lib.iwae_train_step(self._ctx, _ptr(self.params), _ptr(m), _ptr(v), _ptr(x), _ptr(y), B, k,
                                       float(beta), objective_id, _ptr(eps1), _ptr(eps2), seed, 0,
                                       float(optimizer.learning_rate.value), optimizer.beta_1, optimizer.beta_2,
-                                      optimizer.epsilon, optimizer.iterations, C.byref(o), _stream_ptr()),
+                                      optimizer.epsilon, optimizer.iterations + 1, C.byref(o), _stream_ptr()),
                   "iwae_train_step")
+        optimizer.iterations += 1          # only once the step has been issued (a failed call leaves the count alone)
+        self.mark_params_modified()
         bufs["_seed"] = seed
         bufs["_x"], bufs["_y"], bufs["_eps1"], bufs["_eps2"] = x, y, eps1, eps2
         return bufs
@@ -537,6 +551,7 @@ class IWAE:
         per = self._alloc(max(N, 1))[:N]
         total = torch.zeros((), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
+            self._declare_params_version()
             check(lib.iwae_llh_eval(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), N, int(n_samples),
                                     self._next_seed(seed), int(img_offset), _abi.PRECISIONS[precision], _ptr(per),
                                     _ptr(total), _stream_ptr()), "iwae_llh_eval")
@@ -552,6 +567,7 @@ class IWAE:
         per_i, per_v = self._alloc(max(N, 1))[:N], self._alloc(max(N, 1))[:N]
         sums = torch.zeros(2, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
+            self._declare_params_version()
             check(lib.iwae_monitor_eval(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), N, int(n_samples),
                                         self._next_seed(seed), 0, _abi.PRECISIONS[precision], _ptr(per_i), _ptr(per_v),
                                         _ptr(sums), _stream_ptr()), "iwae_monitor_eval")
@@ -573,6 +589,7 @@ class IWAE:
         total = C.c_double(0.0)
         yh = None if y_host is None else np.ascontiguousarray(y_host, dtype=np.float32)
         with torch.cuda.device(self.device):
+            self._declare_params_version()
             check(lib.iwae_llh_eval_host(self._ctx, _ptr(self.params), x_host.ctypes.data_as(C.c_void_p),
                                          None if yh is None else yh.ctypes.data_as(C.c_void_p), N, int(n_samples),
                                          self._next_seed(seed), int(img_offset), _abi.PRECISIONS[precision],

@@ -5,7 +5,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 import iwae_b200 as ib
-from iwae_b200.dist import model_llh_sharded, dp_train_step
+from iwae_b200.dist import model_llh_sharded, dp_train_step, init_comm
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -18,6 +18,8 @@ ref_per, ref_tot = m.llh(X[:37], 300, seed=11)
 ok_eval = torch.equal(per, ref_per) and abs(float(mean) - float(ref_tot) / 37) < 1e-9 * abs(float(mean))
 # data-parallel training vs single-GPU training with the same noise (same seed, global image index keying)
 m1 = ib.IWAE2([200, 100], [100, 50], seed=1, out_bias=bias)
+if os.environ.get('IWAE_DP_TORCH') is None:
+    init_comm(m)          # library-owned NCCL communicator: the all-reduce runs inside the step's CUDA graph
 o, o1 = ib.Adam(1e-3, epsilon=1e-4), ib.Adam(1e-3, epsilon=1e-4)
 for t in range(3):
     xb = X[t * 20:(t + 1) * 20]
