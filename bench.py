@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py - BASELINE.json's headline metric on B200: k=5000 test-LLH image-samples/s.
+"""bench.py - BASELINE.json's headline metric on B200: k=5000 test-LLH image-samples/s (and k=50 train steps/s).
 
 A "step" is one pass of the k=5000 importance-weighted log-likelihood estimator (main.py:170-184 of
 nbip/IWAE) over 10,000 synthetic binarised 28x28 images with the 2-stochastic-layer IWAE
@@ -8,11 +8,16 @@ with one all-reduce of the fp64 LLH sum and its read-back on the host.
 
   python bench.py [--gpus N --steps K --warmup W]            (N>1: launched by torch.distributed.run)
   python bench.py --impl reference ...                       the reference's CPU path (oracle port: the
-                                                             TF2 stack is not installable here)
+                                                             TF2 stack is not installable here); imports
+                                                             nothing of iwae_b200 and loads no .so of this repo
 
-Prints ONE JSON line (see README / DESIGN.md §Measurement for the keys).
+Prints ONE JSON line (see README / DESIGN.md §Measurement for the keys).  Besides the headline it carries
+`train` (M2 of BASELINE.md: k=50 train steps/s for BASELINE configs[1], at EVERY N - data-parallel with the gradient
+all-reduce inside the step for N > 1), `train_configs` (configs[0], [3], [4]), `cpu_baseline` and `cpu_baseline_train`.
 """
 import argparse
+import csv
+import glob
 import json
 import os
 import subprocess
@@ -31,6 +36,18 @@ UNIT = "image-samples/s"
 FLOP_PER_ROW_2L = 563600.0      # 281,800 MAC per (image, sample) row, 2-layer [100,50]
 FLOP_PER_ROW_1L = 433600.0      # 1-layer d=100
 
+# training configurations of BASELINE.json (batch 20 everywhere, main.py:21)
+TRAIN_CONFIGS = {
+    "C2": dict(config="configs[1]: IWAE 2 stochastic layers (100/50) k=50", kind="iwae2", h=[200, 100], d=[100, 50], k=50,
+               objective="iwae_elbo"),
+    "C1": dict(config="configs[0]: IWAE 1 stochastic layer k=5 (784-200-200-50)", kind="iwae1", h=200, d=50, k=5,
+               objective="iwae_elbo"),
+    "C4": dict(config="configs[3]: DReG estimator (task02) 1 stochastic layer k=50", kind="dreg", h=200, d=100, k=50,
+               objective="dreg"),
+    "C5": dict(config="configs[4]: conditional IWAE (task04) label-conditioned prior k=50", kind="ciwae", h=200, d=100, k=50,
+               objective="iwae_elbo"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -42,35 +59,40 @@ def parse():
     ap.add_argument("--k", type=int, default=5000)
     ap.add_argument("--layers", type=int, default=2, choices=[1, 2])
     ap.add_argument("--precision", default="tc_f16_fast", choices=["fp32", "tc_f16", "tc_f16_fast"])
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of each cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=1000)
     ap.add_argument("--ref-images", type=int, default=32, help="images per step of --impl reference")
     return ap.parse_args()
 
 
-def synthetic(n_images):
-    from iwae_b200 import data
-    P, X, _ = data.synthetic_binarised(n_images, seed=123)
-    return P, X
-
-
-def config_dict(args, n_local_note="contiguous image shards"):
+def config_dict(args, n_local_note="contiguous image shards", precision=None):
     arch = "784-200-200-100/100-100-100-50" if args.layers == 2 else "784-200-200-100"
     return {
         "workload": f"k={args.k} test-set LLH, {args.images} synthetic binarised 28x28 images, "
                     f"IWAE {args.layers} stochastic layer(s) {arch} (BASELINE.json configs[2])",
-        "images": args.images, "k": args.k, "stochastic_layers": args.layers, "precision": args.precision,
+        "images": args.images, "k": args.k, "stochastic_layers": args.layers, "precision": precision or args.precision,
         "sharding": n_local_note, "l2": "256 MiB buffer rewritten between timed steps (L2 flush)",
-        "noise": "Philox4x32-10 + Box-Muller in registers, keyed on the global image index",
+        "noise": "Philox4x32-10 + Box-Muller (16-bit uniforms, 8 normals per call) in registers, keyed on the global image index",
     }
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU leg: the reference's path as restated by the oracle (fp32, PyTorch-CPU, reference call shape:
-# one eager call per image with B=1, k=5000, every dict entry computed - main.py:175-177)
+# CPU legs: the reference's path as restated by the oracle (fp32, PyTorch-CPU, reference call shapes).
+# Nothing below imports iwae_b200: the reference arm must not load this repo's native library.
 # ---------------------------------------------------------------------------------------------
+def cpu_threads(torch):
+    # torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
+    return torch.get_num_threads()
+
+
 def cpu_llh_pass(params32, X, k, layers, torch, oracle, gen):
+    """main.py:175-177: one eager call per image with B=1, k=5000, every dict entry computed."""
     total = 0.0
     for i in range(X.shape[0]):
         x = torch.from_numpy(X[i:i + 1])
@@ -87,13 +109,9 @@ def cpu_llh_pass(params32, X, k, layers, torch, oracle, gen):
 
 def cpu_setup(args):
     import torch
-    # torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can
-    try:
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-    except Exception:
-        torch.set_num_threads(os.cpu_count() or 1)
+    cpu_threads(torch)
     from oracle import iwae_oracle as oracle
-    P, X = synthetic(max(args.ref_images, 1000))
+    P, X, _ = oracle.synthetic_data(max(args.ref_images, 1000), seed=123)
     rs = np.random.RandomState(123)
     if args.layers == 2:
         shapes = oracle.param_shapes("iwae2", [200, 100], [100, 50])
@@ -122,6 +140,53 @@ def cpu_baseline(args):
                       f"{dt:.1f} s, host has {os.cpu_count()} logical cores"}
 
 
+def cpu_baseline_train(args):
+    """M2 of BASELINE.md §2 on the host cores: model.train_step (src/iwae1.py:153-162) restated as oracle forward +
+    torch.autograd + Keras-rule Adam (eps = 1e-4, main.py:93), batch 20, >= 200 steps after 20 warm-up steps, for the
+    shapes of BASELINE configs[0] (C1) and configs[1] (C2)."""
+    import torch
+    threads = cpu_threads(torch)
+    from oracle import iwae_oracle as oracle
+    P, X, _ = oracle.synthetic_data(1000, seed=123)
+    out = {}
+    for name in ("C1", "C2"):
+        c = TRAIN_CONFIGS[name]
+        shapes = oracle.param_shapes(c["kind"], c["h"], c["d"])
+        params = oracle.glorot_params(shapes, np.random.RandomState(123), out_bias=oracle.get_bias(P.mean(0)))
+        p = oracle.to_torch(params, torch.float32, requires_grad=True)
+        m = {k_: torch.zeros_like(v) for k_, v in p.items()}
+        v2 = {k_: torch.zeros_like(v) for k_, v in p.items()}
+        gen = torch.Generator().manual_seed(1)
+        k = c["k"]
+
+        def step(t):
+            x = torch.from_numpy(X[(t % 50) * 20:(t % 50) * 20 + 20])
+            if c["kind"] == "iwae2":
+                e1, e2 = torch.randn(k, 20, 100, generator=gen), torch.randn(k, 20, 50, generator=gen)
+                g, _ = oracle.grads_objective(oracle.iwae2_call, p, "iwae_elbo", x, k, 1.0, e1, e2)
+            else:
+                e1 = torch.randn(k, 20, c["d"], generator=gen)
+                g, _ = oracle.grads_objective(oracle.iwae1_call, p, "iwae_elbo", x, k, 1.0, e1)
+            with torch.no_grad():
+                for n_ in p:
+                    th, m[n_], v2[n_] = oracle.keras_adam_step(p[n_], g[n_], m[n_], v2[n_], t + 1, 1e-3)
+                    p[n_].copy_(th)
+
+        for t in range(20):
+            step(t)
+        t0 = time.perf_counter()
+        n_steps = 0
+        while n_steps < 200 or (time.perf_counter() - t0 < min(args.cpu_seconds, 5.0) and n_steps < 5000):
+            step(20 + n_steps)
+            n_steps += 1
+        dt = time.perf_counter() - t0
+        out[name] = {"value": n_steps / dt, "unit": "steps/s", "steps": n_steps, "config": c["config"]}
+    return {"metric": "k=50 / k=5 train steps/s on the host cores", "cores": threads, "kind": "port",
+            "sample": "oracle forward + torch.autograd + Keras-rule Adam, batch 20, >= 200 steps after 20 warm-up "
+                      "(main.py:135-143); PyTorch-CPU fp32 port standing in for TF2-CPU",
+            **out}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -140,10 +205,12 @@ def run_reference(args):
     cb = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
           "sample": f"each step = {n} images x k={args.k} (bounded sample of the 10,000-image workload), one eager "
                     f"B=1 call per image (main.py:175-177), PyTorch-CPU fp32 oracle port standing in for TF2-CPU"}
+    assert "iwae_b200" not in sys.modules, "the reference arm must not import the product package"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, "CPU, rank 0 only"),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, "CPU, rank 0 only", precision="f32 (PyTorch-CPU)"),
         "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -190,6 +257,36 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(layers):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fused kernel on the default
+    single-GPU workload, parsed from the newest committed `ncu` capture profiles/r*_ncu_traffic_full_launch*.csv
+    (scripts/gpu_traffic.sh writes it; the file name carries the round).  None when no capture of this workload exists."""
+    pat = "profiles/r*_ncu_traffic_full_launch.csv" if layers == 2 else "profiles/r*_ncu_traffic_full_launch_1layer.csv"
+    files = sorted(glob.glob(os.path.join(ROOT, pat)))
+    if not files:
+        return None, None
+    path = files[-1]
+    rd = wr = None
+    try:
+        for row in csv.reader(open(path)):
+            if len(row) < 3 or "iwae_eval_tc_kernel" not in ",".join(row):
+                continue
+            name = next((c for c in row if c.startswith("dram__bytes_")), None)
+            if name is None:
+                continue
+            unit, val = row[-2], float(row[-1].replace(",", ""))
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+            if name == "dram__bytes_read.sum":
+                rd = val * mult
+            elif name == "dram__bytes_write.sum":
+                wr = val * mult
+    except Exception:
+        return None, None
+    if rd is None or wr is None:
+        return None, None
+    return rd + wr, os.path.relpath(path, ROOT)
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -210,7 +307,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    P, X = synthetic(args.images)
+    P, X, Y = ib.data.synthetic_binarised(args.images, seed=123)
     bias = ib.data.get_bias(P.mean(0))
     if args.layers == 2:
         model = ib.IWAE2([200, 100], [100, 50], seed=123, out_bias=bias)
@@ -304,48 +401,111 @@ def run_ours(args):
         kms = float(np.mean(kernel_ms))
         flop_row = FLOP_PER_ROW_2L if args.layers == 2 else FLOP_PER_ROW_1L
         ach = (b - a) * args.k * flop_row / (kms * 1e-3) / 1e12
-        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of this kernel on the default
-        # single-GPU workload, from the ncu capture committed as profiles/r01_v5_ncu_traffic_full_launch.csv;
-        # other workloads were not captured
-        traffic = 40567040 + 34816 if (world == 1 and args.images == 10000 and args.k == 5000 and args.layers == 2) else None
+        default_workload = world == 1 and args.images == 10000 and args.k == 5000
+        traffic, traffic_src = ncu_traffic(args.layers) if default_workload else (None, None)
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                           "traffic": traffic, "traffic_unit": "bytes/launch (DRAM; L2->SM weight streaming is 221 GB/launch)",
+                           "traffic": traffic, "traffic_unit": "bytes/launch (DRAM, ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                           "traffic_source": traffic_src,
                            "kernel": "tc::iwae_eval_tc_kernel", "kernel_ms": kms,
                            "kernel_share_of_step": kms / (ms_total / args.steps),
                            "flop_per_row": flop_row, "rows_per_launch": (b - a) * args.k, "peak_source": which,
                            "note": "fp16 operands; peak is the measured dense bf16 cuBLAS figure (same tensor rate)"}
 
-    if rank == 0 and world == 1 and not args.no_train:
-        out["train"] = bench_train(ib, torch, X, bias)
+    if not args.no_train:
+        tr = bench_train(ib, torch, dist, rank, world, dev, X, Y, bias, "C2", args.train_steps)
+        extra = {n: bench_train(ib, torch, dist, rank, world, dev, X, Y, bias, n, args.train_steps) for n in ("C1", "C4", "C5")}
+        if rank == 0:
+            out["train"] = tr
+            out["train_configs"] = extra
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
+        out["cpu_baseline_train"] = cpu_baseline_train(args)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_train(ib, torch, X, bias, steps=1000, warmup=50):
-    """Second half of BASELINE.json's metric: k=50 train steps/s, batch 20, 2 stochastic layers
-    (configs[1]); batch already on the device, forward + backward + Keras-Adam per step."""
+def bench_train(ib, torch, dist, rank, world, dev, X, Y, bias, name, steps=1000, warmup=50):
+    """Second half of BASELINE.json's metric: train steps/s, global batch 20 already on the device, forward + backward
+    + Keras-Adam per step.  One GPU: model.train_step (the step replayed from a CUDA graph).  N GPUs: data-parallel over
+    image shards (3,3,3,3,2,2,2,2 at N=8) with ONE ncclAllReduce of the flat gradient inside the step's graph
+    (iwae_dp_train_step); timed with CUDA events between barriers, max over ranks."""
     from iwae_b200 import _abi
-    model = ib.IWAE2([200, 100], [100, 50], seed=123, out_bias=bias)
+    from iwae_b200.dist import dp_train_step, init_comm
+    c = TRAIN_CONFIGS[name]
+    if c["kind"] == "iwae2":
+        model = ib.IWAE2(c["h"], c["d"], seed=123, out_bias=bias)
+    elif c["kind"] == "dreg":
+        model = ib.IWAEDReG(c["h"], c["d"], seed=123, out_bias=bias)
+    elif c["kind"] == "ciwae":
+        model = ib.CIWAE(c["h"], c["d"], seed=123, out_bias=bias)
+    else:
+        model = ib.IWAE(c["h"], c["d"], seed=123, out_bias=bias)
     opt = ib.Adam(1e-3, epsilon=1e-4)
-    xb = [torch.from_numpy(X[i * 20:(i + 1) * 20]).cuda() for i in range(16)]
+    k = c["k"]
+    xb = [torch.from_numpy(X[i * 20:(i + 1) * 20]).to(dev) for i in range(16)]
+    yb = [torch.from_numpy(Y[i * 20:(i + 1) * 20].astype(np.float32)).to(dev) for i in range(16)]
+    if world > 1:
+        init_comm(model)
+
+    def step(i):
+        j = i % 16
+        if world > 1:
+            dp_train_step(model, xb[j], k, 1.0, opt, c["objective"], y=yb[j] if c["kind"] == "ciwae" else None, seed=1000 + i)
+            return None
+        if c["kind"] == "dreg":
+            return model.train_step(xb[j], k, 1.0, opt, seed=1000 + i)
+        if c["kind"] == "ciwae":
+            return model.train_step(xb[j], yb[j], k, 1.0, opt, objective=c["objective"], seed=1000 + i)
+        return model.train_step(xb[j], k, 1.0, opt, objective=c["objective"], seed=1000 + i)
+
     for i in range(warmup):
-        model.train_step(xb[i % 16], 50, 1.0, opt, objective="iwae_elbo")
+        step(i)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     l0 = _abi.lib.iwae_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    res = None
     for i in range(steps):
-        res = model.train_step(xb[i % 16], 50, 1.0, opt, objective="iwae_elbo")
+        res = step(warmup + i)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    return {"metric": "k=50 train steps/s", "value": steps / (ms * 1e-3), "unit": "steps/s", "batch": 20, "k": 50,
-            "stochastic_layers": 2, "objective": "iwae_elbo", "launches_per_step": (_abi.lib.iwae_launch_count() - l0) / steps,
-            "note": "latency-bound: ~1.7 GFLOP per step; fp32 FFMA kernels, the step replayed from a CUDA graph inside iwae_train_step", "last_iwae_elbo": float(res["iwae_elbo"])}
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    launches = (_abi.lib.iwae_launch_count() - l0) / steps
+    allreduce_us = None
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # the collective by itself: the same ~2 MB sum all-reduce, back to back on one stream
+        import ctypes as C
+        g = torch.zeros(model.n_params, dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(20):
+            _abi.check(_abi.lib.iwae_allreduce_sum_f32(model._ctx, C.c_void_p(g.data_ptr()), model.n_params, st))
+        torch.cuda.synchronize(); dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(200):
+            _abi.check(_abi.lib.iwae_allreduce_sum_f32(model._ctx, C.c_void_p(g.data_ptr()), model.n_params, st))
+        a1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a0.elapsed_time(a1) / 200 * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_us = float(t.item())
+    ms = float(ms.item())
+    rec = {"metric": f"k={k} train steps/s", "value": steps / (ms * 1e-3), "unit": "steps/s", "ms_per_step": ms / steps,
+           "config": c["config"], "global_batch": 20, "k": k, "objective": c["objective"], "n_gpus": world,
+           "parallelism": "single GPU, step replayed from a CUDA graph" if world == 1 else
+                          f"data-parallel over image shards, dp{world}; ncclAllReduce of the {model.n_params}-float gradient inside the step's CUDA graph",
+           "launches_per_step": launches, "n_params": int(model.n_params),
+           "allreduce_us": allreduce_us,
+           "note": "latency-bound (north_star): ~1.7 GFLOP per C2 step; fp32 FFMA kernels"}
+    if res is not None:
+        rec["last_iwae_elbo"] = float(res["iwae_elbo"])
+    return rec
 
 
 def main():

@@ -215,6 +215,29 @@ int iwae_decode(iwae_ctx* ctx, const float* params, const float* z, const float*
 int iwae_block_forward(iwae_ctx* ctx, const float* params, int32_t block, const float* in, int32_t R,
                        float* mu, float* sd, void* stream);
 
+/* Distribution shims: what the reference's scripts ask of the tfd objects model.encoder / model.decoder return.
+ *   iwae_bernoulli_log_prob : pxz.log_prob(x) elementwise (tasks/plot_task01.py:63): logits [R,n], x [B,n] (row r % B)
+ *                             -> out [R,n] = -(1-x) softplus(l) - x softplus(-l)        
+ *   iwae_normal_log_prob    : qzx.log_prob(z) elementwise (tasks/plot_task01.py:72): z [R,d], loc/scale [Rm,d]
+ *                             (row r % Rm; both NULL = N(0,1)) -> out [R,d], TFP op order (A.2)
+ *   iwae_normal_sample      : qzx.sample(n) (src/iwae1.py:59): out [n,Rm,d] = eps*scale + loc; eps_in [n,Rm,d], or NULL to
+ *                             draw it from the device Philox generator (seed, stream_id)
+ *   iwae_bernoulli_sample_logits : Bernoulli(logits).sample() and .probs (src/iwae1.py:172-176): probs = sigmoid(logits),
+ *                             x = (u < probs) with the uniforms of iwae_bernoulli_sample; probs_out may be NULL */
+int iwae_bernoulli_log_prob(const float* logits, const float* x, int64_t R, int32_t B, int32_t n, float* out, void* stream);
+int iwae_normal_log_prob(const float* z, const float* loc, const float* scale, int64_t R, int32_t Rm, int32_t d, float* out,
+                         void* stream);
+int iwae_normal_sample(const float* loc, const float* scale, const float* eps_in, int32_t Rm, int32_t n, int32_t d,
+                       uint64_t seed, int32_t stream_id, float* out, void* stream);
+int iwae_bernoulli_sample_logits(const float* logits, int64_t n, uint64_t seed, uint64_t epoch, float* x_out,
+                                 float* probs_out, void* stream);
+
+/* The true-posterior grid of tasks/plot_task01.py:46-73 for a 2-D latent, entirely on the device: grid =
+ * meshgrid(linspace(x0,x1,n1), linspace(y0,y1,n2)) [n1*n2, 2]; out_log_post [n2*n1] = lpxz + lpz - logsumexp over the
+ * grid; out_log_q [n2*n1] = sum_j log q(z_j | x).  x: one image [n_x]. */
+int iwae_posterior_grid(iwae_ctx* ctx, const float* params, const float* x, double x0, double x1, double y0, double y1,
+                        int32_t n1, int32_t n2, float* out_log_post, float* out_log_q, float* out_grid, void* stream);
+
 /* SIR: numpy.random.RandomState.choice(arange(L), size, replace=False, p=al)
  * (tasks/plot_task01.py:88) bit-exactly, given the float64 uniforms the RandomState would draw.
  *   al [L] fp32 normalised weights; uniforms [n_uniforms] fp64 (device); out_idx [size] int64;
@@ -230,19 +253,6 @@ int iwae_softmax_f32(const float* log_w, int32_t L, float* out, void* stream);
  * to NumPy's legacy binomial. */
 int iwae_bernoulli_sample(const float* p, int64_t n, uint64_t seed, uint64_t epoch, float* out,
                           void* stream);
-
-/* Tensor-core unit test hook: D[128,N] = A[128,K] * B[N,K]^T with fp16 operands staged exactly like
- * the fused evaluation kernel stages them (no-swizzle K-major core matrices, one tcgen05.mma chain).
- * A, B fp32 on the device (rounded to fp16 inside).  variant 0 = the descriptor convention the fused
- * kernel uses (LBO = K-direction core-matrix stride, SBO = M/N-direction); 1 = the two swapped
- * (diagnostic only).  Used by tests/test_umma_unit.py. */
-int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, int32_t variant, float* D,
-                       void* stream);
-
-/* Tensor-core micro-benchmark (diagnostic): `reps` back-to-back tcgen05.mma of shape M=128, N, K=16 in the
- * fused kernel's operand layout on `nctas` CTAs; out_cycles [nctas] (device) receives the SM cycles from
- * first issue to completion.  Used to size the fused kernel's MMA width (scripts/umma_bench.py). */
-int iwae_umma_bench(int32_t N, int32_t reps, int32_t nctas, int64_t* out_cycles, void* stream);
 
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t iwae_launch_count(void);

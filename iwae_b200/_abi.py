@@ -67,11 +67,14 @@ def _load():
         "iwae_sir": (C.c_int, [vp, i32, vp, i32, i32, vp, vp, vp]),
         "iwae_softmax_f32": (C.c_int, [vp, i32, vp, vp]),
         "iwae_bernoulli_sample": (C.c_int, [vp, i64, u64, u64, vp, vp]),
-        "iwae_umma_selftest": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "iwae_launch_count": (i64, []),
-        "iwae_umma_bench": (C.c_int, [i32, i32, i32, vp, vp]),
         "iwae_llh_kernel_ms": (C.c_int, [vp, P(C.c_float)]),
         "iwae_set_params_version": (C.c_int, [vp, C.c_uint64]),
+        "iwae_bernoulli_log_prob": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
+        "iwae_normal_log_prob": (C.c_int, [vp, vp, vp, i64, i32, i32, vp, vp]),
+        "iwae_normal_sample": (C.c_int, [vp, vp, vp, i32, i32, i32, u64, i32, vp, vp]),
+        "iwae_bernoulli_sample_logits": (C.c_int, [vp, i64, u64, u64, vp, vp, vp]),
+        "iwae_posterior_grid": (C.c_int, [vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, i32, i32, vp, vp, vp, vp]),
         "iwae_comm_unique_id": (C.c_int, [vp]),
         "iwae_comm_init": (C.c_int, [vp, vp, i32, i32]),
         "iwae_comm_destroy": (C.c_int, [vp]),
@@ -89,11 +92,37 @@ def _load():
 
 
 lib = _load()
+
+DIAG_LIB_PATH = os.path.join(_HERE, "lib", "libiwae_b200_diag.so")
+_diag = None
+
+
+def diag_lib():
+    """libiwae_b200_diag.so (include/iwae_b200_diag.h): the tensor-core unit-test hook and the tcgen05.mma
+    micro-benchmark.  Tests and scripts/ only - the product library does not carry them."""
+    global _diag
+    if _diag is None:
+        d = C.CDLL(DIAG_LIB_PATH)
+        vp, i32 = C.c_void_p, C.c_int32
+        d.iwae_diag_last_error.restype = C.c_char_p
+        d.iwae_umma_selftest.restype = C.c_int
+        d.iwae_umma_selftest.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+        d.iwae_umma_bench.restype = C.c_int
+        d.iwae_umma_bench.argtypes = [i32, i32, i32, vp, vp]
+        _diag = d
+    return _diag
+
+
+def check_diag(rc: int, what: str = ""):
+    if rc != 0:
+        msg = diag_lib().iwae_diag_last_error()
+        raise IwaeError(f"{what} failed (rc={rc}): {msg.decode('utf-8', 'replace') if msg else ''}")
 EXPORTS = ("iwae_last_error", "iwae_version", "iwae_create", "iwae_destroy", "iwae_param_count",
            "iwae_param_layout", "iwae_layout_for_config", "iwae_forward", "iwae_llh_eval", "iwae_llh_eval_host",
            "iwae_grads", "iwae_adam_step", "iwae_train_step", "iwae_philox_normal", "iwae_decode", "iwae_sir",
-           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_umma_selftest", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_set_params_version", "iwae_comm_unique_id", "iwae_comm_init", "iwae_comm_destroy", "iwae_comm_info",
-           "iwae_allreduce_sum_f32", "iwae_allreduce_sum_f64", "iwae_dp_train_step", "iwae_umma_bench", "iwae_monitor_eval",
+           "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_set_params_version", "iwae_comm_unique_id", "iwae_comm_init", "iwae_comm_destroy", "iwae_comm_info",
+           "iwae_allreduce_sum_f32", "iwae_allreduce_sum_f64", "iwae_dp_train_step", "iwae_monitor_eval", "iwae_bernoulli_log_prob", "iwae_normal_log_prob",
+           "iwae_normal_sample", "iwae_bernoulli_sample_logits", "iwae_posterior_grid",
            "iwae_block_forward")
 
 

@@ -955,14 +955,3 @@ extern "C" int iwae_bernoulli_sample(const float* p, int64_t n, uint64_t seed, u
   IWAE_REQUIRE(p && out && n >= 0, "iwae_bernoulli_sample: bad argument");
   return bernoulli_sample_f32(p, n, seed, epoch, out, (cudaStream_t)stream);
 }
-
-extern "C" int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, int32_t variant, float* D,
-                                  void* stream) {
-  IWAE_REQUIRE(A && B && D, "iwae_umma_selftest: null argument");
-  return umma_selftest(A, B, N, K, variant, D, (cudaStream_t)stream);
-}
-
-extern "C" int iwae_umma_bench(int32_t N, int32_t reps, int32_t nctas, int64_t* out_cycles, void* stream) {
-  IWAE_REQUIRE(out_cycles, "iwae_umma_bench: null argument");
-  return umma_bench(N, reps, nctas, reinterpret_cast<long long*>(out_cycles), (cudaStream_t)stream);
-}

@@ -244,5 +244,3 @@ int comm_allreduce_f32(iwae_ctx* ctx, float* buf, int64_t n, cudaStream_t st);
 float* comm_grad_buffer(iwae_ctx* ctx);
 int comm_world(const iwae_ctx* ctx);
 void comm_release(iwae_ctx* ctx);
-int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream_t st);
-int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st);

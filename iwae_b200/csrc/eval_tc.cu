@@ -25,6 +25,7 @@
 // measured timeline.
 #include "common.cuh"
 #include "rng.cuh"
+#include "tc_ptx.cuh"
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
@@ -34,312 +35,6 @@
 #include <vector>
 
 namespace tc {
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the
-// hint (ns) expires, so a waiting role does not burn issue slots of the SM sub-partition it shares
-// with an epilogue warp (ncu on v1: 32 % of all executed instructions were this spin loop).
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU.
-// The waiting warp SLEEPS between polls (nanosleep): ncu showed that the hardware-suspended try_wait
-// returns early whenever any mbarrier of the CTA changes, so a free-running poll loop of the producer
-// warp alone executed 42 % of all instructions of the kernel and took issue slots from the epilogue
-// warps of its SM sub-partition - whose rows then finish every layer last.
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns) {
-  uint64_t t0 = 0;
-  uint32_t polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(sleep_ns);
-    if ((++polls & 0xFFFu) == 0) {
-      const uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) {
-        printf("iwae_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-        __trap();
-      }
-    }
-  }
-}
-// sleep_ns: poll period once the first (hardware-suspended) try_wait has failed - short for waits on the
-// critical path (MMA issuer, epilogue), long for the weight producer, which runs ahead of its consumer
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns = 32) {
-  if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow(bar, parity, tag, sleep_ns);
-}
-// One lane of a fully converged warp (the same lane every time): PTX elect.sync.
-__device__ __forceinline__ uint32_t elect_one_sync() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}"
-      : "+r"(pred));
-  return pred;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate, M=128
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=0.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (bit4), a=b=f16 (0), K-major both,
-// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Self-test GEMM: D[128,N] = A[128,K] B[N,K]^T through exactly the staging the fused kernel uses.
-// variant 0: LBO = K-direction stride, SBO = M/N-direction stride (CUTLASS canonical); 1: swapped.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int N,
-                                                            int K, float* __restrict__ D, int variant) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_base_s;
-  const int Kp = (K + 15) & ~15;
-  uint8_t* sA = smem;                          // [Kp/8][128][8] halves
-  uint8_t* sB = smem + (size_t)Kp * 128 * 2;   // [Kp/8][N][8] halves
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < 128 * Kp; i += 128) {
-    const int r = i / Kp, k = i % Kp;
-    const float v = (k < K) ? A[(size_t)r * K + k] : 0.f;
-    *reinterpret_cast<__half*>(sA + (size_t)(k >> 3) * 128 * 16 + r * 16 + (k & 7) * 2) = __float2half_rn(v);
-  }
-  for (int i = tid; i < N * Kp; i += 128) {
-    const int n = i / Kp, k = i % Kp;
-    const float v = (k < K) ? B[(size_t)n * K + k] : 0.f;
-    *reinterpret_cast<__half*>(sB + (size_t)(k >> 3) * N * 16 + n * 16 + (k & 7) * 2) = __float2half_rn(v);
-  }
-  uint32_t ncols = 32;
-  while ((int)ncols < N) ncols <<= 1;
-  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-  __syncwarp();
-  if (warp == 0) { tmem_alloc(&tmem_base_s, ncols); tmem_relinquish(); }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc((uint32_t)N);
-    const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16, sbo = 128;
-    for (int ks = 0; ks < Kp / 16; ++ks) {
-      const uint32_t a_addr = smem_u32(sA) + ks * 2 * lboA;
-      const uint32_t b_addr = smem_u32(sB) + ks * 2 * lboB;
-      const uint64_t ad = variant ? make_smem_desc(a_addr, sbo, lboA) : make_smem_desc(a_addr, lboA, sbo);
-      const uint64_t bd = variant ? make_smem_desc(b_addr, sbo, lboB) : make_smem_desc(b_addr, lboB, sbo);
-      umma_f16(tmem_base, ad, bd, idesc, ks > 0);
-    }
-    umma_commit(&bar);
-  }
-  mbar_wait(&bar, 0, 900);
-  tc_fence_after();
-  const int row = warp * 32 + (tid & 31);
-  for (int c0 = 0; c0 < N; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c0 + j < N) D[(size_t)row * N + c0 + j] = __uint_as_float(r[j]);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, ncols);
-}
-
-// Micro-benchmark: `reps` back-to-back tcgen05.mma (M=128, K=16, fp16, smem A and B in the fused kernel's
-// no-swizzle K-major layout) of width N into one accumulator; returns cycles from first issue to the
-// commit's mbarrier completion.  Sizes the chunk width of the fused kernel (SS-mode A-operand fetch).
-__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int mode, long long* out) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar, bar2, bar3;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (128 + N) * 16 * 2 * 4 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
-  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_init(&bar3, 1); fence_barrier_init(); }
-  __syncwarp();
-  if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  long long t0 = 0;
-  if (warp == 1) {
-    const uint32_t idesc = make_idesc((uint32_t)N);
-    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem) + 128 * 16 * 2 * 4;
-    t0 = clock64();
-    if (mode == 0) {
-      if (elect_one_sync()) {
-        for (int r = 0; r < reps; ++r) {
-          const uint32_t ks = r & 3;
-          const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
-          umma_f16(tmem_base, ad, bd, idesc, r > 0);
-        }
-        umma_commit(&bar);
-      }
-      __syncwarp();
-    } else if (mode & 32) {
-      // as the fused kernel's slab loop (elect per slab of two MMAs) but unrolled by four, so that consecutive
-      // slabs use different uniform registers for their descriptors
-#pragma unroll 4
-      for (int r = 0; r < reps; r += 2) {
-        if (mode & 2) tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t ks = r & 3;
-          const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
-          umma_f16(tmem_base, ad, bd, idesc, r > 0);
-          if (r + 1 < reps) umma_f16(tmem_base, ad + (uint64_t)(2u * 128u), bd + (uint64_t)(2u * (uint32_t)N), idesc, true);
-          if (mode & 1) umma_commit(&bar2);
-        }
-        if (mode & 4) __syncwarp();
-      }
-      if (elect_one_sync()) umma_commit(&bar);
-      __syncwarp();
-    } else if (mode & 16) {
-      // warp-uniform descriptor arithmetic OUTSIDE the elected region (uniform datapath), only the
-      // tcgen05 instructions inside it
-      for (int r = 0; r < reps; r += 2) {
-        if (mode & 2) tc_fence_after();
-        const uint32_t ks = r & 3;
-        const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
-        const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
-        const uint64_t ad1 = ad + (uint64_t)(2u * 128u), bd1 = bd + (uint64_t)(2u * (uint32_t)N);
-        const bool two = r + 1 < reps;
-        if (elect_one_sync()) {
-          umma_f16(tmem_base, ad, bd, idesc, r > 0);
-          if (two) umma_f16(tmem_base, ad1, bd1, idesc, true);
-          if (mode & 1) umma_commit(&bar2);
-        }
-        if (mode & 4) __syncwarp();
-      }
-      if (elect_one_sync()) umma_commit(&bar);
-      __syncwarp();
-    } else if (mode & 8) {
-      // everything inside ONE elected thread: per slab (bit 0) a commit to a second mbarrier, (bit 1) a
-      // try_wait on an already-completed mbarrier
-      if (elect_one_sync()) {
-        mbar_arrive(&bar3);
-        for (int r = 0; r < reps; r += 2) {
-          if (mode & 2) { while (!mbar_try_wait(&bar3, 0)) {} tc_fence_after(); }
-          for (int rr = r; rr < min(r + 2, reps); ++rr) {
-            const uint32_t ks = rr & 3;
-            const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
-            const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
-            umma_f16(tmem_base, ad, bd, idesc, rr > 0);
-          }
-          if (mode & 1) umma_commit(&bar2);
-        }
-        umma_commit(&bar);
-      }
-      __syncwarp();
-    } else {
-      // the issue pattern of the fused kernel: per slab of two MMAs a warp-uniform iteration with
-      // (mode bit 0) a commit to a second mbarrier, (bit 1) a tcgen05 fence, (bit 2) an elect + __syncwarp
-      for (int r = 0; r < reps; r += 2) {
-        if (mode & 2) tc_fence_after();
-        if (elect_one_sync()) {
-          for (int rr = r; rr < min(r + 2, reps); ++rr) {
-            const uint32_t ks = rr & 3;
-            const uint64_t ad = make_smem_desc(a_addr + ks * 2 * 128 * 16, 128 * 16, 128);
-            const uint64_t bd = make_smem_desc(b_addr + ks * 2 * N * 16, (uint32_t)N * 16, 128);
-            umma_f16(tmem_base, ad, bd, idesc, rr > 0);
-          }
-          if (mode & 1) umma_commit(&bar2);
-        }
-        if (mode & 4) __syncwarp();
-      }
-      if (elect_one_sync()) umma_commit(&bar);
-      __syncwarp();
-    }
-    mbar_wait(&bar, 0, 901);
-    const long long t1 = clock64();
-    if (tid == 32) out[blockIdx.x] = t1 - t0;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Fused evaluation kernel
@@ -1570,23 +1265,3 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   return 0;
 }
 
-int umma_bench(int N, int reps, int nctas, long long* out_cycles_dev, cudaStream_t st) {
-  IWAE_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && nctas > 0, "umma_bench: bad argument");
-  const size_t smem = (size_t)(128 + N) * 16 * 2 * 4;
-  CUDA_TRY(cudaFuncSetAttribute(tc::umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const char* md = getenv("IWAE_UMMA_BENCH_MODE");      // diagnostics: issue-pattern variants, see the kernel
-  tc::umma_bench_kernel<<<nctas, 128, smem, st>>>(N, reps, md ? atoi(md) : 0, out_cycles_dev);
-  LAUNCH_CHECK();
-  return 0;
-}
-
-int umma_selftest(const float* A, const float* B, int N, int K, int variant, float* D, cudaStream_t st) {
-  IWAE_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "umma_selftest: N must be a multiple of 16 in [16,256]");
-  IWAE_REQUIRE(K >= 1 && K <= 256, "umma_selftest: K must be in [1,256]");
-  const int Kp = (K + 15) & ~15;
-  const size_t smem = (size_t)Kp * (128 + N) * 2;
-  CUDA_TRY(cudaFuncSetAttribute(tc::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::umma_selftest_kernel<<<1, 128, smem, st>>>(A, B, N, K, D, variant);
-  LAUNCH_CHECK();
-  return 0;
-}

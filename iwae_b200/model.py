@@ -125,26 +125,82 @@ class Variable:
         return f"<Variable {self.name} shape={self.shape}>"
 
 
-class Normal:
-    """Minimal stand-in for `tfd.Normal` as the reference reads it: `.loc`, `.scale`
-    (plot_task01.py:40-42, task02.py:61)."""
+def _as_dev(a, device) -> torch.Tensor:
+    if isinstance(a, DeviceValue):
+        a = a.tensor
+    if not isinstance(a, torch.Tensor):
+        a = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
+    return a.to(device=device, dtype=_F32).contiguous()
 
-    def __init__(self, loc: torch.Tensor, scale: torch.Tensor):
+
+class Normal:
+    """Stand-in for `tfd.Normal(loc, scale)` as the reference uses it: `.loc`, `.scale` (plot_task01.py:40-42,
+    task02.py:61), `.log_prob(z)` (plot_task01.py:72, iwae1.py:109) and `.sample(n)` (iwae1.py:59), all backed by the
+    library's kernels (iwae_normal_log_prob / iwae_normal_sample; TFP's op order)."""
+
+    def __init__(self, loc: torch.Tensor, scale: torch.Tensor, seed_source=None):
         self.loc = DeviceValue(loc)
         self.scale = DeviceValue(scale)
+        self._seed_source = seed_source
+
+    def log_prob(self, z) -> DeviceValue:
+        """Elementwise log N(z; loc, scale); z [..., *loc.shape] broadcast over leading (sample) dims."""
+        loc, scale = self.loc.tensor.contiguous(), self.scale.tensor.contiguous()
+        z = _as_dev(z, loc.device)
+        d = loc.shape[-1]
+        if z.shape[-1] != d or z.numel() % loc.numel():
+            raise ValueError(f"z {tuple(z.shape)} does not broadcast against loc {tuple(loc.shape)}")
+        out = torch.empty_like(z)
+        check(lib.iwae_normal_log_prob(_ptr(z), _ptr(loc), _ptr(scale), z.numel() // d, loc.numel() // d, d, _ptr(out),
+                                       _stream_ptr()), "iwae_normal_log_prob")
+        return DeviceValue(out)
+
+    def sample(self, n: Optional[int] = None, seed: Optional[int] = None) -> DeviceValue:
+        """eps * scale + loc with eps ~ N(0,1) from the device Philox generator: [n, *loc.shape], or loc.shape if n is
+        None (`q(z2|z1).sample()`, iwae2.py:65)."""
+        loc, scale = self.loc.tensor.contiguous(), self.scale.tensor.contiguous()
+        d = loc.shape[-1]
+        k = 1 if n is None else int(n)
+        if seed is None:
+            seed = self._seed_source() if self._seed_source is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        out = torch.empty((k,) + tuple(loc.shape), dtype=_F32, device=loc.device)
+        check(lib.iwae_normal_sample(_ptr(loc), _ptr(scale), None, loc.numel() // d, k, d, int(seed), 1, _ptr(out),
+                                     _stream_ptr()), "iwae_normal_sample")
+        return DeviceValue(out[0] if n is None else out)
 
 
 class Bernoulli:
-    """Minimal stand-in for `tfd.Bernoulli(logits)`: `.logits`, `.log_prob(x)` (plot_task01.py:63)."""
+    """Stand-in for `tfd.Bernoulli(logits)`: `.logits`, `.log_prob(x)` (plot_task01.py:63; elementwise),
+    `.sample()` and `.probs` (iwae1.py:172-176), backed by iwae_bernoulli_log_prob / iwae_bernoulli_sample_logits."""
 
     def __init__(self, owner: "IWAE", z: torch.Tensor, y, logits: torch.Tensor):
         self._owner, self._z, self._y = owner, z, y
         self.logits = DeviceValue(logits)
 
+    def log_prob(self, x) -> DeviceValue:
+        """Elementwise log p(x_j | z) [..., n_x]; x [B, n_x] (or [n_x]) broadcast over the leading dims of logits."""
+        lg = self.logits.tensor.contiguous()
+        n = lg.shape[-1]
+        x = _as_dev(x, lg.device).reshape(-1, n)
+        R = lg.numel() // n
+        if R % x.shape[0]:
+            raise ValueError("logits rows must be a multiple of the rows of x")
+        out = torch.empty_like(lg)
+        check(lib.iwae_bernoulli_log_prob(_ptr(lg), _ptr(x), R, x.shape[0], n, _ptr(out), _stream_ptr()),
+              "iwae_bernoulli_log_prob")
+        return DeviceValue(out)
+
     def log_prob_sum(self, x) -> DeviceValue:
         """sum_j log p(x_j | z): the reduction the reference applies right after log_prob
         (iwae1.py:111), computed in the decoder kernel's fused epilogue."""
         return self._owner._decode(self._z, self._y, x, want_logits=False)[1]
+
+    @property
+    def probs(self) -> DeviceValue:
+        return self._owner._bernoulli(self.logits.tensor, 0)[1]
+
+    def sample(self, seed: Optional[int] = None) -> DeviceValue:
+        return self._owner._bernoulli(self.logits.tensor, self._owner._next_seed(seed))[0]
 
 
 def _block_names(prefix):
@@ -178,7 +234,7 @@ class _Encoder(_SubModel):
         """Encoder.call (iwae1.py:56-61): returns (z [k,B,d], qzx)."""
         o = self._owner
         res = o._forward(x, y, int(n_samples), 1.0, want=("z1", "q_mu", "q_std"))
-        return DeviceValue(res["z1"]), Normal(res["q_mu"], res["q_std"])
+        return DeviceValue(res["z1"]), Normal(res["q_mu"], res["q_std"], seed_source=o._next_seed)
 
 
 class _Decoder(_SubModel):
@@ -297,12 +353,14 @@ class IWAE:
         torch-side writes are tracked by the tensor's own version counter)."""
         self._native_writes += 1
 
+    def _params_version(self) -> int:
+        return (((self.params._version + 1) & 0xFFFFFFFF) << 32) | (self._native_writes & 0xFFFFFFFF)
+
     def _declare_params_version(self):
         """iwae_set_params_version: lets the fused evaluation reuse its packed fp16 weight image while the parameters
         are unchanged.  Version = torch's in-place version counter of the flat buffer (every torch write to it or to a
         Variable view bumps it) combined with the count of native writes."""
-        ver = (((self.params._version + 1) & 0xFFFFFFFF) << 32) | (self._native_writes & 0xFFFFFFFF)
-        check(lib.iwae_set_params_version(self._ctx, C.c_uint64(ver)), "iwae_set_params_version")
+        check(lib.iwae_set_params_version(self._ctx, C.c_uint64(self._params_version())), "iwae_set_params_version")
 
     def _dev(self, a, dtype=_F32) -> Optional[torch.Tensor]:
         if a is None:
@@ -423,14 +481,28 @@ class IWAE:
     _WANT = ("lpxz", "lpz", "lq1", "log_w", "al", "iwae", "vae", "eq14", "snis_z1", "scalars")
 
     def _lazy(self, bufs, k, beta, names):
-        """Thunk that re-runs the forward with the same noise and keeps only `names`."""
+        """Entries of the result dict that are large and rarely read (`z`, `logits`: [k,B,784] is 1.6 GB for a
+        full-test-set val_step).  If the step wrote them (train_step(materialize=...)) they are returned as they are.
+        Otherwise a thunk re-runs the forward with the same noise on first access - valid only while the parameters
+        are the ones the call used: after a train_step (whose Adam update has already changed them) or any other
+        parameter change the thunk raises instead of silently returning values of a different model
+        (the reference's tape returns the PRE-update forward, src/iwae1.py:153-162)."""
+        version = self._params_version()
+        after_train = bool(bufs.get("_after_train"))
+
         def run():
-            r = self._forward(bufs["_x"], bufs["_y"], k, beta, names, bufs["_eps1"], bufs["_eps2"], bufs["_seed"],
-                              bufs.get("_img_offset", 0))
-            return r
+            if after_train or self._params_version() != version:
+                raise RuntimeError(
+                    "this result's 'z'/'logits' were not materialised and the parameters have changed since the call; "
+                    "pass materialize=('z', 'logits') to train_step (or read them before updating the weights)")
+            return self._forward(bufs["_x"], bufs["_y"], k, beta, names, bufs["_eps1"], bufs["_eps2"], bufs["_seed"],
+                                 bufs.get("_img_offset", 0))
         cache = {}
 
         def get(name):
+            if name in bufs:
+                return DeviceValue(bufs[name])
+
             def thunk():
                 if not cache:
                     cache.update(run())
@@ -483,12 +555,20 @@ class IWAE:
 
     _OBJECTIVES = ("vae_elbo", "iwae_elbo", "iwae_eq14", "vae_elbo_kl")
 
-    def _train(self, x, y, k, beta, optimizer, objective_id, eps1=None, eps2=None, seed=None, want=None):
+    _MATERIALIZE = {"z": ("z1",), "z1": ("z1",), "z2": ("z2",), "logits": ("logits",)}
+
+    def _train(self, x, y, k, beta, optimizer, objective_id, eps1=None, eps2=None, seed=None, want=None,
+               materialize=()):
         x, y = self._check_x(x, y)
         B = x.shape[0]
         eps1 = self._check_eps(eps1, k, B, self._d1, "eps")
         eps2 = self._check_eps(eps2, k, B, self._d2, "eps2") if self._d2 else None
-        o, bufs = self._outputs(B, k, want or self._WANT)
+        want = tuple(want or self._WANT)
+        for key in materialize:
+            for f in self._MATERIALIZE[key]:        # KeyError for anything but z / z1 / z2 / logits
+                if f not in want and (f != "z2" or self._d2):
+                    want += (f,)
+        o, bufs = self._outputs(B, k, want)
         seed = self._next_seed(seed)
         m, v = optimizer._state_for(self)
         with torch.cuda.device(self.device):
@@ -501,14 +581,17 @@ class IWAE:
         self.mark_params_modified()
         bufs["_seed"] = seed
         bufs["_x"], bufs["_y"], bufs["_eps1"], bufs["_eps2"] = x, y, eps1, eps2
+        bufs["_after_train"] = True
         return bufs
 
-    def train_step(self, x, n_samples, beta, optimizer, objective="vae_elbo", eps=None, seed=None):
+    def train_step(self, x, n_samples, beta, optimizer, objective="vae_elbo", eps=None, seed=None, materialize=()):
         """IWAE.train_step (src/iwae1.py:153-162): forward, reverse pass of -res[objective], Keras-Adam
-        update.  The returned dict holds the PRE-update forward values, like the reference's tape."""
+        update.  The returned dict holds the PRE-update forward values, like the reference's tape; the large entries
+        `z` and `logits` are written only if named in `materialize` (reading them otherwise raises: by then the
+        parameters are the updated ones, so they cannot be recomputed)."""
         oid = self._objective_id(objective, self._OBJECTIVES)
         k = int(n_samples)
-        bufs = self._train(x, None, k, beta, optimizer, oid, eps, None, seed)
+        bufs = self._train(x, None, k, beta, optimizer, oid, eps, None, seed, materialize=materialize)
         return self._result(bufs, k, beta)
 
     def grads(self, x, n_samples, beta=1.0, objective="iwae_elbo", eps=None, eps2=None, seed=None, y=None,
@@ -606,11 +689,11 @@ class IWAE:
     # ---- sampling (iwae1.py:168-178) ------------------------------------------------------------
     def _bernoulli(self, logits: torch.Tensor, seed):
         """(x_sample, probs) of tfd.Bernoulli(logits) - the order every `sample` of the reference returns."""
-        probs = torch.sigmoid(logits)
-        out = torch.empty_like(probs)
+        logits = logits.contiguous()
+        probs, out = torch.empty_like(logits), torch.empty_like(logits)
         with torch.cuda.device(self.device):
-            check(lib.iwae_bernoulli_sample(_ptr(probs), probs.numel(), int(seed), 0, _ptr(out), _stream_ptr()),
-                  "iwae_bernoulli_sample")
+            check(lib.iwae_bernoulli_sample_logits(_ptr(logits), logits.numel(), int(seed), 0, _ptr(out), _ptr(probs),
+                                                   _stream_ptr()), "iwae_bernoulli_sample_logits")
         return DeviceValue(out), DeviceValue(probs)
 
     def _block(self, block_id: int, inp: torch.Tensor, n_out: int):
@@ -630,11 +713,11 @@ class IWAE:
             check(lib.iwae_philox_normal(int(seed), stream_id, 0, rows, n, d, _ptr(eps), _stream_ptr()), "iwae_philox_normal")
         return eps
 
-    def sample(self, z, y=None, seed=0):
+    def sample(self, z, y=None, seed=None):
         """model.sample(z) -> (x_sample, probs) (iwae1.py:168-178): decode prior samples to Bernoulli
-        probabilities and one binary draw each."""
+        probabilities and one binary draw each (a fresh draw per call unless `seed` is given)."""
         logits, _ = self._decode(z, y, None, want_logits=True)
-        return self._bernoulli(logits.tensor, seed)
+        return self._bernoulli(logits.tensor, self._next_seed(seed))
 
     def posterior_grid(self, x, range_x, range_y, n1=200, n2=200):
         """The true-posterior grid of tasks/plot_task01.py:46-70 for a 2-D latent: log p(z|x) on an n2 x n1 grid
@@ -642,18 +725,16 @@ class IWAE:
         (log_posterior [n2,n1], variational_log_posterior [n2,n1], grid [n1*n2, 2])."""
         if self._d1 != 2 or self._cfg.n_cond:
             raise ValueError("posterior_grid needs an unconditional model with a 2-D latent (tasks/task01.py:84)")
-        xs = torch.linspace(float(range_x[0]), float(range_x[1]), n1, device=self.device, dtype=_F32)
-        ys = torch.linspace(float(range_y[0]), float(range_y[1]), n2, device=self.device, dtype=_F32)
-        Y1, X1 = torch.meshgrid(ys, xs, indexing="ij")                      # get_grid: np.meshgrid(x, y)
-        grid = torch.stack([X1.reshape(-1), Y1.reshape(-1)], dim=1).contiguous()
-        x1 = self._dev(x).reshape(1, -1)
-        _, lpxz = self._decode(grid, None, x1, want_logits=False)
-        lpz = (-0.5 * grid * grid - 0.5 * float(np.log(2.0 * np.pi))).sum(-1)
-        unnorm = lpxz.tensor + lpz
-        log_post = unnorm - torch.logsumexp(unnorm, 0)
-        mu, sd = self._block(_abi.BLOCK_ENCODER, x1, 2)
-        lq = (-0.5 * ((grid - mu) / sd) ** 2 - (0.5 * float(np.log(2.0 * np.pi)) + torch.log(sd))).sum(-1)
-        return DeviceValue(log_post.view(n2, n1)), DeviceValue(lq.view(n2, n1)), DeviceValue(grid)
+        x1 = self._dev(x).reshape(-1)
+        if x1.numel() != self._cfg.n_x:
+            raise ValueError("posterior_grid takes ONE image")
+        log_post, lq = self._alloc(n2, n1), self._alloc(n2, n1)
+        grid = self._alloc(n1 * n2, 2)
+        with torch.cuda.device(self.device):        # grid, decoder + Bernoulli log-lik, prior, normalisation, q: all in the library
+            check(lib.iwae_posterior_grid(self._ctx, _ptr(self.params), _ptr(x1), float(range_x[0]), float(range_x[1]),
+                                          float(range_y[0]), float(range_y[1]), int(n1), int(n2), _ptr(log_post), _ptr(lq),
+                                          _ptr(grid), _stream_ptr()), "iwae_posterior_grid")
+        return DeviceValue(log_post), DeviceValue(lq), DeviceValue(grid)
 
     @staticmethod
     def write_to_tensorboard(res, step, writer=None):
@@ -715,10 +796,11 @@ class IWAE2(IWAE):
 
     __call__ = call
 
-    def train_step(self, x, n_samples, beta, optimizer, objective="vae_elbo", eps=None, eps2=None, seed=None):
+    def train_step(self, x, n_samples, beta, optimizer, objective="vae_elbo", eps=None, eps2=None, seed=None,
+                   materialize=()):
         oid = self._objective_id(objective, self._OBJECTIVES)
         k = int(n_samples)
-        bufs = self._train(x, None, k, beta, optimizer, oid, eps, eps2, seed)
+        bufs = self._train(x, None, k, beta, optimizer, oid, eps, eps2, seed, materialize=materialize)
         return self._result(bufs, k, beta)
 
 
@@ -727,18 +809,18 @@ class IWAE2(IWAE):
         if z2.shape[-1] != self._d2:
             raise ValueError(f"z2 must have last dim {self._d2}")
         mu, sd = self._block(_abi.BLOCK_DECODER21, z2, self._d1)
-        rows = mu.reshape(-1, self._d1).shape[0]
-        eps = self._normal(seed, 1, n, rows, self._d1).view(n, *mu.shape)
-        return mu + sd * eps                                                # pz1z2.sample(n) (A.2)
+        return Normal(mu, sd).sample(n, seed=seed).tensor                   # pz1z2.sample(n) (A.2)
 
-    def sample(self, z2, seed=0):
+    def sample(self, z2, seed=None):
         """iwae2.IWAE.sample (iwae2.py:184-198): z1 ~ p(z1|z2), x ~ Bernoulli(decode(z1)) -> (x_sample, probs)."""
+        seed = self._next_seed(seed)
         z1 = self._z1_given_z2(z2, 1, seed)[0]
         logits, _ = self._decode(z1, None, None, want_logits=True)
         return self._bernoulli(logits.tensor, seed)
 
-    def conditional_sample(self, z2, seed=0, n=10):
+    def conditional_sample(self, z2, seed=None, n=10):
         """iwae2.IWAE.conditional_sample (iwae2.py:200-213): ten z1 draws per fixed z2 -> ([10, ..., 784] x2)."""
+        seed = self._next_seed(seed)
         z1 = self._z1_given_z2(z2, n, seed)
         logits, _ = self._decode(z1, None, None, want_logits=True)
         return self._bernoulli(logits.tensor, seed)
@@ -766,9 +848,9 @@ class IWAEDReG(IWAE):
         res["log_w"] = DeviceValue(bufs["log_w"])
         return res
 
-    def train_step(self, x, n_samples, beta, optimizer, eps=None, seed=None):
+    def train_step(self, x, n_samples, beta, optimizer, eps=None, seed=None, materialize=()):
         k = int(n_samples)
-        bufs = self._train(x, None, k, beta, optimizer, _abi.OBJ["dreg"], eps, None, seed)
+        bufs = self._train(x, None, k, beta, optimizer, _abi.OBJ["dreg"], eps, None, seed, materialize=materialize)
         return self._result(bufs, k, beta)
 
 
@@ -782,6 +864,8 @@ class CIWAE(IWAE):
     def __init__(self, n_hidden, n_latent, learned_prior: bool = True, **kwargs):
         self.KIND = _abi.KIND_CIWAE if learned_prior else _abi.KIND_CIWAE_STD
         self._learned_prior = learned_prior
+        if not learned_prior:
+            self.TERM_KEYS = ("lpxzy", "lpz", "lqzxy")      # tasks/task05.py keeps the key "lpz" (N(0,1) prior)
         super().__init__(n_hidden, n_latent, **kwargs)
 
     def _make_config(self, n_hidden, n_latent, n_x, n_cond):
@@ -809,14 +893,14 @@ class CIWAE(IWAE):
     def val_step(self, x, y, n_samples, beta):
         return self.call(x, y, n_samples, beta)
 
-    def train_step(self, x, y, n_samples, beta, optimizer, objective="vae_elbo", eps=None, seed=None):
+    def train_step(self, x, y, n_samples, beta, optimizer, objective="vae_elbo", eps=None, seed=None, materialize=()):
         oid = self._objective_id(objective, self._OBJECTIVES)
         k = int(n_samples)
-        bufs = self._train(x, y, k, beta, optimizer, oid, eps, None, seed)
+        bufs = self._train(x, y, k, beta, optimizer, oid, eps, None, seed, materialize=materialize)
         return self._result(bufs, k, beta)
 
 
-    def sample(self, z, y, seed=0):
+    def sample(self, z, y, seed=None):
         """CIWAE.sample(z, y) (task04.py:190-209 / task05.py:185-199): every row of z decoded under the single
         label y; with the learned prior z is first mapped through p(z|y): z_new = loc + scale * z."""
         z = self._dev(z)
@@ -826,10 +910,14 @@ class CIWAE(IWAE):
             onehot = torch.zeros(1, self._cfg.n_cond, device=self.device, dtype=_F32)
             onehot[0, int(label)] = 1.0
             mu, sd = self._block(_abi.BLOCK_PRIOR, onehot, self._d1)
-            rows = (mu + sd * rows).contiguous()
+            moved = self._alloc(rows.shape[0], 1, self._d1)                 # z_new = loc + scale * z (task04.py:196)
+            with torch.cuda.device(self.device):
+                check(lib.iwae_normal_sample(_ptr(mu), _ptr(sd), _ptr(rows.contiguous()), 1, rows.shape[0], self._d1, 0, 1,
+                                             _ptr(moved), _stream_ptr()), "iwae_normal_sample")
+            rows = moved.view(rows.shape[0], self._d1)
         yv = torch.full((rows.shape[0],), label, device=self.device, dtype=_F32)
         logits, _ = self._decode(rows, yv, None, want_logits=True)
-        return self._bernoulli(logits.tensor.view(*z.shape[:-1], self._cfg.n_x), seed)
+        return self._bernoulli(logits.tensor.view(*z.shape[:-1], self._cfg.n_x), self._next_seed(seed))
 
 class BasicBlock:
     """iwae1.BasicBlock(n_hidden, n_latent) as tasks/task04.py:108 constructs it directly.  In this

@@ -304,7 +304,8 @@ def ciwae_call(p, x, y, n_samples: int, beta: float = 1.0, eps=None, learned_pri
     res = _objectives(log_w)
     res["vae_elbo_kl"] = torch.mean(lpxzy) - beta * torch.mean(kl)
     res["snis_z"] = torch.sum(res["al"][:, :, None] * z, dim=0)
-    res.update(z=z, logits=logits, lpxzy=lpxzy, lpzy=lpzy, lqzxy=lqzxy, q_mu=mu, q_std=std, kl=kl)
+    res.update(z=z, logits=logits, lpxzy=lpxzy, lqzxy=lqzxy, q_mu=mu, q_std=std, kl=kl)
+    res["lpzy" if learned_prior else "lpz"] = lpzy                    # task04.py:169 'lpzy' / task05.py:167 'lpz'
     return res
 
 

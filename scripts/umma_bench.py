@@ -2,7 +2,8 @@
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from iwae_b200._abi import lib, check
+from iwae_b200._abi import diag_lib, check_diag as check
+lib = diag_lib()
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 for nctas in (1, 148):

@@ -4,7 +4,8 @@ import ctypes as C, os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1:
     import torch
-    from iwae_b200._abi import lib, check
+    from iwae_b200._abi import diag_lib, check_diag as check
+    lib = diag_lib()
     out = torch.zeros(148, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for reps in (4, 8, 14, 26, 52):

@@ -69,7 +69,7 @@ def run_case(oracle, c):
         learned = kind == "ciwae"
         fn = lambda p_, x_, y_, k_, b_, e_: oracle.ciwae_call(p_, x_, y_, k_, b_, e_, learned_prior=learned)
         g, r = oracle.grads_objective(fn, p, "iwae_elbo", x, case["y"], c["k"], 1.0, e1)
-        keys = ["lpxzy", "lpzy", "lqzxy", "al", "snis_z", "iwae_elbo_per_example", "kl"]
+        keys = ["lpxzy", "lpzy" if learned else "lpz", "lqzxy", "al", "snis_z", "iwae_elbo_per_example", "kl"]
         scal = ["vae_elbo", "vae_elbo_kl", "iwae_elbo", "iwae_eq14"]
     for k_ in keys + scal:
         out[k_] = r[k_].detach().numpy()

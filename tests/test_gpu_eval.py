@@ -43,7 +43,8 @@ def _case(oracle, kind, B, scale=1.0, seed=51):
 @pytest.mark.parametrize("N,K", [(16, 16), (112, 112), (96, 208), (256, 64), (48, 100), (112, 7)])
 def test_umma_descriptor_selftest(N, K):
     """One tcgen05.mma chain through the exact operand staging of the fused kernel."""
-    from iwae_b200._abi import lib, check
+    from iwae_b200._abi import diag_lib, check_diag as check
+    lib = diag_lib()               # libiwae_b200_diag.so: the unit-test hook is not part of the product library
     rs = np.random.RandomState(N * 1000 + K)
     A = rs.randn(128, K).astype(np.float32)
     Bm = rs.randn(N, K).astype(np.float32)

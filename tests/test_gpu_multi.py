@@ -34,7 +34,7 @@ def _worker(rank, world, port, out_path):
         assert init_comm(m) == (rank, world)
         o, o1 = ib.Adam(1e-3, epsilon=1e-4), ib.Adam(1e-3, epsilon=1e-4)
         for t in range(5):          # call 1 eager, call 2 captures the graph (all-reduce inside), calls 3.. replay it
-            xb = X[t * 20:(t + 1) * 20]
+            xb = X[(t % 3) * 20:(t % 3 + 1) * 20]
             dp_train_step(m, xb, 50, 1.0, o, obj, seed=100 + t)
             if kind == "iwae2":
                 m1.train_step(xb, 50, 1.0, o1, objective="iwae_elbo", seed=100 + t)
