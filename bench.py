@@ -505,11 +505,20 @@ def bench_train(ib, torch, dist, rank, world, dev, X, Y, bias, name, steps=1000,
            "note": "latency-bound (north_star): ~1.7 GFLOP per C2 step; fp32 FFMA kernels"}
     if res is not None:
         rec["last_iwae_elbo"] = float(res["iwae_elbo"])
+    # tear the context (and its NCCL communicator) down at the same program point on every rank, not whenever the
+    # garbage collector gets to it (models hold reference cycles)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    model.close()
     return rec
 
 
 def main():
     args = parse()
+    if os.environ.get("IWAE_BENCH_DEBUG"):        # where is a rank stuck: dump every thread's stack after N seconds and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["IWAE_BENCH_DEBUG"]), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -297,7 +297,11 @@ class IWAE:
         self.encoder = _Encoder(self, "encoder")
         self.decoder = _Decoder(self, "decoder")
 
-    def __del__(self):
+    def close(self):
+        """Destroy the library context now (scratch arena, packed weights, CUDA graph, NCCL communicator).  Models hold
+        reference cycles, so without this the context is freed whenever the cyclic GC runs - and destroying an NCCL
+        communicator is a blocking call that every rank must reach at the same point of its program: multi-rank
+        callers close their models explicitly (bench.py, tests)."""
         ctx = getattr(self, "_ctx", None)
         if ctx is not None and ctx.value:
             try:
@@ -305,6 +309,9 @@ class IWAE:
             except Exception:
                 pass
             self._ctx = C.c_void_p()
+
+    def __del__(self):
+        self.close()
 
     # ---- weights --------------------------------------------------------------------------------
     def init_weights(self, rs: np.random.RandomState, out_bias: Optional[np.ndarray] = None, scale: float = 1.0):

@@ -42,6 +42,9 @@ def _worker(rank, world, port, out_path):
                 m1.train_step(xb, 50, 1.0, o1, seed=100 + t)
         report[kind] = float((m.params - m1.params).abs().max())
         assert o.iterations == o1.iterations == 5
+        torch.cuda.synchronize()
+        dist.barrier()
+        m.close()                   # the communicator goes away at the same point on both ranks
     # sharded evaluation: per-example values identical to the single-GPU call, bit for bit
     m = ib.IWAE2([200, 100], [100, 50], seed=1, out_bias=bias)
     mean, per = model_llh_sharded(m, X[:37], 300, seed=11, gather=True)
