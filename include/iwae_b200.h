@@ -122,6 +122,14 @@ int iwae_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const floa
                   int64_t N, int32_t k, uint64_t seed, int64_t img_offset, int32_t precision,
                   float* out_per_example, double* out_sum, void* stream);
 
+/* Same estimator through the fused tensor-core kernel with INJECTED noise instead of Philox (north_star: "an injected-eps
+ * mode takes an externally supplied eps tensor"): eps1 [k,N,d1], eps2 [k,N,d2] (IWAE2 only, else NULL), sample-major like
+ * qzx.sample(k) (src/iwae1.py:59).  The parity tests feed the oracle the very same tensors, so the comparison does not
+ * rest on the restatement of the device RNG.  precision: IWAE_PREC_TC_F16 or IWAE_PREC_TC_F16_FAST. */
+int iwae_llh_eval_eps(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
+                      const float* eps1, const float* eps2, int32_t precision, float* out_per_example, double* out_sum,
+                      void* stream);
+
 /* Monitoring pass (model.val_step on the whole test set, main.py:152) through the same
  * fused kernel: per-example logmeanexp_k(log_w) AND mean_k(log_w) for N images at beta = 1, i.e. the
  * iwae_elbo / vae_elbo the training loop prints, without materialising [k,B,784].

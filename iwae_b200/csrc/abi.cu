@@ -448,6 +448,20 @@ static int llh_eval_impl(iwae_ctx* ctx, const float* params, const float* x, con
   return 0;
 }
 
+extern "C" int iwae_llh_eval_eps(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int32_t k,
+                                 const float* eps1, const float* eps2, int32_t precision, float* out_per_example,
+                                 double* out_sum, void* stream) {
+  IWAE_REQUIRE(ctx && params && x && eps1 && out_per_example, "iwae_llh_eval_eps: null argument");
+  IWAE_REQUIRE(N > 0 && k > 0, "iwae_llh_eval_eps: bad N=%lld k=%d", (long long)N, k);
+  IWAE_REQUIRE(precision == IWAE_PREC_TC_F16 || precision == IWAE_PREC_TC_F16_FAST,
+               "iwae_llh_eval_eps: tensor-core precisions only (iwae_forward takes injected noise on the fp32 path)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ctx->arena.reset();
+  IWAE_TRY(tc_llh_eval(ctx, params, x, y, N, k, 0, 0, precision == IWAE_PREC_TC_F16_FAST, out_per_example, nullptr, st, eps1, eps2));
+  if (out_sum) IWAE_TRY(sum_to_double(out_per_example, N, out_sum, 0, st));
+  return 0;
+}
+
 extern "C" int iwae_set_params_version(iwae_ctx* ctx, uint64_t version) {
   IWAE_REQUIRE(ctx, "iwae_set_params_version: null context");
   ctx->params_version = version;

@@ -196,6 +196,10 @@ struct EvalArgs {
   int64_t n_tiles;
   int tiles_per_img, rows_per_tile, k;
   uint64_t seed; int64_t img_offset;
+  // injected-eps mode (parity vehicle: the oracle is fed the SAME tensors, no dependence on the RNG restatement):
+  const float* eps1;           // [k, n_images, d1] or null (Philox)
+  const float* eps2;           // [k, n_images, d2] or null
+  int64_t n_images;
   long long* trace;            // debug timeline (IWAE_TC_TRACE=<file>): [cta<4][role<3][512] (tag, clock64) pairs, else null
 };
 
@@ -341,7 +345,8 @@ __device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int
 }
 
 // TRACE: the timeline instrumentation (IWAE_TC_TRACE) is compiled into a separate instantiation
-template <bool FAST, bool TRACE>
+// INJECT: the N(0,1) noise is read from args.eps1 / args.eps2 instead of being drawn in registers
+template <bool FAST, bool TRACE, bool INJECT>
 __global__ void
 #if IWAE_PAIR
 __cluster_dims__(2, 1, 1)
@@ -527,6 +532,17 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
       const int tin = (int)(tile - img32 * (uint32_t)args.tiles_per_img);
       const int s = tin * args.rows_per_tile + row;                 // sample index of this row
       const bool valid = tile_ok && (row < args.rows_per_tile) && (s < args.k);
+      // the 8 normals of dims 8g..8g+7 of this row in noise stream 1 (first latent, d = d1) or 2 (second latent)
+      auto noise8 = [&](uint32_t stream_id, uint32_t g, int d, float (&e)[8]) {
+        if (INJECT) {
+          const float* src = (stream_id == 1u ? args.eps1 : args.eps2) +
+                             ((int64_t)min(s, args.k - 1) * args.n_images + img) * d + 8 * (int)g;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = (8 * (int)g + i < d) ? __ldg(src + i) : 0.f;
+        } else {
+          normal8<FAST>(args.seed, stream_id, (uint32_t)(args.img_offset + img), (uint32_t)s, g, e);
+        }
+      };
 
       // ---- per-image constants into smem (only when the image changes)
       if (img32 != prev_img) {
@@ -569,7 +585,6 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
 
       // ---- stage 0: z1 = mu + std*eps (A.2), lq1, lpz; fp16 z1 | onehot(y) | 1 | 0.. into bufZ
       {
-        const uint32_t gimg = (uint32_t)(args.img_offset + img);
         const int one_col = d1 + P.nc;
         float e1sum = 0.f, z1sum = 0.f;
         // complete group of 8 latent dims (FAST): no per-element predicates, vector constant loads
@@ -598,8 +613,8 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           // generator is a long dependent chain - 10 rounds - so one chain alone issues at ~0.25 IPC)
           for (; k0 + 24 <= d1_full; k0 += 32) {
             float ea[8], eb[8], va[8], vb[8];
-            normal8<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3), ea);
-            normal8<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3) + 2u, eb);
+            noise8(1u, (uint32_t)(k0 >> 3), d1, ea);
+            noise8(1u, (uint32_t)(k0 >> 3) + 2u, d1, eb);
             full_group(k0, ea, va);
             full_group(k0 + 16, eb, vb);
           }
@@ -608,12 +623,12 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           float v[8];
           if (FAST && k0 < d1_full) {
             float ea[8];
-            normal8<true>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3), ea);
+            noise8(1u, (uint32_t)(k0 >> 3), d1, ea);
             full_group(k0, ea, v);
             continue;
           } else {
             float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (k0 < d1) normal8<FAST>(args.seed, 1u, gimg, (uint32_t)s, (uint32_t)(k0 >> 3), e);
+            if (k0 < d1) noise8(1u, (uint32_t)(k0 >> 3), d1, e);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = k0 + i;
@@ -700,8 +715,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8]
             // (FAST: the log-std head is pre-scaled by log2(e) at pack time).
             // z2 = mu2 + std2*eps2 (iwae2.py:65); one 16-byte A-operand row segment per group.
-            const uint32_t gimg = (uint32_t)(args.img_offset + img);
-            float e2sum = 0.f, z2sum = 0.f, lgsum = 0.f;
+                float e2sum = 0.f, z2sum = 0.f, lgsum = 0.f;
             for (int g8 = 8 * half; g8 < Ly.next_kpad; g8 += 16) {
               float v[8];
               if (FAST && g8 + 8 <= cnt) {
@@ -709,7 +723,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                 uint32_t r[16];
                 tmem_ld16(tbase + 2 * g8, r);
                 float e[8];
-                normal8<true>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 3), e);
+                noise8(2u, (uint32_t)((off + g8) >> 3), P.d2, e);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -724,7 +738,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                 tmem_ld16(tbase + 2 * g8, r);
                 tmem_ld_wait();
                 float e[8];
-                normal8<FAST>(args.seed, 2u, gimg, (uint32_t)s, (uint32_t)((off + g8) >> 3), e);
+                noise8(2u, (uint32_t)((off + g8) >> 3), P.d2, e);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const int j = g8 + i;
@@ -1172,7 +1186,8 @@ void tc_release(iwae_ctx* ctx) {
 }
 
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k, uint64_t seed,
-                int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st) {
+                int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st, const float* eps1,
+                const float* eps2) {
   const ModelP& m = ctx->model;
   const iwae_config& c = m.cfg;
   IWAE_REQUIRE(!m.cond() || y, "tensor-core path: CIWAE needs labels");
@@ -1207,6 +1222,8 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   a.n_tiles = N * a.tiles_per_img;
   IWAE_REQUIRE(a.n_tiles < ((int64_t)1 << 31), "tensor-core path: too many tiles in one call (N * ceil(k/128) must be < 2^31)");
   a.k = k; a.seed = seed; a.img_offset = img_offset;
+  a.eps1 = eps1; a.eps2 = eps2; a.n_images = N;
+  IWAE_REQUIRE(!eps1 || !m.two_layer() || eps2, "tensor-core path: injected noise needs eps2 for two stochastic layers");
   const size_t need = (size_t)a.n_tiles * sizeof(float2);
   if (tp.partial_cap < need) {
     if (tp.partial) CUDA_TRY(cudaFree(tp.partial));
@@ -1226,13 +1243,16 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   }
 
   const size_t smem = sizeof(tc::SmemLayout);     // (the dynamic window is 128-byte aligned: no static shared memory in this kernel)
-  auto kern = a.trace ? (fast ? tc::iwae_eval_tc_kernel<true, true> : tc::iwae_eval_tc_kernel<false, true>)
-                      : (fast ? tc::iwae_eval_tc_kernel<true, false> : tc::iwae_eval_tc_kernel<false, false>);
+  using KernelT = void (*)(const tc::EvalArgs, const tc::Program);
+  KernelT kern;
+  if (eps1) kern = fast ? tc::iwae_eval_tc_kernel<true, false, true> : tc::iwae_eval_tc_kernel<false, false, true>;
+  else if (a.trace) kern = fast ? tc::iwae_eval_tc_kernel<true, true, false> : tc::iwae_eval_tc_kernel<false, true, false>;
+  else kern = fast ? tc::iwae_eval_tc_kernel<true, false, false> : tc::iwae_eval_tc_kernel<false, false, false>;
   if (!tp.attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(tc::iwae_eval_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelT all[6] = {tc::iwae_eval_tc_kernel<true, false, false>, tc::iwae_eval_tc_kernel<false, false, false>,
+                      tc::iwae_eval_tc_kernel<true, true, false>,  tc::iwae_eval_tc_kernel<false, true, false>,
+                      tc::iwae_eval_tc_kernel<true, false, true>,  tc::iwae_eval_tc_kernel<false, false, true>};
+    for (KernelT f : all) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tp.attr_set = true;
   }
   // one CTA group (a pair of CTAs on the two SMs of a TPC) per unit of PAIR tiles, at most CTAS_PER_SM CTAs per SM

@@ -132,9 +132,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
 __device__ __forceinline__ uint32_t make_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
+// two fp32 -> packed fp16x2 (a in the low half), round-to-nearest, SATURATING to +-65504: an operand element that
+// overflows fp16 must not become inf (inf * 0 = NaN in the next GEMM).  Only latent samples z = mu + std*eps can get
+// there (std = e^a with a large pre-activation; seen with Glorot x3 weights) - such a sample has a log-weight of
+// -1e9 and does not contribute, and its log-density terms are computed from the unrounded fp32 value.
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 }  // namespace tc

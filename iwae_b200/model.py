@@ -632,14 +632,28 @@ class IWAE:
             return "tc_f16_fast" if self.tc_supported() else "fp32"
         return precision
 
-    def llh(self, x, n_samples=5000, y=None, precision="auto", seed=None, img_offset=0):
+    def llh(self, x, n_samples=5000, y=None, precision="auto", seed=None, img_offset=0, eps=None, eps2=None):
         """Per-example log-mean-exp of `n_samples` importance weights for every row of x (device
-        resident), and their fp64 sum: returns (per_example [N] tensor, sum as 0-dim fp64 tensor)."""
+        resident), and their fp64 sum: returns (per_example [N] tensor, sum as 0-dim fp64 tensor).
+        `eps` [k,N,d1] (and `eps2` [k,N,d2]) inject the N(0,1) noise instead of the device Philox generator."""
         precision = self._precision(precision)
         x, y = self._check_x(x, y)
         N = x.shape[0]
         per = self._alloc(max(N, 1))[:N]
         total = torch.zeros((), dtype=torch.float64, device=self.device)
+        if eps is not None:
+            k = int(n_samples)
+            eps = self._check_eps(eps, k, N, self._d1, "eps")
+            eps2 = self._check_eps(eps2, k, N, self._d2, "eps2") if self._d2 else None
+            if precision == "fp32":      # the fp32 kernels take injected noise through IWAE.call
+                r = self._forward(x, y, k, 1.0, ("iwae",), eps, eps2)
+                return r["iwae"], r["iwae"].double().sum()
+            with torch.cuda.device(self.device):
+                self._declare_params_version()
+                check(lib.iwae_llh_eval_eps(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), N, k, _ptr(eps), _ptr(eps2),
+                                            _abi.PRECISIONS[precision], _ptr(per), _ptr(total), _stream_ptr()),
+                      "iwae_llh_eval_eps")
+            return per, total
         with torch.cuda.device(self.device):
             self._declare_params_version()
             check(lib.iwae_llh_eval(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), N, int(n_samples),
