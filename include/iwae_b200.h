@@ -114,6 +114,14 @@ int iwae_forward(iwae_ctx* ctx, const float* params, const float* x, const float
                  int32_t B, int32_t k, float beta, const float* eps1, const float* eps2,
                  uint64_t seed, int64_t img_offset, const iwae_outputs* outs, void* stream);
 
+/* The same call with the fused tensor-core kernel as the engine (model.val_step on the whole test set at k = n_samples,
+ * main.py:152; generate_and_save_posteriors' call(Xtest, 10), src/iwae1.py:207): every output of iwae_forward except
+ * `logits` and `dreg` - per-row terms, log_w, al, per-example ELBOs, SNIS means, z1 / z2, q_mu / q_std, scalars - with
+ * no [k,B,784] tensor ever materialised.  Philox noise only.  precision: IWAE_PREC_TC_F16 or IWAE_PREC_TC_F16_FAST. */
+int iwae_forward_tc(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,
+                    float beta, uint64_t seed, int64_t img_offset, int32_t precision, const iwae_outputs* outs,
+                    void* stream);
+
 /* Replaces the k=5000 test-set loop of main.py:170-184 (+ utils.MyMetric, src/utils.py:30-45):
  * per-example logmeanexp_k(log_w) for N images, and their fp64 sum (mean = sum / N is the LLH).
  *   x [N,n_x]; y [N] or NULL; out_per_example [N] or NULL; out_sum: one double on the device.

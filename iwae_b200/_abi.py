@@ -54,6 +54,7 @@ def _load():
         "iwae_param_layout": (C.c_int, [vp, P(i64), P(i32), P(i32)]),
         "iwae_layout_for_config": (C.c_int, [P(Config), P(i64), P(i32), P(i64), P(i32), P(i32)]),
         "iwae_forward": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, vp, vp, u64, i64, P(Outputs), vp]),
+        "iwae_forward_tc": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, u64, i64, i32, P(Outputs), vp]),
         "iwae_llh_eval": (C.c_int, [vp, vp, vp, vp, i64, i32, u64, i64, i32, vp, vp, vp]),
         "iwae_llh_eval_eps": (C.c_int, [vp, vp, vp, vp, i64, i32, vp, vp, i32, vp, vp, vp]),
         "iwae_monitor_eval": (C.c_int, [vp, vp, vp, vp, i64, i32, u64, i64, i32, vp, vp, vp, vp]),
@@ -122,7 +123,7 @@ EXPORTS = ("iwae_last_error", "iwae_version", "iwae_create", "iwae_destroy", "iw
            "iwae_param_layout", "iwae_layout_for_config", "iwae_forward", "iwae_llh_eval", "iwae_llh_eval_host",
            "iwae_grads", "iwae_adam_step", "iwae_train_step", "iwae_philox_normal", "iwae_decode", "iwae_sir",
            "iwae_softmax_f32", "iwae_bernoulli_sample", "iwae_launch_count", "iwae_llh_kernel_ms", "iwae_set_params_version", "iwae_comm_unique_id", "iwae_comm_init", "iwae_comm_destroy", "iwae_comm_info",
-           "iwae_allreduce_sum_f32", "iwae_allreduce_sum_f64", "iwae_dp_train_step", "iwae_llh_eval_eps", "iwae_monitor_eval", "iwae_bernoulli_log_prob", "iwae_normal_log_prob",
+           "iwae_allreduce_sum_f32", "iwae_allreduce_sum_f64", "iwae_dp_train_step", "iwae_forward_tc", "iwae_llh_eval_eps", "iwae_monitor_eval", "iwae_bernoulli_log_prob", "iwae_normal_log_prob",
            "iwae_normal_sample", "iwae_bernoulli_sample_logits", "iwae_posterior_grid",
            "iwae_block_forward")
 

@@ -367,6 +367,67 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   return 0;
 }
 
+// IWAE.call / val_step with the fused tensor-core kernel as the engine: the kernel (TERMS mode) writes the per-row
+// log-density terms and the latent samples, the same reduction kernels as the fp32 path turn them into log_w, al, the
+// ELBO variants, SNIS means and the batch scalars.  logits [k,B,784] never exist (not available from this entry point:
+// ask iwae_forward for them); DReG's extra outputs likewise.
+extern "C" int iwae_forward_tc(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,
+                               float beta, uint64_t seed, int64_t img_offset, int32_t precision, const iwae_outputs* o,
+                               void* stream) {
+  IWAE_REQUIRE(ctx && params && x && o, "iwae_forward_tc: null argument");
+  IWAE_REQUIRE(B > 0 && k > 0, "iwae_forward_tc: B and k must be positive (B=%d k=%d)", B, k);
+  IWAE_REQUIRE(precision == IWAE_PREC_TC_F16 || precision == IWAE_PREC_TC_F16_FAST, "iwae_forward_tc: tensor-core precisions only");
+  IWAE_REQUIRE(!o->logits && !o->dreg, "iwae_forward_tc: logits / dreg are not produced by the fused kernel (use iwae_forward)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ModelP& m = ctx->model;
+  const iwae_config& c = m.cfg;
+  Arena& ar = ctx->arena;
+  ar.reset();
+  const int64_t R = (int64_t)B * k;
+  const int d1 = c.d1, d2 = c.d2;
+  // buffers that must outlive tc_llh_eval's own arena use: take them first (the arena only grows within a call)
+  Fwd f;
+  f.B = B; f.k = k; f.R = R;
+  IWAE_TRY(pick(ar, o->q_mu, (size_t)B * d1, &f.mu1)); IWAE_TRY(pick(ar, o->q_std, (size_t)B * d1, &f.std1));
+  IWAE_TRY(pick(ar, o->lpxz, (size_t)R, &f.lpxz)); IWAE_TRY(pick(ar, o->lpz, (size_t)R, &f.lpz));
+  IWAE_TRY(pick(ar, o->lq1, (size_t)R, &f.lq1));
+  const bool want_snis1 = o->snis_z1 != nullptr, want_snis2 = m.two_layer() && o->snis_z2 != nullptr;
+  if (o->z1 || want_snis1) IWAE_TRY(pick(ar, o->z1, (size_t)R * d1, &f.z1));
+  if (m.two_layer()) {
+    IWAE_TRY(pick(ar, o->lq2, (size_t)R, &f.lq2)); IWAE_TRY(pick(ar, o->lp12, (size_t)R, &f.lp12));
+    if (o->z2 || want_snis2) IWAE_TRY(pick(ar, o->z2, (size_t)R * d2, &f.z2));
+  }
+  float* per; IWAE_TRY(ar.get(&per, (size_t)B));
+  TcTerms t = {f.lpxz, f.lpz, f.lq1, f.lq2, f.lp12, f.z1, f.z2, f.mu1, f.std1};
+  IWAE_TRY(tc_llh_eval(ctx, params, x, y, B, k, seed, img_offset, precision == IWAE_PREC_TC_F16_FAST, per, nullptr, st, nullptr,
+                       nullptr, &t));
+  if ((o->kl || o->scalars) && !m.two_layer()) {
+    IWAE_TRY(pick(ar, o->kl, (size_t)B, &f.kl));
+    IWAE_TRY(kl_rows(f.mu1, f.std1, B, d1, f.kl, st));                                      // iwae1.py:116
+  }
+  LogwArgs la;
+  la.B = B; la.k = k; la.beta = beta; la.two_layer = m.two_layer() ? 1 : 0;
+  la.lpxz = f.lpxz; la.lpz = f.lpz; la.lq1 = f.lq1; la.lq2 = f.lq2; la.lp12 = f.lp12;
+  la.z1 = f.z1; la.z2 = f.z2; la.d1 = d1; la.d2 = d2;
+  f.iwae = o->iwae; f.vae = o->vae; f.eq14 = o->eq14;
+  if (o->scalars) {
+    if (!f.iwae) IWAE_TRY(ar.get(&f.iwae, (size_t)B));
+    if (!f.vae) IWAE_TRY(ar.get(&f.vae, (size_t)B));
+    if (!f.eq14) IWAE_TRY(ar.get(&f.eq14, (size_t)B));
+  }
+  la.log_w = o->log_w; la.al = o->al; la.iwae = f.iwae; la.vae = f.vae; la.eq14 = f.eq14;
+  la.snis1 = want_snis1 ? o->snis_z1 : nullptr; la.snis2 = want_snis2 ? o->snis_z2 : nullptr;
+  IWAE_TRY(logw_reduce(la, st));
+  if (o->scalars) {
+    ScalarArgs sa;
+    sa.B = B; sa.R = R; sa.beta = beta;
+    sa.iwae = f.iwae; sa.vae = f.vae; sa.eq14 = f.eq14; sa.kl = f.kl;
+    sa.lpxz = f.lpxz; sa.lpz = f.lpz; sa.lq1 = f.lq1; sa.out = o->scalars;
+    IWAE_TRY(finalize_scalars(sa, st));
+  }
+  return 0;
+}
+
 extern "C" int iwae_forward(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,
                             float beta, const float* eps1, const float* eps2, uint64_t seed, int64_t img_offset,
                             const iwae_outputs* outs, void* stream) {

@@ -229,9 +229,12 @@ int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st);
 
 // ---- fused tcgen05 evaluation (eval_tc.cu) ----
 int tc_pack_weights(iwae_ctx* ctx, const float* params, bool fast, cudaStream_t st);
+// TERMS mode of the fused kernel: per-row log-density terms [k,N], latent samples [k,N,d] and the per-image q(z1|x)
+// parameters [N,d1] (q_mu / q_std must be given; every other pointer may be null)
+struct TcTerms { float *lpxz, *prior, *lq1, *lq2, *lp12, *z1, *z2, *q_mu, *q_std; };
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k,
                 uint64_t seed, int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st,
-                const float* eps1 = nullptr, const float* eps2 = nullptr);
+                const float* eps1 = nullptr, const float* eps2 = nullptr, const TcTerms* terms = nullptr);
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
                   float* mu, float* sd, cudaStream_t st, float* l1_scratch = nullptr);
 // out[m, n] = act(sum_s partial[s][m, n] + bias[n])   (split-K forward, see dense_fwd in abi.cu)

@@ -180,6 +180,7 @@ struct Layer {
 struct Program {
   int nlayers, two_layer, cond, learned_prior;
   int d1, d2, nc, nx, kz_pad;  // kz_pad: K of the layers that read z1
+  int z1_lo;                   // 1: room for the fp16 "lo" halves of z1 (hi + lo = 22 bits) next to the operands, see stage 0
   Layer L[MAX_LAYERS];
 };
 
@@ -200,6 +201,10 @@ struct EvalArgs {
   const float* eps1;           // [k, n_images, d1] or null (Philox)
   const float* eps2;           // [k, n_images, d2] or null
   int64_t n_images;
+  // TERMS mode (the val_step / IWAE.call engine): per-row log-density terms [k, n_images] sample-major like the reference
+  // (src/iwae1.py:141-151, src/iwae2.py:154-167) and the latent samples [k, n_images, d]; any pointer may be null
+  float* term_lpxz; float* term_prior; float* term_lq1; float* term_lq2; float* term_lp12;
+  float* z1_out; float* z2_out;
   long long* trace;            // debug timeline (IWAE_TC_TRACE=<file>): [cta<4][role<3][512] (tag, clock64) pairs, else null
 };
 
@@ -223,6 +228,7 @@ struct __align__(16) SubTile {       // the CTA's 128-row tile
   float psd[D_MAX];            // learned prior: 1/std in FAST mode, std in precise mode
   float red[16];               // [0,4) max, [4,8) sum-exp, [8,16) per-warp constant partials
   float red_lw[4];             // per-quarter sums of log_w (monitoring)
+  float red_p[8];              // per-warp partial of sum_j log std of a learned prior (TERMS mode keeps it apart from red[8..16))
   // (the partial log-weights of the second column half of each row are parked in bufP, which is dead
   //  once the last layer's MMAs have retired: a 4th weight slab fits in the shared memory this frees)
   int label; int pad_[3];
@@ -345,8 +351,31 @@ __device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int
 }
 
 // TRACE: the timeline instrumentation (IWAE_TC_TRACE) is compiled into a separate instantiation
+// The five log-density terms of a row (sums over columns).  The evaluation needs only their signed sum (one register);
+// TERMS mode keeps them apart (five registers) and writes them per row.
+enum { T_LPXZ = 0, T_PRIOR = 1, T_LQ1 = 2, T_LQ2 = 3, T_LP12 = 4 };
+template <bool TERMS>
+struct RowAcc {
+  float v[TERMS ? 5 : 1];
+  __device__ __forceinline__ RowAcc() {
+#pragma unroll
+    for (int i = 0; i < (TERMS ? 5 : 1); ++i) v[i] = 0.f;
+  }
+  // term T of log_w = lpxz + prior + lp12 - lq1 - lq2
+  template <int T>
+  __device__ __forceinline__ void add(float x) {
+    if (TERMS) v[T] += x;
+    else v[0] += (T == T_LQ1 || T == T_LQ2) ? -x : x;
+  }
+  __device__ __forceinline__ float log_w() const {
+    if (TERMS) return v[T_LPXZ] + v[T_PRIOR] + v[TERMS ? T_LP12 : 0] - v[TERMS ? T_LQ1 : 0] - v[TERMS ? T_LQ2 : 0];
+    return v[0];
+  }
+};
+
 // INJECT: the N(0,1) noise is read from args.eps1 / args.eps2 instead of being drawn in registers
-template <bool FAST, bool TRACE, bool INJECT>
+// TERMS: per-row terms and latent samples are written out (RowAcc above)
+template <bool FAST, bool TRACE, bool INJECT, bool TERMS>
 __global__ void
 #if IWAE_PAIR
 __cluster_dims__(2, 1, 1)
@@ -384,6 +413,12 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
 #endif
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
+
+#ifdef IWAE_PHASE_SHIFT_NS
+  // Experiment: the second wave of CTA groups (co-resident with the first on the same SMs) starts half a tile late, so
+  // that the two resident CTAs of an SM run their MMA-heavy and their XU-heavy layers out of phase.
+  if (group >= n_groups / 2) __nanosleep(IWAE_PHASE_SHIFT_NS);
+#endif
 
   if (warp == 0) {
     // ===================== weight producer: one elected thread =====================
@@ -550,7 +585,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
       epi_bar_sync();
       for (int j = et; j < nx_pad; j += 256)
         T.sgn[j] = (j < nx) ? 1.f - 2.f * __ldg(args.x + img * nx + j) : 0.f;
-      float csum = 0.f;
+      float csum = 0.f, csum_p = 0.f;
       for (int j = et; j < d1; j += 256) {
         const float sd = __ldg(args.std1 + img * d1 + j);
         const float ls = logf(sd);
@@ -560,7 +595,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           const float ps = __ldg(args.pstd + img * d1 + j);
           const float lps = logf(ps);
           T.pmu[j] = __ldg(args.pmu + img * d1 + j); T.psd[j] = FAST ? 1.f / ps : ps;
-          csum -= lps;
+          if (TERMS) csum_p += lps; else csum -= lps;
         }
       }
       if (FAST) {
@@ -571,6 +606,11 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
         if (lane == 0) T.red[8 + (e_warp & 7)] = csum;
+        if (TERMS) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) csum_p += __shfl_xor_sync(0xffffffffu, csum_p, o);
+          if (lane == 0) T.red_p[e_warp & 7] = csum_p;
+        }
       }
       if (et == 0 && P.cond) T.label = (int)(unsigned char)(int)__ldg(args.y + img);
       epi_bar_sync();
@@ -581,7 +621,40 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
       // columns.  Precise mode adds log-probabilities term by term in TFP's op order; FAST mode
       // accumulates sums of squares / logs and applies the constants once (algebraically identical:
       // (z-mu)/sd == eps for a reparameterised sample).
-      float lw = 0.f;
+      RowAcc<TERMS> acc;
+      // latent samples of this row, for the TERMS outputs (fp32, before the fp16 rounding of the operand)
+      const int64_t out_row = (int64_t)min(s, args.k - 1) * args.n_images + img;
+      auto put_z = [&](float* base, int d, int k0, const float (&v)[8]) {
+        if (TERMS && base && valid) {
+          float* dstp = base + out_row * d + k0;
+          if (k0 + 8 <= d && (d & 3) == 0) {            // rows are 16-byte aligned: one full 32-byte sector per thread
+            *reinterpret_cast<float4*>(dstp) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dstp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else if (k0 + 8 <= d && (d & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) *reinterpret_cast<float2*>(dstp + i) = make_float2(v[i], v[i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (k0 + i < d) dstp[i] = v[i];
+          }
+        }
+      };
+
+      // Accurate modes (TERMS, or the libm-accurate tc_f16) keep z1 as an fp16 hi + lo PAIR for log p(z1|z2): that term
+      // amplifies the 2^-11 rounding of the operand copy by |z1 - mu| / sigma^2 (measured: 1.4e-3 relative on the single
+      // term at Glorot init).  The lo halves of dims 8g..8g+7 live in columns that are dead while q(z2|z1) / p(z1|z2)
+      // run: K groups 14..25 of the activation buffer (those layers use at most 112 of its 208 columns) for g < 12, and
+      // the zero-weight padding columns 104..111 of the z1 buffer for g = 12.
+      constexpr bool Z1LO = TERMS || !FAST;
+      auto put_lo = [&](int k0, const float (&v)[8]) {
+        if (Z1LO && P.z1_lo) {
+          float lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) lo[i] = v[i] - __half2float(__float2half_rn(v[i]));
+          const int g = k0 >> 3;
+          if (g < 12) store8(T.bufP, row, (14 + g) * 8, lo); else store8(T.bufZ, row, 104, lo);
+        }
+      };
 
       // ---- stage 0: z1 = mu + std*eps (A.2), lq1, lpz; fp16 z1 | onehot(y) | 1 | 0.. into bufZ
       {
@@ -606,6 +679,8 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             for (int i = 0; i < 8; ++i) z1sum = fmaf(v[i], v[i], z1sum);
           }
           store8(T.bufZ, row, k0, v);
+          put_lo(k0, v);
+          put_z(args.z1_out, d1, k0, v);
         };
         int k0 = 8 * half;
         if (FAST) {
@@ -642,14 +717,14 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                   else if (!P.two_layer) z1sum = fmaf(z, z, z1sum);
                 } else {
                   const float t = z / sd - m / sd;                         // TFP op order
-                  lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));       // - lq(z1|x)
+                  acc.template add<T_LQ1>(-0.5f * t * t - (LOG2PI_HALF_F + logf(sd)));       // lq(z1|x)
                   if (!P.two_layer) {
                     if (P.learned_prior) {
                       const float ps = T.psd[j];
                       const float tp = z / ps - T.pmu[j] / ps;
-                      lw += -0.5f * tp * tp - (LOG2PI_HALF_F + logf(ps));
+                      acc.template add<T_PRIOR>(-0.5f * tp * tp - (LOG2PI_HALF_F + logf(ps)));
                     } else {
-                      lw += -0.5f * z * z - LOG2PI_HALF_F;
+                      acc.template add<T_PRIOR>(-0.5f * z * z - LOG2PI_HALF_F);
                     }
                   }
                 }
@@ -663,8 +738,10 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             }
           }
           store8(T.bufZ, row, k0, v);
+          if (k0 < d1) put_lo(k0, v);
+          put_z(args.z1_out, d1, k0, v);
         }
-        if (FAST) lw += 0.5f * e1sum - 0.5f * z1sum;     // constants are added once per row at the end
+        if (FAST) { acc.template add<T_LQ1>(-0.5f * e1sum); acc.template add<T_PRIOR>(-0.5f * z1sum); }     // constants are added once per row at the end
       }
       fence_proxy_async();
       __syncwarp();
@@ -757,8 +834,8 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                       const float sd = expf(a) + 1e-6f;
                       const float z = e[i] * sd + m;
                       const float t = z / sd - m / sd;
-                      lw -= -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                // - lqz2z1 (iwae2.py:118)
-                      lw += -0.5f * z * z - LOG2PI_HALF_F;                              // + lpz2   (iwae2.py:116)
+                      acc.template add<T_LQ2>(-0.5f * t * t - (LOG2PI_HALF_F + logf(sd)));      // lqz2z1 (iwae2.py:118)
+                      acc.template add<T_PRIOR>(-0.5f * z * z - LOG2PI_HALF_F);                  // lpz2   (iwae2.py:116)
                       val = z;
                     }
                   } else if (j == cnt || j == cnt + 1) {
@@ -771,9 +848,10 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                 for (int i = 0; i < 8; ++i) v[i] = (g8 + i == cnt || g8 + i == cnt + 1) ? 1.f : 0.f;
               }
               store8(dst, row, g8, v);
+              put_z(args.z2_out, cnt, g8, v);
             }
-            // -lq2 + lpz2: the two log(2 pi)/2 constants cancel
-            if (FAST) lw += 0.5f * e2sum + LN2_F * lgsum - 0.5f * z2sum;
+            // -lq2 + lpz2: the two log(2 pi)/2 constants cancel (TERMS mode adds them back per term at the end)
+            if (FAST) { acc.template add<T_LQ2>(-0.5f * e2sum - LN2_F * lgsum); acc.template add<T_PRIOR>(-0.5f * z2sum); }
           } else if (kind == EPI_GLOGP) {
             // same column layout; log p(z1|z2) over dims off..off+cnt (iwae2.py:120), z1 re-read from bufZ
             float t2sum = 0.f, lssum = 0.f;
@@ -784,6 +862,23 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
               tmem_ld_wait();
               const uint4 za = *reinterpret_cast<const uint4*>(T.bufZ + (size_t)((off + g8) >> 3) * (TILE_M * 16) + row * 16);
               const uint32_t zw[4] = {za.x, za.y, za.z, za.w};
+              float zf[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
+                zf[i] = (i & 1) ? __high2float(h2) : __low2float(h2);
+              }
+              if (Z1LO && P.z1_lo) {
+                const int g = (off + g8) >> 3;
+                const uint8_t* lp = (g < 12) ? T.bufP + (size_t)(14 + g) * (TILE_M * 16) : T.bufZ + (size_t)13 * (TILE_M * 16);
+                const uint4 zl = *reinterpret_cast<const uint4*>(lp + row * 16);
+                const uint32_t lw4[4] = {zl.x, zl.y, zl.z, zl.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const __half2 h2 = *reinterpret_cast<const __half2*>(&lw4[i >> 1]);
+                  zf[i] += (i & 1) ? __high2float(h2) : __low2float(h2);
+                }
+              }
               const int nv = min(8, cnt - g8);       // valid dims of this group (8 except possibly the last)
               n_mine += nv;
               if (FAST) {
@@ -802,8 +897,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                   if (nv == 8) {                          // complete group (warp-uniform): no per-dim masks
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                      const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
-                      const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                      const float z = zf[i];
                       const float c = 1e-6f * inv[i];
                       const float t = (z - __uint_as_float(r[i])) * fmaf(-c, inv[i], inv[i]);
                       t2sum = fmaf(t, t, t2sum);
@@ -812,8 +906,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                   } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                      const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
-                      const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                      const float z = zf[i];
                       const float isd = fmaf(-1e-6f * inv[i], inv[i], inv[i]);
                       const float ls = fmaf(__uint_as_float(r[8 + i]), LN2_F, 1e-6f * inv[i]);
                       const float t = (i < nv) ? (z - __uint_as_float(r[i])) * isd : 0.f;
@@ -825,8 +918,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     if (i < nv) {
-                      const __half2 h2 = *reinterpret_cast<const __half2*>(&zw[i >> 1]);
-                      const float z = (i & 1) ? __high2float(h2) : __low2float(h2);
+                      const float z = zf[i];
                       const float sd = ex2_approx(__uint_as_float(r[8 + i])) + 1e-6f;
                       const float t = (z - __uint_as_float(r[i])) * rcp_approx(sd);
                       t2sum = fmaf(t, t, t2sum);
@@ -843,12 +935,12 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                     const float m = __uint_as_float(r[i]);
                     const float sd = expf(__uint_as_float(r[8 + i])) + 1e-6f;
                     const float t = z / sd - m / sd;
-                    lw += -0.5f * t * t - (LOG2PI_HALF_F + logf(sd));                     // + lpz1z2 (iwae2.py:120)
+                    acc.template add<T_LP12>(-0.5f * t * t - (LOG2PI_HALF_F + logf(sd)));         // lpz1z2 (iwae2.py:120)
                   }
                 }
               }
             }
-            if (FAST) lw += -0.5f * t2sum - lssum - (float)n_mine * LOG2PI_HALF_F;
+            if (FAST) acc.template add<T_LP12>(-0.5f * t2sum - lssum - (float)n_mine * LOG2PI_HALF_F);
           } else {
             // EPI_BERN: log p(x|z) = -sum_j softplus(s_j), s_j = (1-2x_j) l_j   (A.3 with x in {0,1})
             //   softplus(s) = max(s,0) + log(1 + e^-|s|),  max(s,0) = (s + |l|)/2,  |s| = |l|
@@ -878,17 +970,17 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
               bern_s += s0 + s1; bern_a += a0 + a1;
               bern_lg += lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
             } else {
-              float acc = 0.f;
+              float bsum = 0.f;
               for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float lgt = __uint_as_float(r[i]);
                   const float sg = T.sgn[off + g + i];
                   // padded columns (sgn 0, logit 0) must contribute nothing
-                  acc += (sg != 0.f) ? fmaxf(lgt * sg, 0.f) + log1pf(expf(-fabsf(lgt))) : 0.f;
+                  bsum += (sg != 0.f) ? fmaxf(lgt * sg, 0.f) + log1pf(expf(-fabsf(lgt))) : 0.f;
                 }
               });
-              lw -= acc;
+              acc.template add<T_LPXZ>(-bsum);
             }
           }
           tc_fence_before();
@@ -906,19 +998,49 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + 7);
         }
       }
-      if (FAST) lw -= LN2_F * (0.5f * (bern_s + bern_a) + bern_lg);
+      if (FAST) acc.template add<T_LPXZ>(-LN2_F * (0.5f * (bern_s + bern_a) + bern_lg));
 
       // ---- combine the two column halves of each row, then the tile's (max, sum exp) partial
       float* lwpart = reinterpret_cast<float*>(T.bufP);
-      if (half == 1) lwpart[row] = lw;
-      epi_bar_sync();
-      if (half == 0) {
-        lw += lwpart[row];
-        if (FAST) {
-          float c0 = (float)(nx_pad - nx) * LN2_F + (P.two_layer ? (float)d1 * LOG2PI_HALF_F : 0.f);
+      constexpr int NACC = TERMS ? 5 : 1;
+      if (half == 1) {
 #pragma unroll
-          for (int w = 0; w < 8; ++w) c0 += T.red[8 + w];
-          lw += c0;
+        for (int i = 0; i < NACC; ++i) lwpart[i * TILE_M + row] = acc.v[i];
+      }
+      epi_bar_sync();
+      float lw = 0.f;
+      if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc.v[i] += lwpart[i * TILE_M + row];
+        if (FAST) {
+          // constants of the FAST accumulation: padded pixel columns each added softplus(0) = ln 2 to the Bernoulli sum;
+          // lq1 lacks -sum_j log sd_j - d1 log(2 pi)/2, a first-layer prior lacks -d1 log(2 pi)/2 (and a learned one
+          // -sum_j log psd_j), lq2 and lpz2 lack -d2 log(2 pi)/2 each.  In the signed sum most of them cancel.
+          float cq = 0.f, cp = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { cq += T.red[8 + w]; if (TERMS) cp += T.red_p[w]; }
+          if (TERMS) {
+            acc.v[T_LPXZ] += (float)(nx_pad - nx) * LN2_F;
+            acc.v[TERMS ? T_LQ1 : 0] += -cq - (float)d1 * LOG2PI_HALF_F;
+            if (P.two_layer) {
+              acc.v[T_PRIOR] += -(float)P.d2 * LOG2PI_HALF_F;
+              acc.v[TERMS ? T_LQ2 : 0] += -(float)P.d2 * LOG2PI_HALF_F;
+            } else {
+              acc.v[T_PRIOR] += -cp - (float)d1 * LOG2PI_HALF_F;
+            }
+          } else {
+            acc.v[0] += (float)(nx_pad - nx) * LN2_F + (P.two_layer ? (float)d1 * LOG2PI_HALF_F : 0.f) + cq;
+          }
+        }
+        lw = acc.log_w();
+        if (TERMS && valid) {
+          if (args.term_lpxz) args.term_lpxz[out_row] = acc.v[T_LPXZ];
+          if (args.term_prior) args.term_prior[out_row] = acc.v[T_PRIOR];
+          if (args.term_lq1) args.term_lq1[out_row] = acc.v[TERMS ? T_LQ1 : 0];
+          if (P.two_layer) {
+            if (args.term_lq2) args.term_lq2[out_row] = acc.v[TERMS ? T_LQ2 : 0];
+            if (args.term_lp12) args.term_lp12[out_row] = acc.v[TERMS ? T_LP12 : 0];
+          }
         }
         if (!valid) lw = -INFINITY;
       }
@@ -1097,6 +1219,9 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P, bool fast)
   if (m.two_layer()) {
     IWAE_REQUIRE(c.h2 + 1 <= KP_MAX && c.d2 <= 56, "tensor-core path: needs h2 <= %d and d2 <= 56", KP_MAX - 1);
     const int kh2 = round16(c.h2 + 1), kd2 = round16(c.d2 + 1);
+    // hi + lo copy of z1 for log p(z1|z2): the lo halves need activation-buffer columns 112..207 (free while the
+    // 112-column-or-narrower layers of the two Gaussian blocks run) and z1-buffer columns 104..111 (padding)
+    pr.z1_lo = (kh2 <= 112 && kd2 <= 112 && kz == 112 && c.d1 + 2 <= 104) ? 1 : 0;
     tanh_layer(m.enc2.l1, 0, 1, kz);                                  // q(z2|z1) l1
     tanh_layer(m.enc2.l2, 1, 1, kh2);                                 //          l2
     gauss_layer(m.enc2, EPI_GSAMPLE, 1, 1, kh2, kd2, 56);             //          (mu2|std2) -> z2
@@ -1187,7 +1312,7 @@ void tc_release(iwae_ctx* ctx) {
 
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k, uint64_t seed,
                 int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st, const float* eps1,
-                const float* eps2) {
+                const float* eps2, const TcTerms* terms) {
   const ModelP& m = ctx->model;
   const iwae_config& c = m.cfg;
   IWAE_REQUIRE(!m.cond() || y, "tensor-core path: CIWAE needs labels");
@@ -1205,7 +1330,8 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
     xin = t; ldx = c.n_x + nc;
   }
   IWAE_TRY(ar.get(&h1, (size_t)N * c.h1)); IWAE_TRY(ar.get(&h2, (size_t)N * c.h1));
-  IWAE_TRY(ar.get(&mu1, (size_t)N * c.d1)); IWAE_TRY(ar.get(&std1, (size_t)N * c.d1));
+  if (terms) { mu1 = terms->q_mu; std1 = terms->q_std; IWAE_REQUIRE(mu1 && std1, "tensor-core path: terms mode needs q_mu / q_std buffers"); }
+  else { IWAE_TRY(ar.get(&mu1, (size_t)N * c.d1)); IWAE_TRY(ar.get(&std1, (size_t)N * c.d1)); }
   IWAE_TRY(block_fwd_f32(params, m.enc1, xin, ldx, N, h1, h2, mu1, std1, st));
   if (m.learned_prior()) {
     float* yoh;
@@ -1223,6 +1349,12 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   IWAE_REQUIRE(a.n_tiles < ((int64_t)1 << 31), "tensor-core path: too many tiles in one call (N * ceil(k/128) must be < 2^31)");
   a.k = k; a.seed = seed; a.img_offset = img_offset;
   a.eps1 = eps1; a.eps2 = eps2; a.n_images = N;
+  a.term_lpxz = a.term_prior = a.term_lq1 = a.term_lq2 = a.term_lp12 = a.z1_out = a.z2_out = nullptr;
+  if (terms) {
+    IWAE_REQUIRE(!eps1, "tensor-core path: terms mode takes Philox noise only");
+    a.term_lpxz = terms->lpxz; a.term_prior = terms->prior; a.term_lq1 = terms->lq1; a.term_lq2 = terms->lq2;
+    a.term_lp12 = terms->lp12; a.z1_out = terms->z1; a.z2_out = terms->z2;
+  }
   IWAE_REQUIRE(!eps1 || !m.two_layer() || eps2, "tensor-core path: injected noise needs eps2 for two stochastic layers");
   const size_t need = (size_t)a.n_tiles * sizeof(float2);
   if (tp.partial_cap < need) {
@@ -1245,13 +1377,15 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   const size_t smem = sizeof(tc::SmemLayout);     // (the dynamic window is 128-byte aligned: no static shared memory in this kernel)
   using KernelT = void (*)(const tc::EvalArgs, const tc::Program);
   KernelT kern;
-  if (eps1) kern = fast ? tc::iwae_eval_tc_kernel<true, false, true> : tc::iwae_eval_tc_kernel<false, false, true>;
-  else if (a.trace) kern = fast ? tc::iwae_eval_tc_kernel<true, true, false> : tc::iwae_eval_tc_kernel<false, true, false>;
-  else kern = fast ? tc::iwae_eval_tc_kernel<true, false, false> : tc::iwae_eval_tc_kernel<false, false, false>;
+  if (terms) kern = fast ? tc::iwae_eval_tc_kernel<true, false, false, true> : tc::iwae_eval_tc_kernel<false, false, false, true>;
+  else if (eps1) kern = fast ? tc::iwae_eval_tc_kernel<true, false, true, false> : tc::iwae_eval_tc_kernel<false, false, true, false>;
+  else if (a.trace) kern = fast ? tc::iwae_eval_tc_kernel<true, true, false, false> : tc::iwae_eval_tc_kernel<false, true, false, false>;
+  else kern = fast ? tc::iwae_eval_tc_kernel<true, false, false, false> : tc::iwae_eval_tc_kernel<false, false, false, false>;
   if (!tp.attr_set) {
-    KernelT all[6] = {tc::iwae_eval_tc_kernel<true, false, false>, tc::iwae_eval_tc_kernel<false, false, false>,
-                      tc::iwae_eval_tc_kernel<true, true, false>,  tc::iwae_eval_tc_kernel<false, true, false>,
-                      tc::iwae_eval_tc_kernel<true, false, true>,  tc::iwae_eval_tc_kernel<false, false, true>};
+    KernelT all[8] = {tc::iwae_eval_tc_kernel<true, false, false, false>, tc::iwae_eval_tc_kernel<false, false, false, false>,
+                      tc::iwae_eval_tc_kernel<true, true, false, false>,  tc::iwae_eval_tc_kernel<false, true, false, false>,
+                      tc::iwae_eval_tc_kernel<true, false, true, false>,  tc::iwae_eval_tc_kernel<false, false, true, false>,
+                      tc::iwae_eval_tc_kernel<true, false, false, true>,  tc::iwae_eval_tc_kernel<false, false, false, true>};
     for (KernelT f : all) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tp.attr_set = true;
   }

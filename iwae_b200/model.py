@@ -454,6 +454,35 @@ class IWAE:
         bufs["_x"], bufs["_y"], bufs["_eps1"], bufs["_eps2"] = x, y, eps1, eps2
         return bufs
 
+    def _forward_tc(self, x, y, k, beta, want, seed=None, img_offset=0, precision="tc_f16_fast"):
+        """The same outputs through the fused tensor-core kernel (iwae_forward_tc): per-row terms, log_w, al, ELBOs, SNIS
+        means, scalars - no [k,B,784] tensor is ever written (a full-test-set val_step at k=50 takes ~1.5 ms instead of
+        17 ms).  `logits` (and the noise-injection / DReG extras) are not available here."""
+        x, y = self._check_x(x, y)
+        B = x.shape[0]
+        if k <= 0:
+            raise ValueError("n_samples must be positive")
+        o, bufs = self._outputs(B, k, want)
+        seed = self._next_seed(seed)
+        with torch.cuda.device(self.device):
+            self._declare_params_version()
+            check(lib.iwae_forward_tc(self._ctx, _ptr(self.params), _ptr(x), _ptr(y), B, k, float(beta), seed,
+                                      int(img_offset), _abi.PRECISIONS[precision], C.byref(o), _stream_ptr()),
+                  "iwae_forward_tc")
+        bufs["_seed"] = seed
+        bufs["_x"], bufs["_y"], bufs["_eps1"], bufs["_eps2"] = x, y, None, None
+        return bufs
+
+    def _engine(self, precision, want, eps=None, eps2=None):
+        """Which kernels run a forward call: "fp32" (parity mode, takes injected noise, can write logits) or one of the
+        fused tensor-core modes.  "auto" picks the fused kernel when the architecture and the request allow it."""
+        tc_ok = self.tc_supported() and eps is None and eps2 is None and not ({"logits", "dreg"} & set(want))
+        if precision in (None, "auto"):
+            return "tc_f16_fast" if tc_ok else "fp32"
+        if precision != "fp32" and not tc_ok:
+            raise ValueError("the fused tensor-core forward takes Philox noise only and does not produce logits / dreg")
+        return precision
+
     def _decode(self, z, y, x, want_logits: bool):
         """decoder(z) and/or sum_j Bernoulli(logits).log_prob(x) for arbitrary z [..., d]
         (plot_task01.py:57-63; model.sample, iwae1.py:168-178)."""
@@ -522,6 +551,7 @@ class IWAE:
         kx, kp, kq = self.TERM_KEYS
         lazy = self._lazy(bufs, k, beta, ("z1", "logits"))
         res = Result()
+        res._seed = bufs.get("_seed")
         res["vae_elbo"] = DeviceValue(s[0])
         res["vae_elbo_kl"] = DeviceValue(s[1])
         res["iwae_elbo"] = DeviceValue(s[2])
@@ -542,18 +572,26 @@ class IWAE:
         res["vae_elbo_per_example"] = DeviceValue(bufs["vae"])
         res["log_w"] = DeviceValue(bufs["log_w"])
 
-    def call(self, x, n_samples, beta=1.0, eps=None, seed=None, img_offset=0):
-        """IWAE.call (src/iwae1.py:98-151)."""
+    def call(self, x, n_samples, beta=1.0, eps=None, seed=None, img_offset=0, precision="fp32"):
+        """IWAE.call (src/iwae1.py:98-151).  precision: "fp32" (default: the parity kernels), "auto" / "tc_f16" /
+        "tc_f16_fast" (the fused tensor-core kernel as the engine, see val_step)."""
         k = int(n_samples)
-        bufs = self._forward(x, None, k, beta, self._WANT, eps, None, seed, img_offset)
+        engine = self._engine(precision, self._WANT, eps)
+        if engine == "fp32":
+            bufs = self._forward(x, None, k, beta, self._WANT, eps, None, seed, img_offset)
+        else:
+            bufs = self._forward_tc(x, None, k, beta, self._WANT, seed, img_offset, engine)
         bufs["_img_offset"] = img_offset
         return self._result(bufs, k, beta)
 
     __call__ = call
 
-    def val_step(self, x, n_samples, beta):
-        """IWAE.val_step (src/iwae1.py:164-166)."""
-        return self.call(x, n_samples, beta)
+    def val_step(self, x, n_samples, beta, precision="auto"):
+        """IWAE.val_step (src/iwae1.py:164-166; the driver calls it on the WHOLE test set every 200 steps, main.py:152).
+        Runs on the fused tensor-core kernel when the architecture fits it: every dict entry of `call` with no
+        [k,B,784] tensor written; `logits` / `z` stay lazy (first access recomputes them with the fp32 kernels and the
+        same noise seed)."""
+        return self.call(x, n_samples, beta, precision=precision)
 
     def _objective_id(self, objective: str, res_keys) -> int:
         if objective not in res_keys or objective not in _abi.OBJ:
@@ -791,6 +829,7 @@ class IWAE2(IWAE):
         s = bufs["scalars"]
         lazy = self._lazy(bufs, k, beta, ("z1", "z2", "logits"))
         res = Result()
+        res._seed = bufs.get("_seed")
         res["vae_elbo"] = DeviceValue(s[0])
         res["iwae_elbo"] = DeviceValue(s[2])
         res["iwae_eq14"] = DeviceValue(s[3])
@@ -808,10 +847,14 @@ class IWAE2(IWAE):
         self._extras(res, bufs)
         return res
 
-    def call(self, x, n_samples, beta=1.0, eps=None, eps2=None, seed=None, img_offset=0):
+    def call(self, x, n_samples, beta=1.0, eps=None, eps2=None, seed=None, img_offset=0, precision="fp32"):
         """iwae2.IWAE.call (src/iwae2.py:109-167); eps [k,B,d1], eps2 [k,B,d2] inject the noise."""
         k = int(n_samples)
-        bufs = self._forward(x, None, k, beta, self._WANT, eps, eps2, seed, img_offset)
+        engine = self._engine(precision, self._WANT, eps, eps2)
+        if engine == "fp32":
+            bufs = self._forward(x, None, k, beta, self._WANT, eps, eps2, seed, img_offset)
+        else:
+            bufs = self._forward_tc(x, None, k, beta, self._WANT, seed, img_offset, engine)
         bufs["_img_offset"] = img_offset
         return self._result(bufs, k, beta)
 
@@ -874,6 +917,17 @@ class IWAEDReG(IWAE):
         bufs = self._train(x, None, k, beta, optimizer, _abi.OBJ["dreg"], eps, None, seed, materialize=materialize)
         return self._result(bufs, k, beta)
 
+    @staticmethod
+    def write_to_tensorboard(res, step, writer=None):
+        """tasks/task02.py:103-108: iwae_elbo and the three term means (this dict has no vae_elbo)."""
+        vals = {"Evaluation/iwae_elbo": float(res["iwae_elbo"])}
+        for key in ("lpxz", "lqzx", "lpz"):
+            vals[f"Evaluation/{key}"] = float(res[key].numpy().mean())
+        if writer is not None:
+            for name, v in vals.items():
+                writer.add_scalar(name, v, step)
+        return vals
+
 
 class CIWAE(IWAE):
     """tasks/task04.py:101-188: label-conditioned IWAE with a learned prior p(z|y); `call(x, y, n_samples,
@@ -903,16 +957,20 @@ class CIWAE(IWAE):
         if self._learned_prior:
             self.conditional_prior_network = _SubModel(self, "conditional_prior_network")
 
-    def call(self, x, y, n_samples, beta=1.0, eps=None, seed=None, img_offset=0):
+    def call(self, x, y, n_samples, beta=1.0, eps=None, seed=None, img_offset=0, precision="fp32"):
         k = int(n_samples)
-        bufs = self._forward(x, y, k, beta, self._WANT, eps, None, seed, img_offset)
+        engine = self._engine(precision, self._WANT, eps)
+        if engine == "fp32":
+            bufs = self._forward(x, y, k, beta, self._WANT, eps, None, seed, img_offset)
+        else:
+            bufs = self._forward_tc(x, y, k, beta, self._WANT, seed, img_offset, engine)
         bufs["_img_offset"] = img_offset
         return self._result(bufs, k, beta)
 
     __call__ = call
 
-    def val_step(self, x, y, n_samples, beta):
-        return self.call(x, y, n_samples, beta)
+    def val_step(self, x, y, n_samples, beta, precision="auto"):
+        return self.call(x, y, n_samples, beta, precision=precision)
 
     def train_step(self, x, y, n_samples, beta, optimizer, objective="vae_elbo", eps=None, seed=None, materialize=()):
         oid = self._objective_id(objective, self._OBJECTIVES)

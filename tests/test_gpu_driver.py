@@ -45,3 +45,17 @@ def test_training_improves_elbo_and_eval_loop_matches_fused():
     fused = float(total) / 16
     # different noise streams: agreement to Monte-Carlo accuracy of a k=2000 estimator
     assert abs(float(met.result()) - fused) < 0.5, (float(met.result()), fused)
+
+
+@pytest.mark.parametrize("script,extra", [("task02_dreg", []), ("task04_ciwae", []), ("task04_ciwae", ["--std_prior"])])
+def test_task_drivers_smoke(script, extra, capsys):
+    """examples/task02_dreg.py, task04_ciwae.py: the reference CLIs of tasks/task02.py / task04.py / task05.py."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(script, os.path.join(ROOT, "examples", script + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    llh = mod.main(["--epochs", "1", "--n_train", "400", "--n_test", "40", "--n_samples", "5", "--max_steps", "12",
+                    "--eval_samples", "256"] + extra)
+    out = capsys.readouterr().out
+    assert "train ELBO" in out and "Test-set 256 sample log likelihood estimate" in out
+    assert np.isfinite(llh) and -700 < llh < -100

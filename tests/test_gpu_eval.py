@@ -204,3 +204,76 @@ def test_auto_precision_falls_back_to_fp32_kernels_outside_the_fused_kernels_lim
         m.llh(case["x"], 64, precision="tc_f16_fast", seed=SEED)
     small = _case(oracle, "iwae2", 2)
     assert build("iwae2", small, small).tc_supported()
+
+
+@pytest.mark.parametrize("precision", ["tc_f16", "tc_f16_fast"])
+@pytest.mark.parametrize("kind", ["iwae1", "iwae2", "ciwae", "ciwae_std"])
+def test_val_step_on_the_fused_engine_matches_oracle(oracle, kind, precision):
+    """model.val_step (src/iwae1.py:164-166, main.py:152) through the fused tensor-core kernel (iwae_forward_tc): every
+    entry of the result dict except logits against the fp64 oracle fed with the same Philox noise, at a k that leaves
+    tiles ragged (k = 50: 50 of 128 rows) and one that spans tiles (k = 300); beta != 1 for the one-layer models."""
+    for k, beta in ((50, 1.0), (300, 0.7)):
+        N = 5
+        case = _case(oracle, kind, N, scale=0.7)
+        m = build(kind, case, case)
+        p = oracle.to_torch(case["params"])
+        x = torch.tensor(case["x"], dtype=torch.float64)
+        e1 = torch.tensor(oracle.philox_normal(SEED, 1, 0, N, k, 100), dtype=torch.float64)
+        if kind == "iwae2":
+            e2 = torch.tensor(oracle.philox_normal(SEED, 2, 0, N, k, 50), dtype=torch.float64)
+            ref = oracle.iwae2_call(p, x, k, beta, e1, e2)
+            res = m.call(case["x"], k, beta, seed=SEED, precision=precision)
+            keys = ["lpxz1", "lpz1z2", "lpz2", "lqz1x", "lqz2z1", "al", "snis_z1", "snis_z2", "vae_elbo", "iwae_elbo", "iwae_eq14"]
+        elif kind == "iwae1":
+            ref = oracle.iwae1_call(p, x, k, beta, e1)
+            res = m.call(case["x"], k, beta, seed=SEED, precision=precision)
+            keys = ["lpxz", "lpz", "lqzx", "al", "snis_z", "vae_elbo", "vae_elbo_kl", "iwae_elbo", "iwae_eq14"]
+        else:
+            learned = kind == "ciwae"
+            ref = oracle.ciwae_call(p, x, case["y"], k, beta, e1, learned_prior=learned)
+            res = m.call(case["x"], case["y"], k, beta, seed=SEED, precision=precision)
+            keys = ["lpxzy", "lpzy" if learned else "lpz", "lqzxy", "al", "snis_z", "vae_elbo", "vae_elbo_kl", "iwae_elbo", "iwae_eq14"]
+        for key in keys + ["iwae_elbo_per_example", "vae_elbo_per_example", "log_w"]:
+            got, want = res[key].numpy(), ref[key].detach().numpy()
+            # stated tolerances: log_w and every ELBO <= 1e-4 relative; a SINGLE log-density term of a row <= 3e-4;
+            # softmax weights `al` and SNIS means: 1e-2 ABSOLUTE (rel() floors the denominator at 1) - al = softmax(log_w)
+            # turns an absolute log_w error of 0.02 nats (5e-5 of |log_w| = 450, inside the tolerance) into 2 % of a weight
+            tol = 1e-2 if key in ("al", "snis_z", "snis_z1", "snis_z2") else (3e-4 if key.startswith(("lp", "lq")) else TC_RTOL)
+            assert got.shape == want.shape, (key, got.shape, want.shape)
+            assert rel(got, want) < tol, (kind, k, key, rel(got, want))
+        # the lazily recomputed entries use the same seed on the fp32 kernels
+        zk = "z1" if kind == "iwae2" else "z"
+        assert rel(res[zk].numpy(), ref[zk].detach().numpy()) < RTOL
+        assert rel(res["logits"].numpy(), ref["logits"].detach().numpy()) < RTOL
+
+
+def test_val_step_full_test_set_shape(oracle):
+    """The driver's monitoring call: val_step(Xtest [10000,784], 50, 1.0) (main.py:152).  Fused engine vs the fp32
+    kernels on the same Philox noise at the full size (sampled), and the batch scalars."""
+    import iwae_b200 as ib
+    P, X, _ = ib.data.synthetic_binarised(10000, seed=123)
+    m = ib.IWAE2([200, 100], [100, 50], seed=3, out_bias=ib.data.get_bias(P.mean(0)))
+    a = m.val_step(X, 50, 1.0)
+    assert a["al"].shape == (50, 10000) and a["snis_z1"].shape == (10000, 100) and a["lpxz1"].shape == (50, 10000)
+    b = m.call(X[:512], 50, 1.0, seed=a_seed(a), precision="fp32")
+    for key in ("lpxz1", "lpz1z2", "lpz2", "lqz1x", "lqz2z1", "log_w", "iwae_elbo_per_example", "vae_elbo_per_example"):
+        ga, gb = a[key].numpy()[..., :512], b[key].numpy()
+        err = rel(ga, gb)
+        mean_err = abs(float(ga.mean()) - float(gb.mean())) / abs(float(gb.mean()))
+        print(f"[val_step 10000 x 50] {key}: worst entry rel err vs fp32 kernels {err:.2e}, mean over the set {mean_err:.2e}")
+        # Stated tolerances of the fused engine (fp16 GEMM operands): the per-example ELBOs and the test-set MEAN of every
+        # term (the scalars the driver logs, src/iwae2.py:315-323) <= 1e-4 relative (measured 1e-6); an image's k=50 ELBO <= 3e-4
+        # (measured 1.3e-4 worst of 512); a single row's term / log_w <= 2e-3 in
+        # the worst of 25,600 rows (rows with |z2| >> 1, whose importance weight is e^-1000: z2 = mu2 + e^a eps with
+        # mu2, a from fp16 GEMMs).  precision="fp32" gives the exact parity kernels.
+        assert mean_err < TC_RTOL, key
+        assert err < (3e-4 if key.endswith("per_example") else 2e-3), key       # k=50: one or two rows dominate an image's ELBO
+    assert abs(float(a["iwae_elbo"]) - float(a["iwae_elbo_per_example"].numpy().mean())) < 1e-3
+
+
+def a_seed(res):
+    """the noise seed a result was drawn with (kept for the lazily recomputed entries)"""
+    for cell in (res.__dict__.get("_seed"),):
+        if cell is not None:
+            return cell
+    raise AssertionError("result carries no seed")
