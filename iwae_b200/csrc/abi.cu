@@ -124,6 +124,8 @@ extern "C" int iwae_destroy(iwae_ctx* ctx) {
   if (ctx->stage_aux) cudaFree(ctx->stage_aux);
   train_graph_release(ctx);
   comm_release(ctx);
+  for (cudaStream_t& l : ctx->lane) if (l) { cudaStreamDestroy(l); l = nullptr; }
+  for (cudaEvent_t& e : ctx->lane_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   delete ctx;
@@ -186,7 +188,25 @@ struct Fwd {
 struct FwdOpts {
   bool keep_for_bwd = false;   // materialise logits, eps, al
   bool want_dreg = false;
+  bool lanes = false;          // train step: run independent branches on the context's side streams
 };
+
+// `to` waits for everything issued so far on `from` (an event from the context's pool; re-recording an event after the
+// wait on it has been issued is fine, eagerly and under stream capture)
+static int lane_dep(iwae_ctx* ctx, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return 0;
+  cudaEvent_t& ev = ctx->lane_ev[ctx->lane_ev_next];
+  ctx->lane_ev_next = (ctx->lane_ev_next + 1) % 16;
+  if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(ev, from));
+  CUDA_TRY(cudaStreamWaitEvent(to, ev, 0));
+  return 0;
+}
+static int lanes_init(iwae_ctx* ctx) {
+  for (int i = 0; i < 3; ++i)
+    if (!ctx->lane[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->lane[i], cudaStreamNonBlocking));
+  return 0;
+}
 
 // Training forward of the encoder's first layer: 20 rows x 784 inputs -> 200 units is 7 CTAs walking 49 K-tiles each
 // (22-32 us).  With `scratch` the product is split over K into partial sums that one small kernel reduces with the
@@ -263,6 +283,11 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   if (opt.keep_for_bwd) IWAE_TRY(ar.get(&f.eps1, (size_t)R * d1));
   IWAE_TRY(sample_latent(f.mu1, f.std1, 1, eps1_in, f.eps1, f.z1, B, k, d1, seed, 1, img_offset, st));
 
+  // The decoder p(x|z1) depends on z1 only: in a train step of the two-layer model it runs on lane 0 beside the
+  // q(z2|z1) -> z2 -> p(z1|z2) chain (9 dependent small kernels), which hides its three GEMMs incl. the 784-logit one.
+  cudaStream_t sd = st;
+  if (opt.lanes && m.two_layer()) { IWAE_TRY(lanes_init(ctx)); sd = ctx->lane[0]; IWAE_TRY(lane_dep(ctx, st, sd)); }
+
   // ---- IWAE2: q(z2|z1), z2, p(z1|z2)                                       iwae2.py:63-65,90
   if (m.two_layer()) {
     IWAE_TRY(ar.get(&f.g1, (size_t)R * h2)); IWAE_TRY(ar.get(&f.g2, (size_t)R * h2));
@@ -287,12 +312,12 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   // ---- decoder p(x|z1)                                                     iwae1.py:79-85
   if (nc) {
     float* zin; IWAE_TRY(ar.get(&zin, (size_t)R * (d1 + nc)));
-    IWAE_TRY(concat_onehot(f.z1, d1, d1, y, B, (int)R, nc, zin, st));         // task04.py:119
+    IWAE_TRY(concat_onehot(f.z1, d1, d1, y, B, (int)R, nc, zin, sd));         // task04.py:119
     f.zin = zin; f.ld_zin = d1 + nc;
   } else { f.zin = f.z1; f.ld_zin = d1; }
   IWAE_TRY(ar.get(&f.a1, (size_t)R * h1)); IWAE_TRY(ar.get(&f.a2, (size_t)R * h1));
-  IWAE_TRY(dense_fwd(P, m.dec.d0, f.zin, f.ld_zin, R, ACT_TANH, f.a1, st));
-  IWAE_TRY(dense_fwd(P, m.dec.d1, f.a1, h1, R, ACT_TANH, f.a2, st));
+  IWAE_TRY(dense_fwd(P, m.dec.d0, f.zin, f.ld_zin, R, ACT_TANH, f.a1, sd));
+  IWAE_TRY(dense_fwd(P, m.dec.d1, f.a1, h1, R, ACT_TANH, f.a2, sd));
   {
     const bool mat = opt.keep_for_bwd || o->logits;
     if (mat) IWAE_TRY(pick(ar, o->logits, (size_t)R * nx, &f.logits));
@@ -304,10 +329,11 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     g.C = f.logits; g.ldc = nx;
     g.M = (int)R; g.N = nx; g.K = h1; g.bias = P + m.dec.d2.b;
     g.bern_x = x; g.bern_B = B; g.bern_partial = f.bpart;      // fused Bernoulli log-lik (iwae1.py:111)
-    IWAE_TRY(gemm_f32(g, st));
+    IWAE_TRY(gemm_f32(g, sd));
     IWAE_TRY(pick(ar, o->lpxz, (size_t)R, &f.lpxz));
-    IWAE_TRY(bern_reduce_partials(f.bpart, (int)R, nt, f.lpxz, st));
+    IWAE_TRY(bern_reduce_partials(f.bpart, (int)R, nt, f.lpxz, sd));
   }
+  IWAE_TRY(lane_dep(ctx, sd, st));
 
   // ---- Gaussian terms                                                      iwae1.py:107-109, iwae2.py:116-122
   IWAE_TRY(pick(ar, o->lpz, (size_t)R, &f.lpz));
@@ -362,7 +388,11 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     sa.B = B; sa.R = R; sa.beta = beta;
     sa.iwae = f.iwae; sa.vae = f.vae; sa.eq14 = f.eq14; sa.kl = f.kl; sa.dreg = f.dreg;
     sa.lpxz = f.lpxz; sa.lpz = f.lpz; sa.lq1 = f.lq1; sa.out = o->scalars;
-    IWAE_TRY(finalize_scalars(sa, st));
+    // train step: the batch scalars are outputs only - nothing of the backward pass reads them - so they leave the
+    // critical path for lane 1 (joined at the end of backward_internal together with the weight gradients)
+    cudaStream_t ss = st;
+    if (opt.lanes) { ss = ctx->lane[1]; IWAE_TRY(lanes_init(ctx)); IWAE_TRY(lane_dep(ctx, st, ss)); }
+    IWAE_TRY(finalize_scalars(sa, ss));
   }
   return 0;
 }
@@ -573,8 +603,11 @@ constexpr int GRAD_SPLITS = 8;
 static thread_local int g_grad_stride = 0;      // n_params of the model whose backward is running on this host thread (slice stride)
 
 // dW = X^T dY, db = colsum(dY)
-static int dense_bwd_w(const DenseP& L, const float* X, int64_t ldx, int64_t M, const float* dY, float* grads,
-                       cudaStream_t st) {
+// `st` is the stream dY was produced on; with a weight-gradient lane `wl` the product runs there (after st's work so
+// far) so that the dX chain on st does not wait for it
+static int dense_bwd_w(iwae_ctx* ctx, const DenseP& L, const float* X, int64_t ldx, int64_t M, const float* dY, float* grads,
+                       cudaStream_t st, cudaStream_t wl = nullptr) {
+  if (wl && wl != st) { IWAE_TRY(lane_dep(ctx, st, wl)); st = wl; }
   GemmArgs g;
   g.A = X; g.sa_m = 1; g.sa_k = ldx;                 // A(i_in, row)
   g.B = dY; g.sb_k = L.n_out; g.sb_n = 1;            // B(row, o)
@@ -624,23 +657,23 @@ static int dense_bwd_x(const float* P, const DenseP& L, const float* dY, int64_t
 // BasicBlock backward from (dmu, da) where a is the std pre-activation.  dX may be null.
 static int block_bwd(iwae_ctx* ctx, const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M,
                      const float* h1, const float* h2, const float* dmu, const float* da, float* grads, float* dX,
-                     cudaStream_t st) {
+                     cudaStream_t st, cudaStream_t wl = nullptr) {
   const int h = blk.l1.n_out;
   float *dh2, *dh1;
   IWAE_TRY(ctx->arena.get(&dh2, (size_t)M * h)); IWAE_TRY(ctx->arena.get(&dh1, (size_t)M * h));
-  IWAE_TRY(dense_bwd_w(blk.lmu, h2, h, M, dmu, grads, st));
-  IWAE_TRY(dense_bwd_w(blk.lstd, h2, h, M, da, grads, st));
+  IWAE_TRY(dense_bwd_w(ctx, blk.lmu, h2, h, M, dmu, grads, st, wl));
+  IWAE_TRY(dense_bwd_w(ctx, blk.lstd, h2, h, M, da, grads, st, wl));
   IWAE_TRY(dense_bwd_x(P, blk.lmu, dmu, M, dh2, h, 0, nullptr, 0, st));
   IWAE_TRY(dense_bwd_x(P, blk.lstd, da, M, dh2, h, 1, h2, h, st));            // (.. + ..) * (1 - h2^2)
-  IWAE_TRY(dense_bwd_w(blk.l2, h1, h, M, dh2, grads, st));
+  IWAE_TRY(dense_bwd_w(ctx, blk.l2, h1, h, M, dh2, grads, st, wl));
   IWAE_TRY(dense_bwd_x(P, blk.l2, dh2, M, dh1, h, 0, h1, h, st));
-  IWAE_TRY(dense_bwd_w(blk.l1, X, ldx, M, dh1, grads, st));
+  IWAE_TRY(dense_bwd_w(ctx, blk.l1, X, ldx, M, dh1, grads, st, wl));
   if (dX) IWAE_TRY(dense_bwd_x(P, blk.l1, dh1, M, dX, blk.l1.n_in, 0, nullptr, 0, st));
   return 0;
 }
 
 static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float beta, int objective, int B_norm,
-                             float* grads, cudaStream_t st) {
+                             float* grads, cudaStream_t st, bool lanes = false) {
   const ModelP& m = ctx->model;
   const iwae_config& c = m.cfg;
   Arena& ar = ctx->arena;
@@ -649,22 +682,32 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
   // DReG's decoder part is the IWAE-ELBO gradient (task02.py:96)
   const int dec_obj = (objective == IWAE_OBJ_DREG) ? IWAE_OBJ_IWAE_ELBO : objective;
 
+  // Lanes (train step): the decoder's backward chain (lane 0) and the p(z1|z2) -> z2 -> q(z2|z1) chain (caller's stream)
+  // are independent until they meet in the first latent layer; every weight gradient dW = X^T dY leaves its chain for
+  // lane 1 / lane 2, so a chain is only its dX products.  All weight gradients write disjoint slices of `grads`.
+  cudaStream_t s_dec = st, w_dec = nullptr, w_lat = nullptr;
+  if (lanes) {
+    IWAE_TRY(lanes_init(ctx));
+    w_dec = ctx->lane[1]; w_lat = ctx->lane[2];
+    if (m.two_layer()) s_dec = ctx->lane[0];
+  }
   float *g, *dl, *da2, *da1, *dzin;
   IWAE_TRY(ar.get(&g, (size_t)R));
   IWAE_TRY(row_coef(f.al, B, k, dec_obj, B_norm, g, st));
+  IWAE_TRY(lane_dep(ctx, st, s_dec));
   IWAE_TRY(ar.get(&dl, (size_t)R * nx));
-  IWAE_TRY(dlogits_f32(f.logits, f.x, g, (int)R, B, nx, dl, st));
+  IWAE_TRY(dlogits_f32(f.logits, f.x, g, (int)R, B, nx, dl, s_dec));
   // decoder MLP
   IWAE_TRY(ar.get(&da2, (size_t)R * h1)); IWAE_TRY(ar.get(&da1, (size_t)R * h1));
   IWAE_TRY(ar.get(&dzin, (size_t)R * m.dec_in()));
-  IWAE_TRY(dense_bwd_w(m.dec.d2, f.a2, h1, R, dl, grads, st));
+  IWAE_TRY(dense_bwd_w(ctx, m.dec.d2, f.a2, h1, R, dl, grads, s_dec, w_dec));
   float* dx_scratch = nullptr;       // split-K partial sums of the output layer's dX (training shapes only)
   if (R <= 4096) IWAE_TRY(ar.get(&dx_scratch, (size_t)BWDX_SPLITS * R * h1));
-  IWAE_TRY(dense_bwd_x(P, m.dec.d2, dl, R, da2, h1, 0, f.a2, h1, st, dx_scratch));
-  IWAE_TRY(dense_bwd_w(m.dec.d1, f.a1, h1, R, da2, grads, st));
-  IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, st));
-  IWAE_TRY(dense_bwd_w(m.dec.d0, f.zin, f.ld_zin, R, da1, grads, st));
-  IWAE_TRY(dense_bwd_x(P, m.dec.d0, da1, R, dzin, m.dec_in(), 0, nullptr, 0, st));
+  IWAE_TRY(dense_bwd_x(P, m.dec.d2, dl, R, da2, h1, 0, f.a2, h1, s_dec, dx_scratch));
+  IWAE_TRY(dense_bwd_w(ctx, m.dec.d1, f.a1, h1, R, da2, grads, s_dec, w_dec));
+  IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, s_dec));
+  IWAE_TRY(dense_bwd_w(ctx, m.dec.d0, f.zin, f.ld_zin, R, da1, grads, s_dec, w_dec));
+  IWAE_TRY(dense_bwd_x(P, m.dec.d0, da1, R, dzin, m.dec_in(), 0, nullptr, 0, s_dec));
 
   float* dz1_q = nullptr;
   if (m.two_layer()) {
@@ -673,7 +716,7 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
     IWAE_TRY(ar.get(&dpmu, (size_t)R * d1)); IWAE_TRY(ar.get(&dpa, (size_t)R * d1));
     IWAE_TRY(gauss_rows_bwd(g, f.z1, f.pmu, f.pstd, R, d1, dpmu, dpa, st));
     IWAE_TRY(ar.get(&dz2_p, (size_t)R * d2));
-    IWAE_TRY(block_bwd(ctx, P, m.dec21, f.z2, d2, R, f.p1, f.p2, dpmu, dpa, grads, dz2_p, st));
+    IWAE_TRY(block_bwd(ctx, P, m.dec21, f.z2, d2, R, f.p1, f.p2, dpmu, dpa, grads, dz2_p, st, w_lat));
     // z2 = mu2 + std2 eps2 ; lpz2 ; -lqz2z1                                   iwae2.py:65,116-118
     IWAE_TRY(ar.get(&dmu2, (size_t)R * d2)); IWAE_TRY(ar.get(&da_2, (size_t)R * d2));
     Latent2BwdArgs l2;
@@ -681,8 +724,9 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
     l2.dmu = dmu2; l2.da = da_2;
     IWAE_TRY(latent2_bwd(l2, st));
     IWAE_TRY(ar.get(&dz1_q, (size_t)R * d1));
-    IWAE_TRY(block_bwd(ctx, P, m.enc2, f.z1, d1, R, f.g1, f.g2, dmu2, da_2, grads, dz1_q, st));
+    IWAE_TRY(block_bwd(ctx, P, m.enc2, f.z1, d1, R, f.g1, f.g2, dmu2, da_2, grads, dz1_q, st, w_lat));
   }
+  IWAE_TRY(lane_dep(ctx, s_dec, st));            // the first latent layer needs dz from both chains
 
   // first stochastic layer
   float *dmu1, *da_1, *dpmu_b = nullptr, *dpa_b = nullptr;
@@ -699,9 +743,11 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
   }
   l1.dmu = dmu1; l1.da = da_1;
   IWAE_TRY(latent1_bwd(l1, st));
-  IWAE_TRY(block_bwd(ctx, P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, dmu1, da_1, grads, nullptr, st));
+  IWAE_TRY(block_bwd(ctx, P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, dmu1, da_1, grads, nullptr, st, w_lat));
   if (m.learned_prior())
-    IWAE_TRY(block_bwd(ctx, P, m.prior, f.yoh, c.n_cond, B, f.p1, f.p2, dpmu_b, dpa_b, grads, nullptr, st));
+    IWAE_TRY(block_bwd(ctx, P, m.prior, f.yoh, c.n_cond, B, f.p1, f.p2, dpmu_b, dpa_b, grads, nullptr, st, w_dec));
+  if (w_dec) IWAE_TRY(lane_dep(ctx, w_dec, st));     // every weight gradient is in `grads` before the reduction / Adam
+  if (w_lat) IWAE_TRY(lane_dep(ctx, w_lat, st));
   return 0;
 }
 
@@ -721,6 +767,8 @@ static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, co
   Fwd f; FwdOpts opt;
   opt.keep_for_bwd = true;
   opt.want_dreg = (objective == IWAE_OBJ_DREG);
+  static const bool no_lanes = getenv("IWAE_NO_LANES") != nullptr;
+  opt.lanes = !no_lanes;
   IWAE_TRY(forward_internal(ctx, params, x, y, B, k, beta, eps1, eps2, seed, img_offset, outs, opt, f, st));
   // backward into the zeroed [GRAD_SPLITS][n_params] workspace, then one fixed-order reduction
   float* ws;
@@ -728,7 +776,7 @@ static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, co
   IWAE_TRY(ctx->arena.get(&ws, (size_t)GRAD_SPLITS * n));
   CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(float) * GRAD_SPLITS * n, st));
   g_grad_stride = (int)n;
-  IWAE_TRY(backward_internal(ctx, params, f, beta, objective, B_norm, ws, st));
+  IWAE_TRY(backward_internal(ctx, params, f, beta, objective, B_norm, ws, st, opt.lanes));
   if (adam) return adam_from_partials(adam->params, ws, GRAD_SPLITS, adam->m, adam->v, n, adam->lr, adam->b1, adam->b2,
                                       adam->eps, adam->t, st);
   return grad_reduce(ws, GRAD_SPLITS, n, grads, st);

@@ -119,6 +119,12 @@ struct iwae_ctx {
   StepDyn* dyn_dev = nullptr;
   cudaStream_t gstream = nullptr;
   cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
+  // train step: side streams ("lanes") for the branches of the step that do not depend on each other - the decoder
+  // p(x|z1) beside the q(z2|z1) / p(z1|z2) blocks, every weight gradient dW = X^T dY beside the dX chain - joined with
+  // events (inside a captured step they become parallel branches of the CUDA graph)
+  cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t lane_ev[16] = {};
+  int lane_ev_next = 0;
 };
 
 // ---- fp32 kernels (kernels_f32.cu) ----
