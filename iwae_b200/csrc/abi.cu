@@ -391,7 +391,7 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     // train step: the batch scalars are outputs only - nothing of the backward pass reads them - so they leave the
     // critical path for lane 1 (joined at the end of backward_internal together with the weight gradients)
     cudaStream_t ss = st;
-    if (opt.lanes) { ss = ctx->lane[1]; IWAE_TRY(lanes_init(ctx)); IWAE_TRY(lane_dep(ctx, st, ss)); }
+    if (opt.lanes) { IWAE_TRY(lanes_init(ctx)); ss = ctx->lane[1]; IWAE_TRY(lane_dep(ctx, st, ss)); }
     IWAE_TRY(finalize_scalars(sa, ss));
   }
   return 0;
