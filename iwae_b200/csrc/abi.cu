@@ -236,11 +236,15 @@ static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ld
 }
 
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
-                     float* mu, float* sd, cudaStream_t st, float* l1_scratch) {
+                     float* mu, float* sd, cudaStream_t st, float* l1_scratch, iwae_ctx* lane_ctx, cudaStream_t lane) {
   IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st, l1_scratch));
   IWAE_TRY(dense_fwd(P, blk.l2, h1, blk.l1.n_out, M, ACT_TANH, h2, st));
+  // the two heads read the same h2 and are independent: in a train step the std head runs on a side stream
+  cudaStream_t s2 = (lane_ctx && lane) ? lane : st;
+  if (s2 != st) IWAE_TRY(lane_dep(lane_ctx, st, s2));
   IWAE_TRY(dense_fwd(P, blk.lmu, h2, blk.l2.n_out, M, ACT_NONE, mu, st));
-  IWAE_TRY(dense_fwd(P, blk.lstd, h2, blk.l2.n_out, M, ACT_EXP_EPS, sd, st));   // exp(a) + 1e-6 (iwae1.py:34,42)
+  IWAE_TRY(dense_fwd(P, blk.lstd, h2, blk.l2.n_out, M, ACT_EXP_EPS, sd, s2));   // exp(a) + 1e-6 (iwae1.py:34,42)
+  if (s2 != st) IWAE_TRY(lane_dep(lane_ctx, s2, st));
   return 0;
 }
 
@@ -276,7 +280,9 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   IWAE_TRY(pick(ar, o->q_mu, (size_t)B * d1, &f.mu1)); IWAE_TRY(pick(ar, o->q_std, (size_t)B * d1, &f.std1));
   float* l1_scratch = nullptr;       // split-K partial sums of the encoder's first layer (train step only, see dense_fwd)
   if (opt.keep_for_bwd && B <= 64) IWAE_TRY(ar.get(&l1_scratch, (size_t)FWD_SPLITS * B * h1));
-  IWAE_TRY(block_fwd_f32(P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, f.mu1, f.std1, st, l1_scratch));
+  cudaStream_t hl = nullptr;           // side stream for the std heads of the BasicBlocks (train step)
+  if (opt.lanes) { IWAE_TRY(lanes_init(ctx)); hl = ctx->lane[2]; }
+  IWAE_TRY(block_fwd_f32(P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, f.mu1, f.std1, st, l1_scratch, hl ? ctx : nullptr, hl));
 
   // ---- z1 = mu + std*eps, k samples                                        iwae1.py:59
   IWAE_TRY(pick(ar, o->z1, (size_t)R * d1, &f.z1));
@@ -292,13 +298,13 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   if (m.two_layer()) {
     IWAE_TRY(ar.get(&f.g1, (size_t)R * h2)); IWAE_TRY(ar.get(&f.g2, (size_t)R * h2));
     IWAE_TRY(ar.get(&f.mu2, (size_t)R * d2)); IWAE_TRY(ar.get(&f.std2, (size_t)R * d2));
-    IWAE_TRY(block_fwd_f32(P, m.enc2, f.z1, d1, R, f.g1, f.g2, f.mu2, f.std2, st));
+    IWAE_TRY(block_fwd_f32(P, m.enc2, f.z1, d1, R, f.g1, f.g2, f.mu2, f.std2, st, nullptr, hl ? ctx : nullptr, hl));
     IWAE_TRY(pick(ar, o->z2, (size_t)R * d2, &f.z2));
     if (opt.keep_for_bwd) IWAE_TRY(ar.get(&f.eps2, (size_t)R * d2));
     IWAE_TRY(sample_latent(f.mu2, f.std2, 0, eps2_in, f.eps2, f.z2, B, k, d2, seed, 2, img_offset, st));
     IWAE_TRY(ar.get(&f.p1, (size_t)R * h2)); IWAE_TRY(ar.get(&f.p2, (size_t)R * h2));
     IWAE_TRY(ar.get(&f.pmu, (size_t)R * d1)); IWAE_TRY(ar.get(&f.pstd, (size_t)R * d1));
-    IWAE_TRY(block_fwd_f32(P, m.dec21, f.z2, d2, R, f.p1, f.p2, f.pmu, f.pstd, st));
+    IWAE_TRY(block_fwd_f32(P, m.dec21, f.z2, d2, R, f.p1, f.p2, f.pmu, f.pstd, st, nullptr, hl ? ctx : nullptr, hl));
   }
   // ---- CIWAE learned prior p(z|y)                                          task04.py:123
   if (m.learned_prior()) {

@@ -242,7 +242,8 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
                 uint64_t seed, int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st,
                 const float* eps1 = nullptr, const float* eps2 = nullptr, const TcTerms* terms = nullptr);
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
-                  float* mu, float* sd, cudaStream_t st, float* l1_scratch = nullptr);
+                  float* mu, float* sd, cudaStream_t st, float* l1_scratch = nullptr, iwae_ctx* lane_ctx = nullptr,
+                  cudaStream_t lane = nullptr);
 // out[m, n] = act(sum_s partial[s][m, n] + bias[n])   (split-K forward, see dense_fwd in abi.cu)
 int splitk_bias_act(const float* partial, int splits, int M, int N, const float* bias, int act, float* out, cudaStream_t st);
 // dX[m, n] = (sum_s partial[s][m, n] (+ dX[m, n])) * (1 - H[m, n]^2 if H)   (split-K backward through tanh)
