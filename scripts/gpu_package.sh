@@ -18,3 +18,6 @@ timeout 300 python scripts/prof_eval.py --images 592 --reps 2 > gpurun_out/plain
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:iwae_eval_tc_kernel -s 1 -c 1 -f -o gpurun_out/prof_eval \
     python scripts/prof_eval.py --images 592 --reps 2 > gpurun_out/ncu_full.log 2>&1 ; echo "rc=$?" ; cat gpurun_out/plain_prof.log
 IWAE_TC_TRACE=gpurun_out/trace.txt timeout 300 python scripts/prof_eval.py --images 592 --reps 1 > gpurun_out/trace_run.log 2>&1; echo "trace rc=$?"
+echo "== ncu DRAM / L2 traffic of the full 10,000-image launch"
+bash scripts/gpu_traffic.sh > gpurun_out/traffic_run.log 2>&1; tail -n 4 gpurun_out/traffic_run.log
+echo "== val_step probe"; timeout 300 python scripts/val_probe.py > gpurun_out/val_probe.log 2>&1; cat gpurun_out/val_probe.log
