@@ -11,6 +11,22 @@ def get_bias(train_mean: np.ndarray) -> np.ndarray:
     return -np.log(1.0 / np.clip(np.asarray(train_mean, dtype=np.float64), 0.001, 0.999) - 1.0)
 
 
+_DEFAULT_BIAS = {}
+
+
+def default_out_bias(n_x: int = 784) -> np.ndarray:
+    """What `Decoder.__init__` of the reference does on every construction (src/iwae1.py:74-75 -> utils.get_bias():
+    reload the train set, take the mean image): the output-layer bias of a freshly built model.  MNIST is not reachable
+    here, so the train set is the synthetic stand-in (`synthetic_mnist`, 60,000 images); cached per n_x."""
+    if n_x not in _DEFAULT_BIAS:
+        rs = np.random.RandomState(123)
+        mean = np.zeros(n_x)
+        for _ in range(6):                                   # 6 x 10,000 rows of the same stream as synthetic_mnist's Ptrain
+            mean += (rs.rand(10000, n_x) ** 4).sum(axis=0)
+        _DEFAULT_BIAS[n_x] = get_bias(mean / 60000.0)
+    return _DEFAULT_BIAS[n_x]
+
+
 def bernoullisample(x: np.ndarray) -> np.ndarray:
     """utils.bernoullisample (src/utils.py:26-27), on the NumPy global RNG like the reference."""
     return np.random.binomial(1, x, size=x.shape).astype("float32")

@@ -317,13 +317,17 @@ class IWAE:
     def init_weights(self, rs: np.random.RandomState, out_bias: Optional[np.ndarray] = None, scale: float = 1.0):
         """Keras defaults: kernels glorot_uniform, biases zero; the 784-way output bias is utils.get_bias()
         (iwae1.py:74-75).  TF's seeded initialiser stream is not reproducible outside TF, so values
-        come from `rs`; only the order and shapes are the reference's."""
+        come from `rs`; only the order and shapes are the reference's.  out_bias=None: the get_bias() of the synthetic
+        train set (data.default_out_bias), like a reference model built with its defaults."""
         flat = np.zeros(self.n_params, dtype=np.float32)
         for v in self.trainable_weights:
             shp = v.shape
             if len(shp) == 2:
                 lim = math.sqrt(6.0 / (shp[0] + shp[1])) * scale
                 flat[v.offset:v.offset + shp[0] * shp[1]] = rs.uniform(-lim, lim, size=shp).astype(np.float32).ravel()
+        if out_bias is None:
+            from . import data as _data
+            out_bias = _data.default_out_bias(self._cfg.n_x)     # the reference ALWAYS starts from utils.get_bias()
         if out_bias is not None:
             last = [v for v in self.trainable_weights if v.name.endswith("dense2.bias")][-1]
             flat[last.offset:last.offset + last.shape[0]] = np.asarray(out_bias, dtype=np.float64).astype(np.float32)
