@@ -126,6 +126,8 @@ extern "C" int iwae_destroy(iwae_ctx* ctx) {
   comm_release(ctx);
   for (cudaStream_t& l : ctx->lane) if (l) { cudaStreamDestroy(l); l = nullptr; }
   for (cudaEvent_t& e : ctx->lane_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+  if (ctx->wt_ev) { cudaEventDestroy(ctx->wt_ev); ctx->wt_ev = nullptr; }
+  if (ctx->wt_buf) { cudaFree(ctx->wt_buf); ctx->wt_buf = nullptr; }
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   delete ctx;
@@ -235,8 +237,47 @@ static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ld
   return gemm_f32(g, st);
 }
 
+// Train step only (M <= CHAIN_MAX_ROWS rows, widths <= 256): the block's Dense layers in ONE launch (dense_chain_kernel).
+// A first layer with a long reduction (784 pixels on 20 rows) stays on the split-K product, the chain starts after it.
+// The evaluation paths keep the tiled GEMMs: their per-row rounding must not depend on which kernel a shape selects.
+constexpr int64_t CHAIN_MAX_ROWS = 4096;
+// experimental until it beats the per-layer kernels: IWAE_CHAIN=1 turns it on
+static bool chain_enabled() { static const bool on = getenv("IWAE_CHAIN") != nullptr; return on; }
+static bool chain_ok(const BlockP& blk, int64_t M) {
+  return M <= CHAIN_MAX_ROWS && blk.l1.n_out <= 256 && 2 * blk.lmu.n_out <= 256 && blk.l1.n_in <= 256 * 4;
+}
+static void chain_dense(ChainLayer& L, const float* P, const DenseP& D, int act, float* out) {
+  L.W = P + D.w; L.ldw = D.n_out; L.bias = P + D.b; L.K = D.n_in; L.N = D.n_out; L.nsplit = D.n_out;
+  L.act = act; L.out = out; L.ldo = D.n_out;
+}
+static void chain_heads(ChainLayer& L, const float* P, const BlockP& blk, float* mu, float* sd) {
+  const int d = blk.lmu.n_out;
+  L.W = P + blk.lmu.w; L.Wb = P + blk.lstd.w; L.ldw = d; L.bias = P + blk.lmu.b; L.biasb = P + blk.lstd.b;
+  L.K = blk.lmu.n_in; L.N = 2 * d; L.nsplit = d;
+  L.act = CH_NONE; L.actb = CH_EXP_EPS;                         // exp(a) + 1e-6 (iwae1.py:34,42)
+  L.out = mu; L.ldo = d; L.outb = sd; L.ldob = d;
+}
+static int block_fwd_chain(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
+                           float* mu, float* sd, cudaStream_t st, float* l1_scratch) {
+  ChainArgs a;
+  a.M = (int)M;
+  int n = 0;
+  if (blk.l1.n_in > 256) {
+    IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st, l1_scratch));
+    a.X = h1; a.ldx = blk.l1.n_out; a.kx = blk.l1.n_out;
+  } else {
+    a.X = X; a.ldx = ldx; a.kx = blk.l1.n_in;
+    chain_dense(a.L[n++], P, blk.l1, CH_TANH, h1);
+  }
+  chain_dense(a.L[n++], P, blk.l2, CH_TANH, h2);
+  chain_heads(a.L[n++], P, blk, mu, sd);
+  a.nlayers = n;
+  return dense_chain(a, st);
+}
+
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
                      float* mu, float* sd, cudaStream_t st, float* l1_scratch, iwae_ctx* lane_ctx, cudaStream_t lane) {
+  if (lane_ctx && lane && chain_enabled() && chain_ok(blk, M)) return block_fwd_chain(P, blk, X, ldx, M, h1, h2, mu, sd, st, l1_scratch);
   IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st, l1_scratch));
   IWAE_TRY(dense_fwd(P, blk.l2, h1, blk.l1.n_out, M, ACT_TANH, h2, st));
   // the two heads read the same h2 and are independent: in a train step the std head runs on a side stream
@@ -322,8 +363,16 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     f.zin = zin; f.ld_zin = d1 + nc;
   } else { f.zin = f.z1; f.ld_zin = d1; }
   IWAE_TRY(ar.get(&f.a1, (size_t)R * h1)); IWAE_TRY(ar.get(&f.a2, (size_t)R * h1));
-  IWAE_TRY(dense_fwd(P, m.dec.d0, f.zin, f.ld_zin, R, ACT_TANH, f.a1, sd));
-  IWAE_TRY(dense_fwd(P, m.dec.d1, f.a1, h1, R, ACT_TANH, f.a2, sd));
+  if (opt.lanes && chain_enabled() && R <= CHAIN_MAX_ROWS && h1 <= 256 && f.ld_zin <= 256) {
+    ChainArgs a;
+    a.M = (int)R; a.X = f.zin; a.ldx = f.ld_zin; a.kx = m.dec.d0.n_in; a.nlayers = 2;
+    chain_dense(a.L[0], P, m.dec.d0, CH_TANH, f.a1);
+    chain_dense(a.L[1], P, m.dec.d1, CH_TANH, f.a2);
+    IWAE_TRY(dense_chain(a, sd));
+  } else {
+    IWAE_TRY(dense_fwd(P, m.dec.d0, f.zin, f.ld_zin, R, ACT_TANH, f.a1, sd));
+    IWAE_TRY(dense_fwd(P, m.dec.d1, f.a1, h1, R, ACT_TANH, f.a2, sd));
+  }
   {
     const bool mat = opt.keep_for_bwd || o->logits;
     if (mat) IWAE_TRY(pick(ar, o->logits, (size_t)R * nx, &f.logits));
@@ -660,10 +709,79 @@ static int dense_bwd_x(const float* P, const DenseP& L, const float* dY, int64_t
   return gemm_f32(g, st);
 }
 
+// Transposed weights for the fused backward chains: the copy of a Dense kernel [n_in, n_out] lives at the kernel's own
+// offset in ctx->wt_buf as [n_out, n_in]; a block's two heads are stored back to back ([2d, h]) so that
+// d(h2) = [dmu | da] [Wmu^T ; Wstd^T] is one product (the bias slot between the two kernels gives the room).
+static void add_transpose(TransposeJobs& t, const float* P, float* WT, const DenseP& L, int64_t dst_off) {
+  TransposeJob& j = t.job[t.count++];
+  j.src = P + L.w; j.dst = WT + dst_off; j.rows = L.n_in; j.cols = L.n_out; j.ld_src = L.n_out; j.ld_dst = L.n_in;
+}
+static void add_block_transposes(TransposeJobs& t, const float* P, float* WT, const BlockP& blk, bool need_l1) {
+  add_transpose(t, P, WT, blk.lmu, blk.lmu.w);
+  add_transpose(t, P, WT, blk.lstd, blk.lmu.w + (int64_t)blk.lmu.n_in * blk.lmu.n_out);
+  add_transpose(t, P, WT, blk.l2, blk.l2.w);
+  if (need_l1) add_transpose(t, P, WT, blk.l1, blk.l1.w);
+}
+static bool bwd_chain_ok(const ModelP& m, int64_t R) {
+  if (!chain_enabled() || R > CHAIN_MAX_ROWS) return false;
+  auto blk_ok = [](const BlockP& b) {
+    return b.l1.n_out <= 256 && 2 * b.lmu.n_out <= 256 && b.lstd.w >= b.lmu.w + (int64_t)b.lmu.n_in * b.lmu.n_out;
+  };
+  if (!blk_ok(m.enc1) || m.cfg.h1 > 256 || m.dec_in() > 256) return false;
+  if (m.two_layer() && (!blk_ok(m.enc2) || !blk_ok(m.dec21) || m.cfg.d1 > 256 || m.cfg.d2 > 256)) return false;
+  if (m.learned_prior() && !blk_ok(m.prior)) return false;
+  return true;
+}
+// one launch on `ts` that rebuilds every transposed copy the step's backward chains read; `done` is recorded after it
+static int launch_transposes(iwae_ctx* ctx, const float* P, cudaStream_t ts) {
+  const ModelP& m = ctx->model;
+  if (!ctx->wt_buf) {
+    CUDA_TRY(cudaMalloc((void**)&ctx->wt_buf, sizeof(float) * (size_t)m.n_params));
+    ctx->wt_cap = (size_t)m.n_params;
+  }
+  TransposeJobs t;
+  add_block_transposes(t, P, ctx->wt_buf, m.enc1, false);
+  if (m.two_layer()) {
+    add_block_transposes(t, P, ctx->wt_buf, m.enc2, true);
+    add_block_transposes(t, P, ctx->wt_buf, m.dec21, true);
+  }
+  if (m.learned_prior()) add_block_transposes(t, P, ctx->wt_buf, m.prior, false);
+  add_transpose(t, P, ctx->wt_buf, m.dec.d0, m.dec.d0.w);
+  add_transpose(t, P, ctx->wt_buf, m.dec.d1, m.dec.d1.w);
+  return transpose_jobs(t, ts);
+}
+static void chain_bwd_dense(ChainLayer& L, const float* WT, const DenseP& D, const float* H, float* out) {
+  L.W = WT + D.w; L.ldw = D.n_in; L.K = D.n_out; L.N = D.n_in; L.nsplit = D.n_in;
+  L.act = H ? CH_MULH : CH_NONE; L.H = H; L.ldh = D.n_in; L.out = out; L.ldo = D.n_in;
+}
+// BasicBlock backward with the dX products of the whole block in one launch
+static int block_bwd_chain(iwae_ctx* ctx, const BlockP& blk, const float* X, int64_t ldx, int64_t M,
+                           const float* h1, const float* h2, const float* dmu, const float* da, float* grads, float* dX,
+                           cudaStream_t st, cudaStream_t wl) {
+  const int h = blk.l1.n_out, d = blk.lmu.n_out;
+  float *dh2, *dh1;
+  IWAE_TRY(ctx->arena.get(&dh2, (size_t)M * h)); IWAE_TRY(ctx->arena.get(&dh1, (size_t)M * h));
+  IWAE_TRY(dense_bwd_w(ctx, blk.lmu, h2, h, M, dmu, grads, st, wl));
+  IWAE_TRY(dense_bwd_w(ctx, blk.lstd, h2, h, M, da, grads, st, wl));
+  ChainArgs a;
+  a.M = (int)M; a.X = dmu; a.ldx = d; a.kx = d; a.X2 = da; a.ldx2 = d; a.kx2 = d;
+  ChainLayer& L0 = a.L[0];                                  // dh2 = ([dmu | da] [Wmu^T ; Wstd^T]) * (1 - h2^2)
+  L0.W = ctx->wt_buf + blk.lmu.w; L0.ldw = h; L0.K = 2 * d; L0.N = h; L0.nsplit = h;
+  L0.act = CH_MULH; L0.H = h2; L0.ldh = h; L0.out = dh2; L0.ldo = h;
+  chain_bwd_dense(a.L[1], ctx->wt_buf, blk.l2, h1, dh1);   // dh1 = (dh2 W2^T) * (1 - h1^2)
+  a.nlayers = 2;
+  if (dX) { chain_bwd_dense(a.L[2], ctx->wt_buf, blk.l1, nullptr, dX); a.nlayers = 3; }
+  IWAE_TRY(dense_chain(a, st));
+  IWAE_TRY(dense_bwd_w(ctx, blk.l2, h1, h, M, dh2, grads, st, wl));
+  IWAE_TRY(dense_bwd_w(ctx, blk.l1, X, ldx, M, dh1, grads, st, wl));
+  return 0;
+}
+
 // BasicBlock backward from (dmu, da) where a is the std pre-activation.  dX may be null.
 static int block_bwd(iwae_ctx* ctx, const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M,
                      const float* h1, const float* h2, const float* dmu, const float* da, float* grads, float* dX,
-                     cudaStream_t st, cudaStream_t wl = nullptr) {
+                     cudaStream_t st, cudaStream_t wl = nullptr, bool chain = false) {
+  if (chain) return block_bwd_chain(ctx, blk, X, ldx, M, h1, h2, dmu, da, grads, dX, st, wl);
   const int h = blk.l1.n_out;
   float *dh2, *dh1;
   IWAE_TRY(ctx->arena.get(&dh2, (size_t)M * h)); IWAE_TRY(ctx->arena.get(&dh1, (size_t)M * h));
@@ -679,7 +797,7 @@ static int block_bwd(iwae_ctx* ctx, const float* P, const BlockP& blk, const flo
 }
 
 static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float beta, int objective, int B_norm,
-                             float* grads, cudaStream_t st, bool lanes = false) {
+                             float* grads, cudaStream_t st, bool lanes = false, bool chain = false) {
   const ModelP& m = ctx->model;
   const iwae_config& c = m.cfg;
   Arena& ar = ctx->arena;
@@ -711,9 +829,17 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
   if (R <= 4096) IWAE_TRY(ar.get(&dx_scratch, (size_t)BWDX_SPLITS * R * h1));
   IWAE_TRY(dense_bwd_x(P, m.dec.d2, dl, R, da2, h1, 0, f.a2, h1, s_dec, dx_scratch));
   IWAE_TRY(dense_bwd_w(ctx, m.dec.d1, f.a1, h1, R, da2, grads, s_dec, w_dec));
-  IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, s_dec));
+  if (chain) {
+    ChainArgs a;                                             // da1 = (da2 W1^T) * (1 - a1^2) ; dzin = da1 W0^T
+    a.M = (int)R; a.X = da2; a.ldx = h1; a.kx = h1; a.nlayers = 2;
+    chain_bwd_dense(a.L[0], ctx->wt_buf, m.dec.d1, f.a1, da1);
+    chain_bwd_dense(a.L[1], ctx->wt_buf, m.dec.d0, nullptr, dzin);
+    IWAE_TRY(dense_chain(a, s_dec));
+  } else {
+    IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, s_dec));
+  }
   IWAE_TRY(dense_bwd_w(ctx, m.dec.d0, f.zin, f.ld_zin, R, da1, grads, s_dec, w_dec));
-  IWAE_TRY(dense_bwd_x(P, m.dec.d0, da1, R, dzin, m.dec_in(), 0, nullptr, 0, s_dec));
+  if (!chain) IWAE_TRY(dense_bwd_x(P, m.dec.d0, da1, R, dzin, m.dec_in(), 0, nullptr, 0, s_dec));
 
   float* dz1_q = nullptr;
   if (m.two_layer()) {
@@ -722,7 +848,7 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
     IWAE_TRY(ar.get(&dpmu, (size_t)R * d1)); IWAE_TRY(ar.get(&dpa, (size_t)R * d1));
     IWAE_TRY(gauss_rows_bwd(g, f.z1, f.pmu, f.pstd, R, d1, dpmu, dpa, st));
     IWAE_TRY(ar.get(&dz2_p, (size_t)R * d2));
-    IWAE_TRY(block_bwd(ctx, P, m.dec21, f.z2, d2, R, f.p1, f.p2, dpmu, dpa, grads, dz2_p, st, w_lat));
+    IWAE_TRY(block_bwd(ctx, P, m.dec21, f.z2, d2, R, f.p1, f.p2, dpmu, dpa, grads, dz2_p, st, w_lat, chain));
     // z2 = mu2 + std2 eps2 ; lpz2 ; -lqz2z1                                   iwae2.py:65,116-118
     IWAE_TRY(ar.get(&dmu2, (size_t)R * d2)); IWAE_TRY(ar.get(&da_2, (size_t)R * d2));
     Latent2BwdArgs l2;
@@ -730,7 +856,7 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
     l2.dmu = dmu2; l2.da = da_2;
     IWAE_TRY(latent2_bwd(l2, st));
     IWAE_TRY(ar.get(&dz1_q, (size_t)R * d1));
-    IWAE_TRY(block_bwd(ctx, P, m.enc2, f.z1, d1, R, f.g1, f.g2, dmu2, da_2, grads, dz1_q, st, w_lat));
+    IWAE_TRY(block_bwd(ctx, P, m.enc2, f.z1, d1, R, f.g1, f.g2, dmu2, da_2, grads, dz1_q, st, w_lat, chain));
   }
   IWAE_TRY(lane_dep(ctx, s_dec, st));            // the first latent layer needs dz from both chains
 
@@ -749,9 +875,9 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
   }
   l1.dmu = dmu1; l1.da = da_1;
   IWAE_TRY(latent1_bwd(l1, st));
-  IWAE_TRY(block_bwd(ctx, P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, dmu1, da_1, grads, nullptr, st, w_lat));
+  IWAE_TRY(block_bwd(ctx, P, m.enc1, f.xin, f.ld_xin, B, f.h1, f.h2, dmu1, da_1, grads, nullptr, st, w_lat, chain));
   if (m.learned_prior())
-    IWAE_TRY(block_bwd(ctx, P, m.prior, f.yoh, c.n_cond, B, f.p1, f.p2, dpmu_b, dpa_b, grads, nullptr, st, w_dec));
+    IWAE_TRY(block_bwd(ctx, P, m.prior, f.yoh, c.n_cond, B, f.p1, f.p2, dpmu_b, dpa_b, grads, nullptr, st, w_dec, chain));
   if (w_dec) IWAE_TRY(lane_dep(ctx, w_dec, st));     // every weight gradient is in `grads` before the reduction / Adam
   if (w_lat) IWAE_TRY(lane_dep(ctx, w_lat, st));
   return 0;
@@ -775,14 +901,26 @@ static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, co
   opt.want_dreg = (objective == IWAE_OBJ_DREG);
   static const bool no_lanes = getenv("IWAE_NO_LANES") != nullptr;
   opt.lanes = !no_lanes;
+  // transposed weights for the backward chains: built on lane 1 while the forward pass runs
+  const bool chain = opt.lanes && bwd_chain_ok(m, (int64_t)B * k);
+  cudaEvent_t wt_done = nullptr;
+  if (chain) {
+    IWAE_TRY(lanes_init(ctx));
+    IWAE_TRY(lane_dep(ctx, st, ctx->lane[1]));
+    IWAE_TRY(launch_transposes(ctx, params, ctx->lane[1]));
+    if (!ctx->wt_ev) CUDA_TRY(cudaEventCreateWithFlags(&ctx->wt_ev, cudaEventDisableTiming));
+    wt_done = ctx->wt_ev;
+    CUDA_TRY(cudaEventRecord(wt_done, ctx->lane[1]));
+  }
   IWAE_TRY(forward_internal(ctx, params, x, y, B, k, beta, eps1, eps2, seed, img_offset, outs, opt, f, st));
+  if (wt_done) CUDA_TRY(cudaStreamWaitEvent(st, wt_done, 0));
   // backward into the zeroed [GRAD_SPLITS][n_params] workspace, then one fixed-order reduction
   float* ws;
   const int64_t n = m.n_params;
   IWAE_TRY(ctx->arena.get(&ws, (size_t)GRAD_SPLITS * n));
   CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(float) * GRAD_SPLITS * n, st));
   g_grad_stride = (int)n;
-  IWAE_TRY(backward_internal(ctx, params, f, beta, objective, B_norm, ws, st, opt.lanes));
+  IWAE_TRY(backward_internal(ctx, params, f, beta, objective, B_norm, ws, st, opt.lanes, chain));
   if (adam) return adam_from_partials(adam->params, ws, GRAD_SPLITS, adam->m, adam->v, n, adam->lr, adam->b1, adam->b2,
                                       adam->eps, adam->t, st);
   return grad_reduce(ws, GRAD_SPLITS, n, grads, st);

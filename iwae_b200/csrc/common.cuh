@@ -123,6 +123,8 @@ struct iwae_ctx {
   // p(x|z1) beside the q(z2|z1) / p(z1|z2) blocks, every weight gradient dW = X^T dY beside the dX chain - joined with
   // events (inside a captured step they become parallel branches of the CUDA graph)
   cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t wt_ev = nullptr;
+  float* wt_buf = nullptr; size_t wt_cap = 0;      // transposed weights of the fused backward chains (rebuilt every step)
   cudaEvent_t lane_ev[16] = {};
   int lane_ev_next = 0;
 };
@@ -232,6 +234,31 @@ int copy_table(const CopyTable& t, cudaStream_t st);
 int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64_t* out_idx,
                int32_t* out_consumed, cudaStream_t st);
 int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st);
+
+// ---- fused Dense chain of the train step (kernels_f32.cu) ----
+enum { CH_NONE = 0, CH_TANH = 1, CH_EXP_EPS = 2, CH_MULH = 3 };
+struct ChainLayer {
+  const float* W = nullptr; int ldw = 0;      // W(k, n) = W[k*ldw + n] for n < nsplit
+  const float* Wb = nullptr;                  // columns n >= nsplit read Wb[k*ldw + (n - nsplit)] (second head), else unused
+  const float* bias = nullptr; const float* biasb = nullptr;
+  int K = 0, N = 0, nsplit = 0;               // nsplit == N: one matrix
+  int act = CH_NONE, actb = CH_NONE;
+  const float* H = nullptr; int64_t ldh = 0;  // CH_MULH: v *= 1 - H[r*ldh + n]^2
+  float* out = nullptr; int64_t ldo = 0;      // global output for n < nsplit (may be null)
+  float* outb = nullptr; int64_t ldob = 0;    // ... for n >= nsplit
+  int vec = 1;                                // cp.async width in floats (set by dense_chain)
+};
+struct ChainArgs {
+  const float* X = nullptr; int64_t ldx = 0; int kx = 0;        // input rows: [X (kx columns) | X2 (kx2 columns)]
+  const float* X2 = nullptr; int64_t ldx2 = 0; int kx2 = 0;
+  int M = 0, nlayers = 0;
+  int TM = 0, kpad = 0, wsz = 0;                                 // set by dense_chain
+  ChainLayer L[3];
+};
+int dense_chain(const ChainArgs& a, cudaStream_t st);
+struct TransposeJob { const float* src; float* dst; int rows, cols; int64_t ld_src, ld_dst; };
+struct TransposeJobs { TransposeJob job[16]; int count = 0; };
+int transpose_jobs(const TransposeJobs& t, cudaStream_t st);
 
 // ---- fused tcgen05 evaluation (eval_tc.cu) ----
 int tc_pack_weights(iwae_ctx* ctx, const float* params, bool fast, cudaStream_t st);

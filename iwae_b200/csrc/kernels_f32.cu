@@ -5,6 +5,28 @@
 #include <math.h>
 #include <algorithm>
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The train step is a chain of ~35 dependent kernels of a few microseconds each: the gap between two of them (drain,
+// launch, ramp) is as long as the kernels.  Every kernel of this file starts with griddepcontrol.wait and is launched
+// with the programmatic-stream-serialization attribute, so its CTAs are scheduled while its predecessor in the stream is
+// still finishing and block at that wait until the predecessor has completed and flushed (a no-op without the
+// attribute).  Under stream capture the dependency becomes a programmatic edge of the CUDA graph.  IWAE_NO_PDL=1: off.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static bool pdl_enabled() { static const bool on = getenv("IWAE_NO_PDL") == nullptr; return on; }
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // =============================================================================================
 // Tiled SGEMM with fused epilogues.  C(m,n) = epi( sum_k A(m,k) B(k,n) ).
 // Generic strides cover x@W (NN), dY@W^T (NT) and X^T@dY (TN); the tile loaders pick the thread
@@ -13,6 +35,7 @@
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_f32_kernel(GemmArgs a) {
+  pdl_wait();
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int TX = BN / TN;   // threads along n
@@ -168,13 +191,13 @@ int gemm_f32(const GemmArgs& a, cudaStream_t st) {
     // tall, narrow outputs (rows = k*B = 1,000 by <= 200 units): 4x2 register tiles halve the shared-memory loads
     // per FFMA of the 2x2 kernel, which is LDS-bound on the long-K products (dX of the 784-logit layer: 48 -> ~20 us)
     dim3 grid((m_rows + 63) / 64, (a.N + 31) / 32, z);
-    gemm_f32_kernel<64, 32, 4, 2><<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(launch_pdl(gemm_f32_kernel<64, 32, 4, 2>, dim3(grid), dim3(256), 0, st, a));
   } else if (a.small_tile) {
     dim3 grid((m_rows + 31) / 32, (a.N + 31) / 32, z);
-    gemm_f32_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(launch_pdl(gemm_f32_kernel<32, 32, 2, 2>, dim3(grid), dim3(256), 0, st, a));
   } else {
     dim3 grid((m_rows + 63) / 64, (a.N + 63) / 64, z);
-    gemm_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(launch_pdl(gemm_f32_kernel<64, 64, 4, 4>, dim3(grid), dim3(256), 0, st, a));
   }
   LAUNCH_CHECK();
   return 0;
@@ -185,6 +208,7 @@ int gemm_f32(const GemmArgs& a, cudaStream_t st) {
 // =============================================================================================
 __global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, int N, float* __restrict__ out,
                               int64_t split_stride) {
+  pdl_wait();
   // one strip of 32 columns per blockIdx.x, one row range per blockIdx.y (partial sum -> out + y*split_stride);
   // blockDim = (32, 8): 8 row-lanes then an smem reduce in a fixed order
   __shared__ float red[8][33];
@@ -205,7 +229,7 @@ __global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, i
 }
 int colsum_f32(const float* A, int64_t lda, int M, int N, float* out, cudaStream_t st, int splits, int64_t split_stride) {
   if (splits < 1 || M < 64 * splits) splits = 1;
-  colsum_kernel<<<dim3((N + 31) / 32, splits), dim3(32, 8), 0, st>>>(A, lda, M, N, out, split_stride);
+  CUDA_TRY(launch_pdl(colsum_kernel, dim3(dim3((N + 31) / 32, splits)), dim3(dim3(32, 8)), 0, st, A, lda, M, N, out, split_stride));
   LAUNCH_CHECK();
   return 0;
 }
@@ -217,6 +241,7 @@ __device__ __forceinline__ int label_of(const float* y, int b) {
 
 __global__ void concat_onehot_kernel(const float* __restrict__ x, int64_t ldx, int n, const float* __restrict__ y,
                                      int B, int rows, int nc, float* __restrict__ out) {
+  pdl_wait();
   const int64_t total = (int64_t)rows * (n + nc);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (n + nc);
@@ -231,7 +256,7 @@ int concat_onehot(const float* x, int64_t ldx, int n, const float* y, int B, int
                   cudaStream_t st) {
   const int64_t total = (int64_t)rows * (n + nc);
   const int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
-  concat_onehot_kernel<<<blocks, 256, 0, st>>>(x, ldx, n, y, B, rows, nc, out);
+  CUDA_TRY(launch_pdl(concat_onehot_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, n, y, B, rows, nc, out));
   LAUNCH_CHECK();
   return 0;
 }
@@ -244,6 +269,7 @@ __global__ void sample_latent_kernel(const float* __restrict__ mu, const float* 
                                      const float* __restrict__ eps_in, float* __restrict__ eps_out,
                                      float* __restrict__ z, int B, int k, int d, uint64_t seed, int stream_id,
                                      int64_t img_offset, const StepDyn* __restrict__ dyn) {
+  pdl_wait();
   if (dyn) { seed = dyn->seed; img_offset = dyn->img_offset; }      // graph replay: per-step values live on the device
   const int nq = (d + 7) / 8;                // one Philox call per dim-octet (rng.cuh)
   const int64_t total = (int64_t)k * B * nq;
@@ -277,8 +303,8 @@ int sample_latent(const float* mu, const float* sd, int bcast, const float* eps_
   const int64_t total = (int64_t)k * B * ((d + 7) / 8);
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  sample_latent_kernel<<<blocks, 256, 0, st>>>(mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset,
-                                               eps_in ? nullptr : g_step_dyn);
+  CUDA_TRY(launch_pdl(sample_latent_kernel, dim3(blocks), dim3(256), 0, st, mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset,
+                                               eps_in ? nullptr : g_step_dyn));
   LAUNCH_CHECK();
   return 0;
 }
@@ -291,6 +317,7 @@ int philox_fill(uint64_t seed, int stream_id, int64_t img_offset, int B, int k, 
 __global__ void normal_logp_rows_kernel(const float* __restrict__ z, const float* __restrict__ mu,
                                         const float* __restrict__ sd, int bcast, float std_extra, int B, int64_t R, int d,
                                         float* __restrict__ out) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -318,12 +345,13 @@ int normal_logp_rows(const float* z, const float* mu, const float* sd, int bcast
   if (R == 0) return 0;
   int64_t blocks = (R + 7) / 8;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  normal_logp_rows_kernel<<<(int)blocks, 256, 0, st>>>(z, mu, sd, bcast, std_extra, B, R, d, out);
+  CUDA_TRY(launch_pdl(normal_logp_rows_kernel, dim3((int)blocks), dim3(256), 0, st, z, mu, sd, bcast, std_extra, B, R, d, out));
   LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void normal_logp_rows_multi_kernel(NlpJobs jobs, int B, int64_t R) {
+  pdl_wait();
   const NlpJob& jb = jobs.job[blockIdx.y];
   const float* __restrict__ z = jb.z; const float* __restrict__ mu = jb.mu; const float* __restrict__ sd = jb.sd;
   const int d = jb.d, bcast = jb.bcast; const float std_extra = jb.std_extra;
@@ -353,13 +381,14 @@ int normal_logp_rows_multi(const NlpJobs& jobs, int B, int k, cudaStream_t st) {
   if (R == 0 || jobs.count == 0) return 0;
   int64_t blocks = (R + 7) / 8;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  normal_logp_rows_multi_kernel<<<dim3((unsigned)blocks, (unsigned)jobs.count), 256, 0, st>>>(jobs, B, R);
+  CUDA_TRY(launch_pdl(normal_logp_rows_multi_kernel, dim3(dim3((unsigned)blocks, (unsigned)jobs.count)), dim3(256), 0, st, jobs, B, R));
   LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void kl_rows_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int B, int d,
                                float* __restrict__ out) {
+  pdl_wait();
   // tfd.kl_divergence(N(mu,sd), N(0,1)) = 0.5 mu^2 + 0.5 expm1(2 log sd) - log sd   (A.2)
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -374,12 +403,13 @@ __global__ void kl_rows_kernel(const float* __restrict__ mu, const float* __rest
   if (lane == 0) out[b] = s;
 }
 int kl_rows(const float* mu, const float* sd, int B, int d, float* out, cudaStream_t st) {
-  kl_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(mu, sd, B, d, out);
+  CUDA_TRY(launch_pdl(kl_rows_kernel, dim3((B + 7) / 8), dim3(256), 0, st, mu, sd, B, d, out));
   LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void bern_reduce_partials_kernel(const float* __restrict__ p, int64_t R, int nt, float* __restrict__ out) {
+  pdl_wait();
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int t = 0; t < nt; ++t) s += p[r * nt + t];
@@ -389,7 +419,7 @@ __global__ void bern_reduce_partials_kernel(const float* __restrict__ p, int64_t
 int bern_reduce_partials(const float* partial, int R, int nt, float* lpxz, cudaStream_t st) {
   if (R == 0) return 0;
   int blocks = (R + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-  bern_reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, R, nt, lpxz);
+  CUDA_TRY(launch_pdl(bern_reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, partial, R, nt, lpxz));
   LAUNCH_CHECK();
   return 0;
 }
@@ -438,6 +468,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 }
 
 __global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
+  pdl_wait();
   __shared__ float red[8];
   extern __shared__ float s_al[];      // normalised weights of this image when k fits (a.al_in_smem)
   const int b = blockIdx.x, B = a.B, k = a.k;
@@ -511,13 +542,14 @@ int logw_reduce(const LogwArgs& a0, cudaStream_t st) {
   if (a0.B == 0) return 0;
   LogwArgs a = a0;
   a.al_in_smem = (a.k <= 10240 && (a.snis1 || a.snis2)) ? 1 : 0;
-  logw_reduce_kernel<<<a.B, 256, a.al_in_smem ? sizeof(float) * a.k : 0, st>>>(a);
+  CUDA_TRY(launch_pdl(logw_reduce_kernel, dim3(a.B), dim3(256), a.al_in_smem ? sizeof(float) * a.k : 0, st, a));
   LAUNCH_CHECK();
   return 0;
 }
 
 // Batch-mean scalars of the result dict (iwae1.py:119-134): one CTA, fixed order -> deterministic.
 __global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
+  pdl_wait();
   // eight means in ONE pass: all loads are issued before the first reduction (eight serial block reductions, each
   // waiting for its own global loads, were a 12 us kernel on the train step's critical path)
   __shared__ float red[8][8];
@@ -557,7 +589,7 @@ __global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
   }
 }
 int finalize_scalars(const ScalarArgs& a, cudaStream_t st) {
-  finalize_scalars_kernel<<<1, 256, 0, st>>>(a);
+  CUDA_TRY(launch_pdl(finalize_scalars_kernel, dim3(1), dim3(256), 0, st, a));
   LAUNCH_CHECK();
   return 0;
 }
@@ -587,6 +619,7 @@ int sum_to_double(const float* v, int64_t n, double* acc, int accumulate, cudaSt
 // g[r] = d(-objective)/d(log_w[r])  (A.4): iwae_elbo / iwae_eq14 / DReG-decoder -> -al/B ; vae -> -1/(kB)
 __global__ void row_coef_kernel(const float* __restrict__ al, int64_t R, int k, int objective, int B_norm,
                                 float* __restrict__ g) {
+  pdl_wait();
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
     float v;
     if (objective == IWAE_OBJ_VAE_ELBO || objective == IWAE_OBJ_VAE_ELBO_KL) v = -1.f / ((float)k * (float)B_norm);
@@ -598,7 +631,7 @@ int row_coef(const float* al, int B, int k, int objective, int B_norm, float* g,
   const int64_t R = (int64_t)B * k;
   if (R == 0) return 0;
   int blocks = (int)((R + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  row_coef_kernel<<<blocks, 256, 0, st>>>(al, R, k, objective, B_norm, g);
+  CUDA_TRY(launch_pdl(row_coef_kernel, dim3(blocks), dim3(256), 0, st, al, R, k, objective, B_norm, g));
   LAUNCH_CHECK();
   return 0;
 }
@@ -606,6 +639,7 @@ int row_coef(const float* al, int B, int k, int objective, int B_norm, float* g,
 // dl[r,j] = g[r] * (x[b,j] - sigmoid(l[r,j]))
 __global__ void dlogits_kernel(const float* __restrict__ logits, const float* __restrict__ x,
                                const float* __restrict__ g, int64_t R, int B, int n, float* __restrict__ dl) {
+  pdl_wait();
   const int64_t total = R * n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / n;
@@ -619,7 +653,7 @@ int dlogits_f32(const float* logits, const float* x, const float* g, int R, int 
   const int64_t total = (int64_t)R * n;
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  dlogits_kernel<<<blocks, 256, 0, st>>>(logits, x, g, R, B, n, dl);
+  CUDA_TRY(launch_pdl(dlogits_kernel, dim3(blocks), dim3(256), 0, st, logits, x, g, R, B, n, dl));
   LAUNCH_CHECK();
   return 0;
 }
@@ -628,6 +662,7 @@ int dlogits_f32(const float* logits, const float* x, const float* g, int R, int 
 // and the KS partial sums are added in a fixed order through shared memory.
 // Uses the total-derivative identities of A.4: d lq/d mu = 0, d lq/d std = -1/std.
 __global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
+  pdl_wait();
   __shared__ float red[4][256];
   const int b = blockIdx.x;
   const int KS = max(1, 256 / a.d);                 // sample slices handled in parallel
@@ -703,7 +738,7 @@ __global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
 int latent1_bwd(const Latent1BwdArgs& a, cudaStream_t st) {
   if (a.B * a.d == 0) return 0;
   IWAE_REQUIRE(a.d <= 256, "latent1_bwd: latent size above 256 is not supported");
-  latent1_bwd_kernel<<<a.B, 256, 0, st>>>(a);
+  CUDA_TRY(launch_pdl(latent1_bwd_kernel, dim3(a.B), dim3(256), 0, st, a));
   LAUNCH_CHECK();
   return 0;
 }
@@ -713,6 +748,7 @@ int latent1_bwd(const Latent1BwdArgs& a, cudaStream_t st) {
 __global__ void gauss_rows_bwd_kernel(const float* __restrict__ g, const float* __restrict__ z,
                                       const float* __restrict__ pmu, const float* __restrict__ pstd, int64_t R, int d,
                                       float* __restrict__ dpmu, float* __restrict__ dpa) {
+  pdl_wait();
   const int64_t total = R * d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const float gg = g[i / d];
@@ -727,13 +763,14 @@ int gauss_rows_bwd(const float* g, const float* z, const float* pmu, const float
   const int64_t total = R * d;
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  gauss_rows_bwd_kernel<<<blocks, 256, 0, st>>>(g, z, pmu, pstd, R, d, dpmu, dpa);
+  CUDA_TRY(launch_pdl(gauss_rows_bwd_kernel, dim3(blocks), dim3(256), 0, st, g, z, pmu, pstd, R, d, dpmu, dpa));
   LAUNCH_CHECK();
   return 0;
 }
 
 // Second stochastic layer of IWAE2 (all per row): z2 = mu2 + std2*eps2, lpz2 = N(0,1), -lq2 total.
 __global__ void latent2_bwd_kernel(Latent2BwdArgs a) {
+  pdl_wait();
   const int64_t total = (int64_t)a.R * a.d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / a.d;
@@ -748,7 +785,7 @@ int latent2_bwd(const Latent2BwdArgs& a, cudaStream_t st) {
   const int64_t total = (int64_t)a.R * a.d;
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
-  latent2_bwd_kernel<<<blocks, 256, 0, st>>>(a);
+  CUDA_TRY(launch_pdl(latent2_bwd_kernel, dim3(blocks), dim3(256), 0, st, a));
   LAUNCH_CHECK();
   return 0;
 }
@@ -797,6 +834,7 @@ int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
 __global__ void grad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t n, float* __restrict__ g,
                                    float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float lr_t,
                                    float b1, float b2, float eps, const StepDyn* __restrict__ dyn) {
+  pdl_wait();
   if (dyn) { lr_t = dyn->lr_t; b1 = dyn->b1; b2 = dyn->b2; eps = dyn->eps; }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -814,7 +852,7 @@ __global__ void grad_reduce_kernel(const float* __restrict__ ws, int splits, int
 int grad_reduce(const float* ws, int splits, int64_t n, float* grads, cudaStream_t st) {
   if (n == 0) return 0;
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, grads, nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, nullptr);
+  CUDA_TRY(launch_pdl(grad_reduce_kernel, dim3(blocks), dim3(256), 0, st, ws, splits, n, grads, nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, nullptr));
   LAUNCH_CHECK();
   return 0;
 }
@@ -823,7 +861,7 @@ int adam_from_partials(float* p, const float* ws, int splits, float* m, float* v
   if (n == 0) return 0;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  grad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, n, nullptr, p, m, v, (float)lr_t, b1, b2, eps, g_step_dyn);
+  CUDA_TRY(launch_pdl(grad_reduce_kernel, dim3(blocks), dim3(256), 0, st, ws, splits, n, nullptr, p, m, v, (float)lr_t, b1, b2, eps, g_step_dyn));
   LAUNCH_CHECK();
   return 0;
 }
@@ -945,6 +983,7 @@ int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64
 // ---- split-K forward epilogue ----
 __global__ void splitk_bias_act_kernel(const float* __restrict__ partial, int splits, int M, int N,
                                        const float* __restrict__ bias, int act, float* __restrict__ out) {
+  pdl_wait();
   const int total = M * N;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -957,13 +996,14 @@ __global__ void splitk_bias_act_kernel(const float* __restrict__ partial, int sp
 }
 int splitk_bias_act(const float* partial, int splits, int M, int N, const float* bias, int act, float* out, cudaStream_t st) {
   if (M * N == 0) return 0;
-  splitk_bias_act_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(partial, splits, M, N, bias, act, out);
+  CUDA_TRY(launch_pdl(splitk_bias_act_kernel, dim3((M * N + 255) / 256), dim3(256), 0, st, partial, splits, M, N, bias, act, out));
   LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void splitk_mul_h_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ H,
                                     int64_t ld_h, int accumulate, float* __restrict__ dX, int64_t ld_dx) {
+  pdl_wait();
   const int total = M * N;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int m = i / N, n = i % N;
@@ -978,7 +1018,7 @@ int splitk_mul_h(const float* partial, int splits, int M, int N, const float* H,
                  int64_t ld_dx, cudaStream_t st) {
   if (M * N == 0) return 0;
   const int blocks = std::min((M * N + 255) / 256, 148 * 8);
-  splitk_mul_h_kernel<<<blocks, 256, 0, st>>>(partial, splits, M, N, H, ld_h, accumulate, dX, ld_dx);
+  CUDA_TRY(launch_pdl(splitk_mul_h_kernel, dim3(blocks), dim3(256), 0, st, partial, splits, M, N, H, ld_h, accumulate, dX, ld_dx));
   LAUNCH_CHECK();
   return 0;
 }
@@ -1005,6 +1045,222 @@ int copy_table(const CopyTable& t, cudaStream_t st) {
   for (int i = 0; i < t.count; ++i) nmax = std::max(nmax, t.n[i]);
   const int bx = (int)std::min<long long>((nmax + 255) / 256, 296);
   copy_table_kernel<<<dim3(bx, t.count), 256, 0, st>>>(t);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// Fused Dense chain (train step): a tile of TM rows goes through up to THREE Dense layers in one launch.
+// At the training shapes (k*B = 1,000 rows, 50..200 units) a Dense layer is ~1 us of FFMAs behind ~6 us of launch,
+// drain and pipeline-fill latency, and a BasicBlock (iwae1.py:36-44) is four of them in a row.  Here one CTA keeps its
+// rows' activations in shared memory, streams each layer's weights from L2 (coalesced: thread n reads W[k][n]) and
+// writes every layer's output to global memory as well (the backward pass needs them).  The backward pass of a block
+// is the SAME kernel on transposed weights (dX = dY W^T is a forward product with W^T; transpose_jobs builds them once
+// per step, off the critical path) with the activation replaced by the multiplication with tanh' = 1 - H^2.
+// =============================================================================================
+constexpr int CHAIN_KT = 32;          // weight rows per shared-memory chunk
+constexpr int CHAIN_TM = 8;           // rows per CTA
+
+template <int V>
+__device__ __forceinline__ void chain_cp_async(float* dst, const float* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  if (V == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  else if (V == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+template <int V>
+__device__ __forceinline__ void chain_copy_flat(float* dst, const float* src, int cnt, int tid) {
+  for (int i = tid * V; i < cnt; i += 256 * V) chain_cp_async<V>(dst + i, src + i);
+}
+// Rows [c*KT, c*KT + KT) of layer L's weights -> wb, one cp.async group.  A kernel's rows are contiguous (ldw == its
+// width), so the chunk is a flat copy; a second head goes to wb + KT*ldw.  Rows beyond K are zero up to a multiple of 4.
+__device__ __forceinline__ void chain_load_chunk(const ChainLayer& L, int c, float* wb, int tid) {
+  const int k0 = c * CHAIN_KT;
+  const int rows = min(CHAIN_KT, L.K - k0);
+  const int cnt = rows * L.ldw, cnt4 = ((rows + 3) & ~3) * L.ldw;
+  const int parts = L.Wb ? 2 : 1;
+  for (int p = 0; p < parts; ++p) {
+    const float* src = (p ? L.Wb : L.W) + (int64_t)k0 * L.ldw;
+    float* dst = wb + p * CHAIN_KT * L.ldw;
+    if (L.vec == 4) chain_copy_flat<4>(dst, src, cnt, tid);
+    else if (L.vec == 2) chain_copy_flat<2>(dst, src, cnt, tid);
+    else chain_copy_flat<1>(dst, src, cnt, tid);
+    for (int i = cnt + tid; i < cnt4; i += 256) dst[i] = 0.f;
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// acc[r] += sum_kk x[r][kk] * w[kk] over the valid rows of one chunk (steps of 4; rows beyond K are zero in both operands)
+template <int RG>
+__device__ __forceinline__ void chain_fma_chunk(const float* __restrict__ wb, int ws, const float* __restrict__ xin, int kpad,
+                                                int ksteps, float (&acc)[8]) {
+#pragma unroll 4
+  for (int s = 0; s < ksteps; ++s) {
+    const float w0 = wb[0], w1 = wb[ws], w2 = wb[2 * ws], w3 = wb[3 * ws];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(&xin[r * kpad]);                         // warp-wide broadcast
+      acc[r] = fmaf(x.x, w0, acc[r]); acc[r] = fmaf(x.y, w1, acc[r]);
+      acc[r] = fmaf(x.z, w2, acc[r]); acc[r] = fmaf(x.w, w3, acc[r]);
+    }
+    wb += 4 * ws; xin += 4;
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_chain_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ __align__(16) float chain_sm[];
+  constexpr int TM = CHAIN_TM;
+  const int kpad = a.kpad;
+  float* in = chain_sm;
+  float* nxt = chain_sm + (size_t)TM * kpad;
+  float* wbuf = chain_sm + 2 * (size_t)TM * kpad;          // [2][a.wsz]
+  const int tid = threadIdx.x;
+  const int r_base = blockIdx.x * TM;
+  // The weights were written long before the kernel this launch programmatically depends on (Adam of the previous
+  // step / the transposes at the start of this one), so the first chunk is fetched BEFORE the dependency wait.
+  chain_load_chunk(a.L[0], 0, wbuf, tid);
+  pdl_wait();
+  // stage-0 input: [X | X2] rows of this tile, zero beyond the data (rows >= M, columns >= kx + kx2)
+  {
+    const int kin = a.kx + a.kx2;
+#pragma unroll 4
+    for (int i = tid; i < TM * kpad; i += 256) {
+      const int r = i / kpad, c = i - r * kpad;
+      const int gr = r_base + r;
+      const bool ok = gr < a.M && c < kin;
+      const float* src = (c < a.kx) ? a.X + (int64_t)gr * a.ldx + c : a.X2 + (int64_t)gr * a.ldx2 + (c - a.kx);
+      in[i] = ok ? __ldg(src) : 0.f;
+    }
+  }
+  int job = 0;                                               // flat (layer, chunk) counter: selects the weight buffer
+#pragma unroll 1
+  for (int l = 0; l < a.nlayers; ++l) {
+    const ChainLayer& L = a.L[l];
+    const int NC = min(256, (L.N + 31) & ~31);          // column slots (N <= 256 is checked on the host)
+    const int G = 256 / NC;                              // row groups that fit the CTA (1, 2, 4 or 8)
+    const int RG = TM / G;                               // rows per thread
+    const int n = tid % NC, g = tid / NC;
+    const bool active = g < G && n < L.N;
+    const bool second = active && n >= L.nsplit;
+    const int r0 = g * RG;
+    const int nchunks = (L.K + CHAIN_KT - 1) / CHAIN_KT;
+    const int wcol = second ? CHAIN_KT * L.ldw + (n - L.nsplit) : n;
+    // epilogue operands fetched now: their latency hides behind the products
+    float hmul[8];
+    float bias = 0.f;
+    const int act = second ? L.actb : L.act;
+    if (active) {
+      const float* bp = second ? L.biasb : L.bias;
+      if (bp) bias = __ldg(bp + (second ? n - L.nsplit : n));
+      if (act == CH_MULH) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int gr = r_base + r0 + r;
+          hmul[r] = (r < RG && gr < a.M) ? __ldg(L.H + (int64_t)gr * L.ldh + n) : 0.f;
+        }
+      }
+    }
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c, ++job) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();      // chunk `job` has landed; every thread is done with chunk job-1 and with the previous layer
+      float* wnext = wbuf + (size_t)((job + 1) & 1) * a.wsz;
+      if (c + 1 < nchunks) chain_load_chunk(L, c + 1, wnext, tid);
+      else if (l + 1 < a.nlayers) chain_load_chunk(a.L[l + 1], 0, wnext, tid);
+      if (active) {
+        const float* wb = wbuf + (size_t)(job & 1) * a.wsz + wcol;
+        const float* xin = in + (size_t)r0 * kpad + c * CHAIN_KT;
+        const int ksteps = (min(CHAIN_KT, L.K - c * CHAIN_KT) + 3) >> 2;
+        if (RG == 8) chain_fma_chunk<8>(wb, L.ldw, xin, kpad, ksteps, acc);
+        else if (RG == 4) chain_fma_chunk<4>(wb, L.ldw, xin, kpad, ksteps, acc);
+        else if (RG == 2) chain_fma_chunk<2>(wb, L.ldw, xin, kpad, ksteps, acc);
+        else chain_fma_chunk<1>(wb, L.ldw, xin, kpad, ksteps, acc);
+      }
+    }
+    // the next layer reads the columns of `nxt` up to its K rounded to 4 (<= kpad): clear what this layer does not write
+    for (int i = tid; i < TM * 4; i += 256) { const int c = L.N + (i & 3); if (c < kpad) nxt[(i >> 2) * kpad + c] = 0.f; }
+    if (active) {
+      float* og = second ? L.outb : L.out;
+      const int64_t ldo = second ? L.ldob : L.ldo;
+      const int on = second ? n - L.nsplit : n;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r < RG) {
+          const int gr = r_base + r0 + r;
+          float v = acc[r] + bias;
+          if (act == CH_TANH) v = tanhf(v);
+          else if (act == CH_EXP_EPS) v = expf(v) + 1e-6f;
+          else if (act == CH_MULH) v *= (1.f - hmul[r] * hmul[r]);
+          nxt[(size_t)(r0 + r) * kpad + n] = v;
+          if (og && gr < a.M) og[(int64_t)gr * ldo + on] = v;
+        }
+      }
+    }
+    float* t = in; in = nxt; nxt = t;
+    // no barrier here: the first chunk of the next layer starts with one
+  }
+}
+
+int dense_chain(const ChainArgs& a_in, cudaStream_t st) {
+  ChainArgs a = a_in;
+  int kmax = (a.kx + a.kx2 + 3) & ~3, wsz = 0;
+  for (int l = 0; l < a.nlayers; ++l) {
+    ChainLayer& L = a.L[l];
+    IWAE_REQUIRE(L.N <= 256 && L.N > 0, "dense_chain: layer width %d not in [1,256]", L.N);
+    IWAE_REQUIRE(L.K <= kmax, "dense_chain: layer %d reads %d columns, the previous layer has %d", l, L.K, kmax);
+    IWAE_REQUIRE(L.ldw == (L.Wb ? L.nsplit : L.N) && (!L.Wb || L.N == 2 * L.nsplit),
+                 "dense_chain: layer %d: the weight rows must be contiguous (ldw %d, width %d)", l, L.ldw, L.N);
+    // widest cp.async every chunk of this layer's weights is aligned for
+    auto al = [](const void* p, int v) { return p == nullptr || ((uintptr_t)p % (4 * v)) == 0; };
+    int v = 4;
+    while (v > 1 && !(L.ldw % v == 0 && al(L.W, v) && al(L.Wb, v))) v >>= 1;
+    L.vec = v;
+    kmax = std::max(kmax, (L.N + 3) & ~3);
+    wsz = std::max(wsz, CHAIN_KT * L.ldw * (L.Wb ? 2 : 1));
+  }
+  a.kpad = kmax;
+  a.wsz = (wsz + 3) & ~3;
+  a.TM = CHAIN_TM;
+  if (a.M <= 0) return 0;
+  const size_t smem = (2 * (size_t)CHAIN_TM * a.kpad + 2 * (size_t)a.wsz) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  IWAE_REQUIRE(smem <= 100 * 1024, "dense_chain: %zu bytes of shared memory", smem);
+  CUDA_TRY(launch_pdl(dense_chain_kernel, dim3((a.M + CHAIN_TM - 1) / CHAIN_TM), dim3(256), smem, st, a));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[c][r] = src[r][c] for a table of matrices (the transposed weights of the fused backward chains), one launch
+__global__ void __launch_bounds__(256) transpose_jobs_kernel(TransposeJobs t) {
+  pdl_wait();
+  __shared__ float tile[32][33];
+  const TransposeJob j = t.job[blockIdx.y];
+  const int tiles_c = (j.cols + 31) / 32, tiles_r = (j.rows + 31) / 32;
+  for (int tt = blockIdx.x; tt < tiles_c * tiles_r; tt += gridDim.x) {
+    const int tr = tt / tiles_c, tc = tt % tiles_c;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int r = tr * 32 + i, c = tc * 32 + tx;
+      tile[i][tx] = (r < j.rows && c < j.cols) ? j.src[(int64_t)r * j.ld_src + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = tc * 32 + i, r = tr * 32 + tx;
+      if (r < j.rows && c < j.cols) j.dst[(int64_t)c * j.ld_dst + r] = tile[tx][i];
+    }
+  }
+}
+int transpose_jobs(const TransposeJobs& t, cudaStream_t st) {
+  if (t.count == 0) return 0;
+  CUDA_TRY(launch_pdl(transpose_jobs_kernel, dim3(24, t.count), dim3(256), 0, st, t));
   LAUNCH_CHECK();
   return 0;
 }
