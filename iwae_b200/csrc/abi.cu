@@ -243,9 +243,6 @@ static int dense_fwd(const float* P, const DenseP& L, const float* X, int64_t ld
 constexpr int64_t CHAIN_MAX_ROWS = 4096;
 // experimental until it beats the per-layer kernels: IWAE_CHAIN=1 turns it on
 static bool chain_enabled() { static const bool on = getenv("IWAE_CHAIN") != nullptr; return on; }
-static bool chain_ok(const BlockP& blk, int64_t M) {
-  return M <= CHAIN_MAX_ROWS && blk.l1.n_out <= 256 && 2 * blk.lmu.n_out <= 256 && blk.l1.n_in <= 256 * 4;
-}
 static void chain_dense(ChainLayer& L, const float* P, const DenseP& D, int act, float* out) {
   L.W = P + D.w; L.ldw = D.n_out; L.bias = P + D.b; L.K = D.n_in; L.N = D.n_out; L.nsplit = D.n_out;
   L.act = act; L.out = out; L.ldo = D.n_out;
@@ -257,27 +254,22 @@ static void chain_heads(ChainLayer& L, const float* P, const BlockP& blk, float*
   L.act = CH_NONE; L.actb = CH_EXP_EPS;                         // exp(a) + 1e-6 (iwae1.py:34,42)
   L.out = mu; L.ldo = d; L.outb = sd; L.ldob = d;
 }
-static int block_fwd_chain(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
-                           float* mu, float* sd, cudaStream_t st, float* l1_scratch) {
+static ChainArgs block_fwd_chain_args(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1,
+                                      float* h2, float* mu, float* sd) {
   ChainArgs a;
-  a.M = (int)M;
-  int n = 0;
-  if (blk.l1.n_in > 256) {
-    IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st, l1_scratch));
-    a.X = h1; a.ldx = blk.l1.n_out; a.kx = blk.l1.n_out;
-  } else {
-    a.X = X; a.ldx = ldx; a.kx = blk.l1.n_in;
-    chain_dense(a.L[n++], P, blk.l1, CH_TANH, h1);
-  }
-  chain_dense(a.L[n++], P, blk.l2, CH_TANH, h2);
-  chain_heads(a.L[n++], P, blk, mu, sd);
-  a.nlayers = n;
-  return dense_chain(a, st);
+  a.M = (int)M; a.X = X; a.ldx = ldx; a.kx = blk.l1.n_in; a.nlayers = 3;
+  chain_dense(a.L[0], P, blk.l1, CH_TANH, h1);
+  chain_dense(a.L[1], P, blk.l2, CH_TANH, h2);
+  chain_heads(a.L[2], P, blk, mu, sd);
+  return a;
 }
 
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
                      float* mu, float* sd, cudaStream_t st, float* l1_scratch, iwae_ctx* lane_ctx, cudaStream_t lane) {
-  if (lane_ctx && lane && chain_enabled() && chain_ok(blk, M)) return block_fwd_chain(P, blk, X, ldx, M, h1, h2, mu, sd, st, l1_scratch);
+  if (lane_ctx && lane && chain_enabled() && M <= CHAIN_MAX_ROWS) {
+    const ChainArgs a = block_fwd_chain_args(P, blk, X, ldx, M, h1, h2, mu, sd);
+    if (dense_chain_fits(a)) return dense_chain(a, st);
+  }
   IWAE_TRY(dense_fwd(P, blk.l1, X, ldx, M, ACT_TANH, h1, st, l1_scratch));
   IWAE_TRY(dense_fwd(P, blk.l2, h1, blk.l1.n_out, M, ACT_TANH, h2, st));
   // the two heads read the same h2 and are independent: in a train step the std head runs on a side stream
@@ -363,13 +355,15 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     f.zin = zin; f.ld_zin = d1 + nc;
   } else { f.zin = f.z1; f.ld_zin = d1; }
   IWAE_TRY(ar.get(&f.a1, (size_t)R * h1)); IWAE_TRY(ar.get(&f.a2, (size_t)R * h1));
-  if (opt.lanes && chain_enabled() && R <= CHAIN_MAX_ROWS && h1 <= 256 && f.ld_zin <= 256) {
+  bool dec_chained = false;
+  if (opt.lanes && chain_enabled() && R <= CHAIN_MAX_ROWS) {
     ChainArgs a;
     a.M = (int)R; a.X = f.zin; a.ldx = f.ld_zin; a.kx = m.dec.d0.n_in; a.nlayers = 2;
     chain_dense(a.L[0], P, m.dec.d0, CH_TANH, f.a1);
     chain_dense(a.L[1], P, m.dec.d1, CH_TANH, f.a2);
-    IWAE_TRY(dense_chain(a, sd));
-  } else {
+    if (dense_chain_fits(a)) { IWAE_TRY(dense_chain(a, sd)); dec_chained = true; }
+  }
+  if (!dec_chained) {
     IWAE_TRY(dense_fwd(P, m.dec.d0, f.zin, f.ld_zin, R, ACT_TANH, f.a1, sd));
     IWAE_TRY(dense_fwd(P, m.dec.d1, f.a1, h1, R, ACT_TANH, f.a2, sd));
   }
@@ -443,6 +437,7 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
     sa.B = B; sa.R = R; sa.beta = beta;
     sa.iwae = f.iwae; sa.vae = f.vae; sa.eq14 = f.eq14; sa.kl = f.kl; sa.dreg = f.dreg;
     sa.lpxz = f.lpxz; sa.lpz = f.lpz; sa.lq1 = f.lq1; sa.out = o->scalars;
+    if (R >= SCALAR_PARTS_MIN_ROWS) IWAE_TRY(ar.get(&sa.partial, (size_t)SCALAR_PARTS * 8));
     // train step: the batch scalars are outputs only - nothing of the backward pass reads them - so they leave the
     // critical path for lane 1 (joined at the end of backward_internal together with the weight gradients)
     cudaStream_t ss = st;
@@ -508,6 +503,7 @@ extern "C" int iwae_forward_tc(iwae_ctx* ctx, const float* params, const float* 
     sa.B = B; sa.R = R; sa.beta = beta;
     sa.iwae = f.iwae; sa.vae = f.vae; sa.eq14 = f.eq14; sa.kl = f.kl;
     sa.lpxz = f.lpxz; sa.lpz = f.lpz; sa.lq1 = f.lq1; sa.out = o->scalars;
+    if (R >= SCALAR_PARTS_MIN_ROWS) IWAE_TRY(ar.get(&sa.partial, (size_t)SCALAR_PARTS * 8));
     IWAE_TRY(finalize_scalars(sa, st));
   }
   return 0;
@@ -759,18 +755,20 @@ static int block_bwd_chain(iwae_ctx* ctx, const BlockP& blk, const float* X, int
                            const float* h1, const float* h2, const float* dmu, const float* da, float* grads, float* dX,
                            cudaStream_t st, cudaStream_t wl) {
   const int h = blk.l1.n_out, d = blk.lmu.n_out;
-  float *dh2, *dh1;
-  IWAE_TRY(ctx->arena.get(&dh2, (size_t)M * h)); IWAE_TRY(ctx->arena.get(&dh1, (size_t)M * h));
-  IWAE_TRY(dense_bwd_w(ctx, blk.lmu, h2, h, M, dmu, grads, st, wl));
-  IWAE_TRY(dense_bwd_w(ctx, blk.lstd, h2, h, M, da, grads, st, wl));
   ChainArgs a;
   a.M = (int)M; a.X = dmu; a.ldx = d; a.kx = d; a.X2 = da; a.ldx2 = d; a.kx2 = d;
   ChainLayer& L0 = a.L[0];                                  // dh2 = ([dmu | da] [Wmu^T ; Wstd^T]) * (1 - h2^2)
   L0.W = ctx->wt_buf + blk.lmu.w; L0.ldw = h; L0.K = 2 * d; L0.N = h; L0.nsplit = h;
-  L0.act = CH_MULH; L0.H = h2; L0.ldh = h; L0.out = dh2; L0.ldo = h;
-  chain_bwd_dense(a.L[1], ctx->wt_buf, blk.l2, h1, dh1);   // dh1 = (dh2 W2^T) * (1 - h1^2)
+  L0.act = CH_MULH; L0.H = h2; L0.ldh = h; L0.out = nullptr; L0.ldo = h;
+  chain_bwd_dense(a.L[1], ctx->wt_buf, blk.l2, h1, nullptr);   // dh1 = (dh2 W2^T) * (1 - h1^2)
   a.nlayers = 2;
   if (dX) { chain_bwd_dense(a.L[2], ctx->wt_buf, blk.l1, nullptr, dX); a.nlayers = 3; }
+  if (!dense_chain_fits(a)) return 1;                       // the caller falls back to the per-layer products
+  float *dh2, *dh1;
+  IWAE_TRY(ctx->arena.get(&dh2, (size_t)M * h)); IWAE_TRY(ctx->arena.get(&dh1, (size_t)M * h));
+  a.L[0].out = dh2; a.L[1].out = dh1;
+  IWAE_TRY(dense_bwd_w(ctx, blk.lmu, h2, h, M, dmu, grads, st, wl));
+  IWAE_TRY(dense_bwd_w(ctx, blk.lstd, h2, h, M, da, grads, st, wl));
   IWAE_TRY(dense_chain(a, st));
   IWAE_TRY(dense_bwd_w(ctx, blk.l2, h1, h, M, dh2, grads, st, wl));
   IWAE_TRY(dense_bwd_w(ctx, blk.l1, X, ldx, M, dh1, grads, st, wl));
@@ -781,7 +779,10 @@ static int block_bwd_chain(iwae_ctx* ctx, const BlockP& blk, const float* X, int
 static int block_bwd(iwae_ctx* ctx, const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M,
                      const float* h1, const float* h2, const float* dmu, const float* da, float* grads, float* dX,
                      cudaStream_t st, cudaStream_t wl = nullptr, bool chain = false) {
-  if (chain) return block_bwd_chain(ctx, blk, X, ldx, M, h1, h2, dmu, da, grads, dX, st, wl);
+  if (chain) {
+    const int rc = block_bwd_chain(ctx, blk, X, ldx, M, h1, h2, dmu, da, grads, dX, st, wl);
+    if (rc != 1) return rc;                                  // 1: this block's chain does not fit shared memory
+  }
   const int h = blk.l1.n_out;
   float *dh2, *dh1;
   IWAE_TRY(ctx->arena.get(&dh2, (size_t)M * h)); IWAE_TRY(ctx->arena.get(&dh1, (size_t)M * h));
@@ -829,17 +830,17 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
   if (R <= 4096) IWAE_TRY(ar.get(&dx_scratch, (size_t)BWDX_SPLITS * R * h1));
   IWAE_TRY(dense_bwd_x(P, m.dec.d2, dl, R, da2, h1, 0, f.a2, h1, s_dec, dx_scratch));
   IWAE_TRY(dense_bwd_w(ctx, m.dec.d1, f.a1, h1, R, da2, grads, s_dec, w_dec));
+  bool dec_chain = false;
   if (chain) {
     ChainArgs a;                                             // da1 = (da2 W1^T) * (1 - a1^2) ; dzin = da1 W0^T
     a.M = (int)R; a.X = da2; a.ldx = h1; a.kx = h1; a.nlayers = 2;
     chain_bwd_dense(a.L[0], ctx->wt_buf, m.dec.d1, f.a1, da1);
     chain_bwd_dense(a.L[1], ctx->wt_buf, m.dec.d0, nullptr, dzin);
-    IWAE_TRY(dense_chain(a, s_dec));
-  } else {
-    IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, s_dec));
+    if (dense_chain_fits(a)) { IWAE_TRY(dense_chain(a, s_dec)); dec_chain = true; }
   }
+  if (!dec_chain) IWAE_TRY(dense_bwd_x(P, m.dec.d1, da2, R, da1, h1, 0, f.a1, h1, s_dec));
   IWAE_TRY(dense_bwd_w(ctx, m.dec.d0, f.zin, f.ld_zin, R, da1, grads, s_dec, w_dec));
-  if (!chain) IWAE_TRY(dense_bwd_x(P, m.dec.d0, da1, R, dzin, m.dec_in(), 0, nullptr, 0, s_dec));
+  if (!dec_chain) IWAE_TRY(dense_bwd_x(P, m.dec.d0, da1, R, dzin, m.dec_in(), 0, nullptr, 0, s_dec));
 
   float* dz1_q = nullptr;
   if (m.two_layer()) {

@@ -193,7 +193,12 @@ struct ScalarArgs {
   const float *iwae = nullptr, *vae = nullptr, *eq14 = nullptr, *kl = nullptr, *dreg = nullptr;
   const float *lpxz = nullptr, *lpz = nullptr, *lq1 = nullptr;
   float* out = nullptr;   // [8]
+  // large calls (val_step on the whole test set: k*B = 500,000 rows): `partial` [SCALAR_PARTS][8] receives per-CTA sums of
+  // contiguous slices first; the single finalising CTA then adds SCALAR_PARTS values per mean in a fixed order
+  float* partial = nullptr;
 };
+constexpr int SCALAR_PARTS = 296;
+constexpr int64_t SCALAR_PARTS_MIN_ROWS = 32768;     // below this one CTA reads everything itself
 int finalize_scalars(const ScalarArgs& a, cudaStream_t st);
 int sum_to_double(const float* v, int64_t n, double* acc, int accumulate, cudaStream_t st);
 
@@ -252,10 +257,11 @@ struct ChainArgs {
   const float* X = nullptr; int64_t ldx = 0; int kx = 0;        // input rows: [X (kx columns) | X2 (kx2 columns)]
   const float* X2 = nullptr; int64_t ldx2 = 0; int kx2 = 0;
   int M = 0, nlayers = 0;
-  int TM = 0, kpad = 0, wsz = 0;                                 // set by dense_chain
+  int TM = 0, kpad = 0, wsz = 0, njobs = 0;                      // set by dense_chain
   ChainLayer L[3];
 };
 int dense_chain(const ChainArgs& a, cudaStream_t st);
+bool dense_chain_fits(const ChainArgs& a);       // every weight chunk of the chain resident in shared memory?
 struct TransposeJob { const float* src; float* dst; int rows, cols; int64_t ld_src, ld_dst; };
 struct TransposeJobs { TransposeJob job[16]; int count = 0; };
 int transpose_jobs(const TransposeJobs& t, cudaStream_t st);

@@ -547,6 +547,37 @@ int logw_reduce(const LogwArgs& a0, cudaStream_t st) {
   return 0;
 }
 
+// Stage 1 of the batch means for large calls: CTA c sums slice c of each of the eight arrays (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) scalars_partial_kernel(ScalarArgs a) {
+  pdl_wait();
+  __shared__ float red[8][8];
+  const float* src[8] = {a.vae, a.iwae, a.eq14, a.kl, a.dreg, a.lpxz, a.lpz, a.lq1};
+  const int64_t len[8] = {a.B, a.B, a.B, a.B, a.B, a.R, a.R, a.R};
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] = 0.f;
+    if (!src[j]) continue;
+    const int64_t per = (len[j] + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = min((int64_t)blockIdx.x * per, len[j]), hi = min(lo + per, len[j]);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s[j] += src[j][i];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[j][threadIdx.x >> 5] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    a.partial[(int64_t)blockIdx.x * 8 + threadIdx.x] = t;
+  }
+}
+
 // Batch-mean scalars of the result dict (iwae1.py:119-134): one CTA, fixed order -> deterministic.
 __global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
   pdl_wait();
@@ -559,7 +590,9 @@ __global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     s[j] = 0.f;
-    if (src[j]) for (int64_t i = threadIdx.x; i < len[j]; i += blockDim.x) s[j] += src[j][i];
+    if (!src[j]) continue;
+    if (a.partial) { for (int i = threadIdx.x; i < SCALAR_PARTS; i += blockDim.x) s[j] += a.partial[i * 8 + j]; }
+    else for (int64_t i = threadIdx.x; i < len[j]; i += blockDim.x) s[j] += src[j][i];
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -589,6 +622,7 @@ __global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
   }
 }
 int finalize_scalars(const ScalarArgs& a, cudaStream_t st) {
+  if (a.partial) { CUDA_TRY(launch_pdl(scalars_partial_kernel, dim3(SCALAR_PARTS), dim3(256), 0, st, a)); LAUNCH_CHECK(); }
   CUDA_TRY(launch_pdl(finalize_scalars_kernel, dim3(1), dim3(256), 0, st, a));
   LAUNCH_CHECK();
   return 0;
@@ -1107,18 +1141,47 @@ __device__ __forceinline__ void chain_fma_chunk(const float* __restrict__ wb, in
   }
 }
 
+// wait until at most `n` of this thread's cp.async groups are pending (the operand must be an immediate)
+__device__ __forceinline__ void chain_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    case 7: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    case 8: asm volatile("cp.async.wait_group 8;" ::: "memory"); break;
+    case 9: asm volatile("cp.async.wait_group 9;" ::: "memory"); break;
+    case 10: asm volatile("cp.async.wait_group 10;" ::: "memory"); break;
+    case 11: asm volatile("cp.async.wait_group 11;" ::: "memory"); break;
+    case 12: asm volatile("cp.async.wait_group 12;" ::: "memory"); break;
+    case 13: asm volatile("cp.async.wait_group 13;" ::: "memory"); break;
+    case 14: asm volatile("cp.async.wait_group 14;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 15;" ::: "memory"); break;
+  }
+}
+
 __global__ void __launch_bounds__(256) dense_chain_kernel(const __grid_constant__ ChainArgs a) {
   extern __shared__ __align__(16) float chain_sm[];
   constexpr int TM = CHAIN_TM;
   const int kpad = a.kpad;
   float* in = chain_sm;
   float* nxt = chain_sm + (size_t)TM * kpad;
-  float* wbuf = chain_sm + 2 * (size_t)TM * kpad;          // [2][a.wsz]
+  float* wbuf = chain_sm + 2 * (size_t)TM * kpad;          // [a.njobs][a.wsz]: every weight chunk of the chain
   const int tid = threadIdx.x;
   const int r_base = blockIdx.x * TM;
   // The weights were written long before the kernel this launch programmatically depends on (Adam of the previous
-  // step / the transposes at the start of this one), so the first chunk is fetched BEFORE the dependency wait.
-  chain_load_chunk(a.L[0], 0, wbuf, tid);
+  // step / the transposes at the start of this one): ALL of them are requested BEFORE the dependency wait, one cp.async
+  // group per chunk, so the round trips to L2 overlap the tail of the previous kernel and each other.
+  {
+    int job = 0;
+    for (int l = 0; l < a.nlayers; ++l) {
+      const int nchunks = (a.L[l].K + CHAIN_KT - 1) / CHAIN_KT;
+      for (int c = 0; c < nchunks; ++c, ++job) chain_load_chunk(a.L[l], c, wbuf + (size_t)job * a.wsz, tid);
+    }
+  }
   pdl_wait();
   // stage-0 input: [X | X2] rows of this tile, zero beyond the data (rows >= M, columns >= kx + kx2)
   {
@@ -1132,7 +1195,7 @@ __global__ void __launch_bounds__(256) dense_chain_kernel(const __grid_constant_
       in[i] = ok ? __ldg(src) : 0.f;
     }
   }
-  int job = 0;                                               // flat (layer, chunk) counter: selects the weight buffer
+  int job = 0;                                               // flat (layer, chunk) counter: selects the weight slot
 #pragma unroll 1
   for (int l = 0; l < a.nlayers; ++l) {
     const ChainLayer& L = a.L[l];
@@ -1165,13 +1228,10 @@ __global__ void __launch_bounds__(256) dense_chain_kernel(const __grid_constant_
     for (int r = 0; r < 8; ++r) acc[r] = 0.f;
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c, ++job) {
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      __syncthreads();      // chunk `job` has landed; every thread is done with chunk job-1 and with the previous layer
-      float* wnext = wbuf + (size_t)((job + 1) & 1) * a.wsz;
-      if (c + 1 < nchunks) chain_load_chunk(L, c + 1, wnext, tid);
-      else if (l + 1 < a.nlayers) chain_load_chunk(a.L[l + 1], 0, wnext, tid);
+      chain_wait_pending(a.njobs - 1 - job);
+      __syncthreads();      // chunk `job` has landed for every thread; the previous layer's outputs are in `in`
       if (active) {
-        const float* wb = wbuf + (size_t)(job & 1) * a.wsz + wcol;
+        const float* wb = wbuf + (size_t)job * a.wsz + wcol;
         const float* xin = in + (size_t)r0 * kpad + c * CHAIN_KT;
         const int ksteps = (min(CHAIN_KT, L.K - c * CHAIN_KT) + 3) >> 2;
         if (RG == 8) chain_fma_chunk<8>(wb, L.ldw, xin, kpad, ksteps, acc);
@@ -1204,15 +1264,13 @@ __global__ void __launch_bounds__(256) dense_chain_kernel(const __grid_constant_
   }
 }
 
-int dense_chain(const ChainArgs& a_in, cudaStream_t st) {
-  ChainArgs a = a_in;
-  int kmax = (a.kx + a.kx2 + 3) & ~3, wsz = 0;
+// fills the derived fields of `a`; returns the dynamic shared memory the launch needs (0: the chain does not qualify)
+static size_t chain_plan(ChainArgs& a) {
+  int kmax = (a.kx + a.kx2 + 3) & ~3, wsz = 0, njobs = 0;
   for (int l = 0; l < a.nlayers; ++l) {
     ChainLayer& L = a.L[l];
-    IWAE_REQUIRE(L.N <= 256 && L.N > 0, "dense_chain: layer width %d not in [1,256]", L.N);
-    IWAE_REQUIRE(L.K <= kmax, "dense_chain: layer %d reads %d columns, the previous layer has %d", l, L.K, kmax);
-    IWAE_REQUIRE(L.ldw == (L.Wb ? L.nsplit : L.N) && (!L.Wb || L.N == 2 * L.nsplit),
-                 "dense_chain: layer %d: the weight rows must be contiguous (ldw %d, width %d)", l, L.ldw, L.N);
+    if (!(L.N <= 256 && L.N > 0 && L.K <= kmax)) return 0;
+    if (!(L.ldw == (L.Wb ? L.nsplit : L.N) && (!L.Wb || L.N == 2 * L.nsplit))) return 0;     // contiguous weight rows
     // widest cp.async every chunk of this layer's weights is aligned for
     auto al = [](const void* p, int v) { return p == nullptr || ((uintptr_t)p % (4 * v)) == 0; };
     int v = 4;
@@ -1220,18 +1278,31 @@ int dense_chain(const ChainArgs& a_in, cudaStream_t st) {
     L.vec = v;
     kmax = std::max(kmax, (L.N + 3) & ~3);
     wsz = std::max(wsz, CHAIN_KT * L.ldw * (L.Wb ? 2 : 1));
+    njobs += (L.K + CHAIN_KT - 1) / CHAIN_KT;
   }
   a.kpad = kmax;
   a.wsz = (wsz + 3) & ~3;
+  a.njobs = njobs;
   a.TM = CHAIN_TM;
+  if (njobs > 16) return 0;
+  return (2 * (size_t)CHAIN_TM * a.kpad + (size_t)njobs * a.wsz) * sizeof(float);
+}
+constexpr size_t CHAIN_SMEM_MAX = 200 * 1024;
+bool dense_chain_fits(const ChainArgs& a_in) {
+  ChainArgs a = a_in;
+  const size_t smem = chain_plan(a);
+  return smem > 0 && smem <= CHAIN_SMEM_MAX;
+}
+int dense_chain(const ChainArgs& a_in, cudaStream_t st) {
+  ChainArgs a = a_in;
+  const size_t smem = chain_plan(a);
+  IWAE_REQUIRE(smem > 0 && smem <= CHAIN_SMEM_MAX, "dense_chain: the chain does not fit shared memory (%zu bytes)", smem);
   if (a.M <= 0) return 0;
-  const size_t smem = (2 * (size_t)CHAIN_TM * a.kpad + 2 * (size_t)a.wsz) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
     attr_set = true;
   }
-  IWAE_REQUIRE(smem <= 100 * 1024, "dense_chain: %zu bytes of shared memory", smem);
   CUDA_TRY(launch_pdl(dense_chain_kernel, dim3((a.M + CHAIN_TM - 1) / CHAIN_TM), dim3(256), smem, st, a));
   LAUNCH_CHECK();
   return 0;
