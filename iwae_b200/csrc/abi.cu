@@ -126,6 +126,7 @@ extern "C" int iwae_destroy(iwae_ctx* ctx) {
   comm_release(ctx);
   for (cudaStream_t& l : ctx->lane) if (l) { cudaStreamDestroy(l); l = nullptr; }
   for (cudaEvent_t& e : ctx->lane_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+  mega_release(ctx);
   if (ctx->wt_ev) { cudaEventDestroy(ctx->wt_ev); ctx->wt_ev = nullptr; }
   if (ctx->wt_buf) { cudaFree(ctx->wt_buf); ctx->wt_buf = nullptr; }
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
@@ -197,6 +198,7 @@ struct FwdOpts {
 // wait on it has been issued is fine, eagerly and under stream capture)
 static int lane_dep(iwae_ctx* ctx, cudaStream_t from, cudaStream_t to) {
   if (from == to) return 0;
+  if (mega_recording()) { mega_dep(from, to); return 0; }     // train-step megakernel: the edge only orders the levels
   cudaEvent_t& ev = ctx->lane_ev[ctx->lane_ev_next];
   ctx->lane_ev_next = (ctx->lane_ev_next + 1) % 16;
   if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -902,6 +904,12 @@ static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, co
   opt.want_dreg = (objective == IWAE_OBJ_DREG);
   static const bool no_lanes = getenv("IWAE_NO_LANES") != nullptr;
   opt.lanes = !no_lanes;
+  // Training shapes: forward + backward + update as ONE persistent kernel (kernels_f32.cu, "train-step megakernel"): the
+  // launches below are recorded with their stream / event structure and run level by level behind grid barriers.
+  static const bool mega_on = getenv("IWAE_MEGA") != nullptr;
+  const bool mega = mega_on && opt.lanes && !chain_enabled() && (int64_t)B * k <= MEGA_MAX_ROWS && k <= MEGA_MAX_K;
+  struct MegaGuard { iwae_ctx* c; bool armed; ~MegaGuard() { if (armed) mega_abort(c); } } guard{ctx, false};
+  if (mega) { IWAE_TRY(lanes_init(ctx)); IWAE_TRY(mega_begin(ctx, st)); guard.armed = true; }
   // transposed weights for the backward chains: built on lane 1 while the forward pass runs
   const bool chain = opt.lanes && bwd_chain_ok(m, (int64_t)B * k);
   cudaEvent_t wt_done = nullptr;
@@ -919,12 +927,15 @@ static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, co
   float* ws;
   const int64_t n = m.n_params;
   IWAE_TRY(ctx->arena.get(&ws, (size_t)GRAD_SPLITS * n));
-  CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(float) * GRAD_SPLITS * n, st));
+  // recorded: a level-0 operation beside the forward pass (levels are global, no edge needed); else a memset in stream order
+  IWAE_TRY(zero_f32(ws, (int64_t)GRAD_SPLITS * n, mega ? MEGA_SIDE_STREAM : st));
   g_grad_stride = (int)n;
   IWAE_TRY(backward_internal(ctx, params, f, beta, objective, B_norm, ws, st, opt.lanes, chain));
-  if (adam) return adam_from_partials(adam->params, ws, GRAD_SPLITS, adam->m, adam->v, n, adam->lr, adam->b1, adam->b2,
-                                      adam->eps, adam->t, st);
-  return grad_reduce(ws, GRAD_SPLITS, n, grads, st);
+  if (adam) IWAE_TRY(adam_from_partials(adam->params, ws, GRAD_SPLITS, adam->m, adam->v, n, adam->lr, adam->b1, adam->b2,
+                                        adam->eps, adam->t, st));
+  else IWAE_TRY(grad_reduce(ws, GRAD_SPLITS, n, grads, st));
+  if (mega) { guard.armed = false; IWAE_TRY(mega_flush(ctx, st)); }
+  return 0;
 }
 
 extern "C" int iwae_grads(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,

@@ -19,9 +19,10 @@ void iwae_set_error(const char* fmt, ...);
 
 extern long long g_iwae_launches;
 // after every kernel launch: count it and surface launch-configuration errors
+bool mega_recording();   // the launch wrappers of kernels_f32.cu are recording a train-step program instead of launching
 #define LAUNCH_CHECK()                                                                          \
   do {                                                                                          \
-    ++g_iwae_launches;                                                                          \
+    if (!mega_recording()) ++g_iwae_launches;                                                   \
     CUDA_TRY(cudaGetLastError());                                                               \
   } while (0)
 
@@ -123,6 +124,7 @@ struct iwae_ctx {
   // p(x|z1) beside the q(z2|z1) / p(z1|z2) blocks, every weight gradient dW = X^T dY beside the dX chain - joined with
   // events (inside a captured step they become parallel branches of the CUDA graph)
   cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
+  struct MegaState* mega = nullptr;                // train-step megakernel: recorder, program buffers, barrier counter
   cudaEvent_t wt_ev = nullptr;
   float* wt_buf = nullptr; size_t wt_cap = 0;      // transposed weights of the fused backward chains (rebuilt every step)
   cudaEvent_t lane_ev[16] = {};
@@ -239,6 +241,18 @@ int copy_table(const CopyTable& t, cudaStream_t st);
 int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64_t* out_idx,
                int32_t* out_consumed, cudaStream_t st);
 int softmax_vec_f32(const float* x, int L, float* out, cudaStream_t st);
+
+// ---- train-step megakernel (kernels_f32.cu) ----
+struct MegaState;
+int mega_begin(iwae_ctx* ctx, cudaStream_t st);            // the launch wrappers record from here on ...
+int mega_flush(iwae_ctx* ctx, cudaStream_t st);            // ... until the program is launched as one kernel
+void mega_abort(iwae_ctx* ctx);
+void mega_dep(cudaStream_t from, cudaStream_t to);         // `to` waits for what has been recorded on `from`
+void mega_release(iwae_ctx* ctx);
+int zero_f32(float* p, int64_t n, cudaStream_t st);
+constexpr int64_t MEGA_MAX_ROWS = 8192;                    // k*B of a recorded step (training shapes)
+constexpr int MEGA_MAX_K = 4096;                           // logw_reduce keeps k weights in the shared-memory pool
+#define MEGA_SIDE_STREAM ((cudaStream_t)(uintptr_t)0x10)   // key of a level-0 side branch while recording (never launched on)
 
 // ---- fused Dense chain of the train step (kernels_f32.cu) ----
 enum { CH_NONE = 0, CH_TANH = 1, CH_EXP_EPS = 2, CH_MULH = 3 };

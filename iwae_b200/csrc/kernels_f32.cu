@@ -4,6 +4,10 @@
 #include "rng.cuh"
 #include <math.h>
 #include <algorithm>
+#include <utility>
+#include <vector>
+#include <string.h>
+#include <stdio.h>
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
 // The train step is a chain of ~35 dependent kernels of a few microseconds each: the gap between two of them (drain,
@@ -15,9 +19,35 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// Every train-step kernel is a `*_body(vb_, vg_, args...)` device function plus a thin __global__ wrapper: the body sees
+// its block index / grid size through these two shadowing locals, so the same code runs as a kernel of its own
+// (vb_ = blockIdx) or as one virtual block of the train-step megakernel (end of this file).
+#define VBLOCK_SHADOW const uint3 blockIdx = vb_; const dim3 gridDim = vg_; (void)blockIdx; (void)gridDim
 static bool pdl_enabled() { static const bool on = getenv("IWAE_NO_PDL") == nullptr; return on; }
+// ---- argument packs of recorded launches (train-step megakernel, end of this file) ----
+constexpr int MEGA_ARG_BYTES = 512;
+constexpr size_t MEGA_SMEM_BYTES = 36 * 1024;       // dynamic shared-memory pool: the largest GEMM ring (64x64 tiles: 34,816 bytes)
+template <class... A> struct ArgPack;
+template <> struct ArgPack<> {};
+template <class H, class... T> struct ArgPack<H, T...> { H head; ArgPack<T...> tail; };
+template <class... A> struct PackMaker;
+template <> struct PackMaker<> { static ArgPack<> make() { return {}; } };
+template <class H, class... T> struct PackMaker<H, T...> {
+  static ArgPack<H, T...> make(H h, T... t) { return ArgPack<H, T...>{h, PackMaker<T...>::make(t...)}; }
+};
+template <size_t I, class H, class... T>
+__host__ __device__ __forceinline__ const auto& pack_get(const ArgPack<H, T...>& p) {
+  if constexpr (I == 0) return p.head; else return pack_get<I - 1>(p.tail);
+}
+bool mega_record(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const void* pack, size_t pack_bytes);
+
 template <class... KArgs, class... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (mega_recording()) {        // train-step megakernel: append to the program instead of launching
+    const ArgPack<KArgs...> pack = PackMaker<KArgs...>::make(static_cast<KArgs>(args)...);
+    mega_record((const void*)kern, grid, block, smem, st, &pack, sizeof(pack));
+    return cudaSuccess;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -33,9 +63,8 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 // mapping that walks the unit-stride dimension so global loads stay coalesced in all three.
 // =============================================================================================
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
-gemm_f32_kernel(GemmArgs a) {
-  pdl_wait();
+__device__ __forceinline__ void gemm_f32_body(const uint3 vb_, const dim3 vg_, GemmArgs a) {
+  VBLOCK_SHADOW;
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int TX = BN / TN;   // threads along n
@@ -46,8 +75,12 @@ gemm_f32_kernel(GemmArgs a) {
   // register-staged double buffer (prefetch distance 1) left every tile exposed to the full global-load latency -
   // ~11 us per launch, 43 launches per train step.  Three tiles in flight hide it.
   constexpr int NSTG = 4;
-  __shared__ __align__(16) float As[NSTG][BK][BM + 4];
-  __shared__ __align__(16) float Bs[NSTG][BK][BN + 4];
+  // the ring lives in DYNAMIC shared memory (gemm_smem_bytes): inside the train-step megakernel every operation shares one pool
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  typedef float AsT[BK][BM + 4];
+  typedef float BsT[BK][BN + 4];
+  AsT* As = reinterpret_cast<AsT*>(dyn_smem);
+  BsT* Bs = reinterpret_cast<BsT*>(dyn_smem + sizeof(AsT) * NSTG);
 
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
@@ -177,6 +210,13 @@ gemm_f32_kernel(GemmArgs a) {
   }
 }
 
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_f32_kernel(GemmArgs a) {
+  pdl_wait();
+  gemm_f32_body<BM, BN, TM, TN>(blockIdx, gridDim, a);
+}
+template <int BM, int BN> constexpr size_t gemm_smem_bytes() { return sizeof(float) * 4 * 16 * ((BM + 4) + (BN + 4)); }
+
 int gemm_f32_ntiles_n(int N, int small_tile) { return small_tile ? (N + 31) / 32 : (N + 63) / 64; }
 
 int gemm_f32(const GemmArgs& a, cudaStream_t st) {
@@ -191,13 +231,13 @@ int gemm_f32(const GemmArgs& a, cudaStream_t st) {
     // tall, narrow outputs (rows = k*B = 1,000 by <= 200 units): 4x2 register tiles halve the shared-memory loads
     // per FFMA of the 2x2 kernel, which is LDS-bound on the long-K products (dX of the 784-logit layer: 48 -> ~20 us)
     dim3 grid((m_rows + 63) / 64, (a.N + 31) / 32, z);
-    CUDA_TRY(launch_pdl(gemm_f32_kernel<64, 32, 4, 2>, dim3(grid), dim3(256), 0, st, a));
+    CUDA_TRY(launch_pdl(gemm_f32_kernel<64, 32, 4, 2>, dim3(grid), dim3(256), gemm_smem_bytes<64, 32>(), st, a));
   } else if (a.small_tile) {
     dim3 grid((m_rows + 31) / 32, (a.N + 31) / 32, z);
-    CUDA_TRY(launch_pdl(gemm_f32_kernel<32, 32, 2, 2>, dim3(grid), dim3(256), 0, st, a));
+    CUDA_TRY(launch_pdl(gemm_f32_kernel<32, 32, 2, 2>, dim3(grid), dim3(256), gemm_smem_bytes<32, 32>(), st, a));
   } else {
     dim3 grid((m_rows + 63) / 64, (a.N + 63) / 64, z);
-    CUDA_TRY(launch_pdl(gemm_f32_kernel<64, 64, 4, 4>, dim3(grid), dim3(256), 0, st, a));
+    CUDA_TRY(launch_pdl(gemm_f32_kernel<64, 64, 4, 4>, dim3(grid), dim3(256), gemm_smem_bytes<64, 64>(), st, a));
   }
   LAUNCH_CHECK();
   return 0;
@@ -239,9 +279,9 @@ __device__ __forceinline__ int label_of(const float* y, int b) {
   return (int)(unsigned char)(int)y[b];
 }
 
-__global__ void concat_onehot_kernel(const float* __restrict__ x, int64_t ldx, int n, const float* __restrict__ y,
+__device__ __forceinline__ void concat_onehot_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ x, int64_t ldx, int n, const float* __restrict__ y,
                                      int B, int rows, int nc, float* __restrict__ out) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   const int64_t total = (int64_t)rows * (n + nc);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (n + nc);
@@ -251,6 +291,10 @@ __global__ void concat_onehot_kernel(const float* __restrict__ x, int64_t ldx, i
     else v = (label_of(y, (int)(r % B)) == c - n) ? 1.f : 0.f;
     out[i] = v;
   }
+}
+__global__ void __launch_bounds__(256) concat_onehot_kernel(const float* __restrict__ x, int64_t ldx, int n, const float* __restrict__ y, int B, int rows, int nc, float* __restrict__ out) {
+  pdl_wait();
+  concat_onehot_body(blockIdx, gridDim, x, ldx, n, y, B, rows, nc, out);
 }
 int concat_onehot(const float* x, int64_t ldx, int n, const float* y, int B, int rows, int nc, float* out,
                   cudaStream_t st) {
@@ -265,11 +309,11 @@ int onehot_f32(const float* y, int B, int nc, float* out, cudaStream_t st) {
 }
 
 // ---- reparameterised sampling: z = eps*std + mu (tfd.Normal.sample, A.2) ----
-__global__ void sample_latent_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int bcast,
+__device__ __forceinline__ void sample_latent_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ mu, const float* __restrict__ sd, int bcast,
                                      const float* __restrict__ eps_in, float* __restrict__ eps_out,
                                      float* __restrict__ z, int B, int k, int d, uint64_t seed, int stream_id,
                                      int64_t img_offset, const StepDyn* __restrict__ dyn) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   if (dyn) { seed = dyn->seed; img_offset = dyn->img_offset; }      // graph replay: per-step values live on the device
   const int nq = (d + 7) / 8;                // one Philox call per dim-octet (rng.cuh)
   const int64_t total = (int64_t)k * B * nq;
@@ -298,6 +342,10 @@ __global__ void sample_latent_kernel(const float* __restrict__ mu, const float* 
     }
   }
 }
+__global__ void __launch_bounds__(256) sample_latent_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int bcast, const float* __restrict__ eps_in, float* __restrict__ eps_out, float* __restrict__ z, int B, int k, int d, uint64_t seed, int stream_id, int64_t img_offset, const StepDyn* __restrict__ dyn) {
+  pdl_wait();
+  sample_latent_body(blockIdx, gridDim, mu, sd, bcast, eps_in, eps_out, z, B, k, d, seed, stream_id, img_offset, dyn);
+}
 int sample_latent(const float* mu, const float* sd, int bcast, const float* eps_in, float* eps_out, float* z,
                   int B, int k, int d, uint64_t seed, int stream_id, int64_t img_offset, cudaStream_t st) {
   const int64_t total = (int64_t)k * B * ((d + 7) / 8);
@@ -314,10 +362,10 @@ int philox_fill(uint64_t seed, int stream_id, int64_t img_offset, int B, int k, 
 
 // ---- Gaussian log-density row sums: one warp per row ----
 #define LOG2PI_HALF 0.91893853320467274178f
-__global__ void normal_logp_rows_kernel(const float* __restrict__ z, const float* __restrict__ mu,
+__device__ __forceinline__ void normal_logp_rows_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ z, const float* __restrict__ mu,
                                         const float* __restrict__ sd, int bcast, float std_extra, int B, int64_t R, int d,
                                         float* __restrict__ out) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -339,6 +387,10 @@ __global__ void normal_logp_rows_kernel(const float* __restrict__ z, const float
     if (lane == 0) out[r] = s;
   }
 }
+__global__ void __launch_bounds__(256) normal_logp_rows_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ sd, int bcast, float std_extra, int B, int64_t R, int d, float* __restrict__ out) {
+  pdl_wait();
+  normal_logp_rows_body(blockIdx, gridDim, z, mu, sd, bcast, std_extra, B, R, d, out);
+}
 int normal_logp_rows(const float* z, const float* mu, const float* sd, int bcast, float std_extra, int B, int k,
                      int d, float* out, cudaStream_t st) {
   const int64_t R = (int64_t)B * k;
@@ -350,8 +402,8 @@ int normal_logp_rows(const float* z, const float* mu, const float* sd, int bcast
   return 0;
 }
 
-__global__ void normal_logp_rows_multi_kernel(NlpJobs jobs, int B, int64_t R) {
-  pdl_wait();
+__device__ __forceinline__ void normal_logp_rows_multi_body(const uint3 vb_, const dim3 vg_, NlpJobs jobs, int B, int64_t R) {
+  VBLOCK_SHADOW;
   const NlpJob& jb = jobs.job[blockIdx.y];
   const float* __restrict__ z = jb.z; const float* __restrict__ mu = jb.mu; const float* __restrict__ sd = jb.sd;
   const int d = jb.d, bcast = jb.bcast; const float std_extra = jb.std_extra;
@@ -376,6 +428,10 @@ __global__ void normal_logp_rows_multi_kernel(NlpJobs jobs, int B, int64_t R) {
     if (lane == 0) jb.out[r] = s;
   }
 }
+__global__ void __launch_bounds__(256) normal_logp_rows_multi_kernel(NlpJobs jobs, int B, int64_t R) {
+  pdl_wait();
+  normal_logp_rows_multi_body(blockIdx, gridDim, jobs, B, R);
+}
 int normal_logp_rows_multi(const NlpJobs& jobs, int B, int k, cudaStream_t st) {
   const int64_t R = (int64_t)B * k;
   if (R == 0 || jobs.count == 0) return 0;
@@ -386,9 +442,9 @@ int normal_logp_rows_multi(const NlpJobs& jobs, int B, int k, cudaStream_t st) {
   return 0;
 }
 
-__global__ void kl_rows_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int B, int d,
+__device__ __forceinline__ void kl_rows_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ mu, const float* __restrict__ sd, int B, int d,
                                float* __restrict__ out) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   // tfd.kl_divergence(N(mu,sd), N(0,1)) = 0.5 mu^2 + 0.5 expm1(2 log sd) - log sd   (A.2)
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -402,19 +458,27 @@ __global__ void kl_rows_kernel(const float* __restrict__ mu, const float* __rest
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[b] = s;
 }
+__global__ void __launch_bounds__(256) kl_rows_kernel(const float* __restrict__ mu, const float* __restrict__ sd, int B, int d, float* __restrict__ out) {
+  pdl_wait();
+  kl_rows_body(blockIdx, gridDim, mu, sd, B, d, out);
+}
 int kl_rows(const float* mu, const float* sd, int B, int d, float* out, cudaStream_t st) {
   CUDA_TRY(launch_pdl(kl_rows_kernel, dim3((B + 7) / 8), dim3(256), 0, st, mu, sd, B, d, out));
   LAUNCH_CHECK();
   return 0;
 }
 
-__global__ void bern_reduce_partials_kernel(const float* __restrict__ p, int64_t R, int nt, float* __restrict__ out) {
-  pdl_wait();
+__device__ __forceinline__ void bern_reduce_partials_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ p, int64_t R, int nt, float* __restrict__ out) {
+  VBLOCK_SHADOW;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int t = 0; t < nt; ++t) s += p[r * nt + t];
     out[r] = s;
   }
+}
+__global__ void __launch_bounds__(256) bern_reduce_partials_kernel(const float* __restrict__ p, int64_t R, int nt, float* __restrict__ out) {
+  pdl_wait();
+  bern_reduce_partials_body(blockIdx, gridDim, p, R, nt, out);
 }
 int bern_reduce_partials(const float* partial, int R, int nt, float* lpxz, cudaStream_t st) {
   if (R == 0) return 0;
@@ -467,8 +531,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
-__global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
-  pdl_wait();
+__device__ __forceinline__ void logw_reduce_body(const uint3 vb_, const dim3 vg_, LogwArgs a) {
+  VBLOCK_SHADOW;
   __shared__ float red[8];
   extern __shared__ float s_al[];      // normalised weights of this image when k fits (a.al_in_smem)
   const int b = blockIdx.x, B = a.B, k = a.k;
@@ -523,7 +587,8 @@ __global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
     if (!out) continue;
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
       float acc = 0.f;
-      for (int s = 0; s < k; ++s) {
+#pragma unroll 10
+      for (int s = 0; s < k; ++s) {          // (unrolled: the loads of z are independent, the sum keeps its order)
         const int64_t r = (int64_t)s * B + b;
         float w;
         if (a.al_in_smem) w = s_al[s];
@@ -538,6 +603,10 @@ __global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
     }
   }
 }
+__global__ void __launch_bounds__(256) logw_reduce_kernel(LogwArgs a) {
+  pdl_wait();
+  logw_reduce_body(blockIdx, gridDim, a);
+}
 int logw_reduce(const LogwArgs& a0, cudaStream_t st) {
   if (a0.B == 0) return 0;
   LogwArgs a = a0;
@@ -548,8 +617,8 @@ int logw_reduce(const LogwArgs& a0, cudaStream_t st) {
 }
 
 // Stage 1 of the batch means for large calls: CTA c sums slice c of each of the eight arrays (fixed order -> deterministic)
-__global__ void __launch_bounds__(256) scalars_partial_kernel(ScalarArgs a) {
-  pdl_wait();
+__device__ __forceinline__ void scalars_partial_body(const uint3 vb_, const dim3 vg_, ScalarArgs a) {
+  VBLOCK_SHADOW;
   __shared__ float red[8][8];
   const float* src[8] = {a.vae, a.iwae, a.eq14, a.kl, a.dreg, a.lpxz, a.lpz, a.lq1};
   const int64_t len[8] = {a.B, a.B, a.B, a.B, a.B, a.R, a.R, a.R};
@@ -577,10 +646,14 @@ __global__ void __launch_bounds__(256) scalars_partial_kernel(ScalarArgs a) {
     a.partial[(int64_t)blockIdx.x * 8 + threadIdx.x] = t;
   }
 }
+__global__ void __launch_bounds__(256) scalars_partial_kernel(ScalarArgs a) {
+  pdl_wait();
+  scalars_partial_body(blockIdx, gridDim, a);
+}
 
 // Batch-mean scalars of the result dict (iwae1.py:119-134): one CTA, fixed order -> deterministic.
-__global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
-  pdl_wait();
+__device__ __forceinline__ void finalize_scalars_body(const uint3 vb_, const dim3 vg_, ScalarArgs a) {
+  VBLOCK_SHADOW;
   // eight means in ONE pass: all loads are issued before the first reduction (eight serial block reductions, each
   // waiting for its own global loads, were a 12 us kernel on the train step's critical path)
   __shared__ float red[8][8];
@@ -621,6 +694,10 @@ __global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
     a.out[5] = m_lpxz; a.out[6] = m_lpz; a.out[7] = m_lq1;
   }
 }
+__global__ void __launch_bounds__(256) finalize_scalars_kernel(ScalarArgs a) {
+  pdl_wait();
+  finalize_scalars_body(blockIdx, gridDim, a);
+}
 int finalize_scalars(const ScalarArgs& a, cudaStream_t st) {
   if (a.partial) { CUDA_TRY(launch_pdl(scalars_partial_kernel, dim3(SCALAR_PARTS), dim3(256), 0, st, a)); LAUNCH_CHECK(); }
   CUDA_TRY(launch_pdl(finalize_scalars_kernel, dim3(1), dim3(256), 0, st, a));
@@ -651,15 +728,19 @@ int sum_to_double(const float* v, int64_t n, double* acc, int accumulate, cudaSt
 // Backward
 // =============================================================================================
 // g[r] = d(-objective)/d(log_w[r])  (A.4): iwae_elbo / iwae_eq14 / DReG-decoder -> -al/B ; vae -> -1/(kB)
-__global__ void row_coef_kernel(const float* __restrict__ al, int64_t R, int k, int objective, int B_norm,
+__device__ __forceinline__ void row_coef_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ al, int64_t R, int k, int objective, int B_norm,
                                 float* __restrict__ g) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
     float v;
     if (objective == IWAE_OBJ_VAE_ELBO || objective == IWAE_OBJ_VAE_ELBO_KL) v = -1.f / ((float)k * (float)B_norm);
     else v = -al[r] / (float)B_norm;
     g[r] = v;
   }
+}
+__global__ void __launch_bounds__(256) row_coef_kernel(const float* __restrict__ al, int64_t R, int k, int objective, int B_norm, float* __restrict__ g) {
+  pdl_wait();
+  row_coef_body(blockIdx, gridDim, al, R, k, objective, B_norm, g);
 }
 int row_coef(const float* al, int B, int k, int objective, int B_norm, float* g, cudaStream_t st) {
   const int64_t R = (int64_t)B * k;
@@ -671,9 +752,9 @@ int row_coef(const float* al, int B, int k, int objective, int B_norm, float* g,
 }
 
 // dl[r,j] = g[r] * (x[b,j] - sigmoid(l[r,j]))
-__global__ void dlogits_kernel(const float* __restrict__ logits, const float* __restrict__ x,
+__device__ __forceinline__ void dlogits_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ logits, const float* __restrict__ x,
                                const float* __restrict__ g, int64_t R, int B, int n, float* __restrict__ dl) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   const int64_t total = R * n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / n;
@@ -682,6 +763,10 @@ __global__ void dlogits_kernel(const float* __restrict__ logits, const float* __
     const float sg = 1.f / (1.f + expf(-l));
     dl[i] = g[r] * (x[(r % B) * (int64_t)n + j] - sg);
   }
+}
+__global__ void __launch_bounds__(256) dlogits_kernel(const float* __restrict__ logits, const float* __restrict__ x, const float* __restrict__ g, int64_t R, int B, int n, float* __restrict__ dl) {
+  pdl_wait();
+  dlogits_body(blockIdx, gridDim, logits, x, g, R, B, n, dl);
 }
 int dlogits_f32(const float* logits, const float* x, const float* g, int R, int B, int n, float* dl, cudaStream_t st) {
   const int64_t total = (int64_t)R * n;
@@ -692,17 +777,18 @@ int dlogits_f32(const float* logits, const float* x, const float* g, int R, int 
   return 0;
 }
 
-// First stochastic layer.  One CTA per image; thread (ks, j) sums dim j over the samples s = ks, ks+KS, ...
-// and the KS partial sums are added in a fixed order through shared memory.
+// First stochastic layer.  One CTA per (image, chunk of 32 latent dims); thread (ks, j) sums dim j over the samples
+// s = ks, ks+8, ... and the 8 partial sums are added in a fixed order through shared memory.  (One CTA per image with
+// d threads x 256/d sample slices was a 23 us serial chain of load latencies on the step's critical path.)
 // Uses the total-derivative identities of A.4: d lq/d mu = 0, d lq/d std = -1/std.
-__global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
-  pdl_wait();
+__device__ __forceinline__ void latent1_bwd_body(const uint3 vb_, const dim3 vg_, Latent1BwdArgs a) {
+  VBLOCK_SHADOW;
   __shared__ float red[4][256];
   const int b = blockIdx.x;
-  const int KS = max(1, 256 / a.d);                 // sample slices handled in parallel
-  const int dpad = (a.d + 0);
-  const int j = threadIdx.x % dpad, ks = threadIdx.x / dpad;
-  const bool active = threadIdx.x < KS * a.d && KS * a.d <= 256;
+  constexpr int KS = 8;                             // sample slices handled in parallel (one warp each)
+  const int jl = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int j = blockIdx.y * 32 + jl;
+  const bool active = j < a.d;
   const bool dreg = (a.objective == IWAE_OBJ_DREG);
   const bool klobj = (a.objective == IWAE_OBJ_VAE_ELBO_KL);
   float acc_mu = 0.f, acc_sd = 0.f, acc_pmu = 0.f, acc_psd = 0.f;
@@ -712,7 +798,7 @@ __global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
     mu = a.mu[idx]; sd = a.std[idx];
     // (unrolled: the ~7 global loads of different samples are independent; one CTA per image leaves most SMs idle,
     //  so this kernel's time is its serial load-latency chain)
-#pragma unroll 5
+#pragma unroll 7
     for (int s = ks; s < a.k; s += KS) {
       const int64_t r = (int64_t)s * a.B + b;
       const float g = a.g[r];
@@ -753,8 +839,8 @@ __global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
   __syncthreads();
   if (active && ks == 0) {
     for (int q = 1; q < KS; ++q) {
-      acc_mu += red[0][q * a.d + j]; acc_sd += red[1][q * a.d + j];
-      acc_pmu += red[2][q * a.d + j]; acc_psd += red[3][q * a.d + j];
+      acc_mu += red[0][q * 32 + jl]; acc_sd += red[1][q * 32 + jl];
+      acc_pmu += red[2][q * 32 + jl]; acc_psd += red[3][q * 32 + jl];
     }
     if (klobj) {
       // loss = -mean lpxz + beta * mean_b kl ; d kl/d mu = mu, d kl/d std = std - 1/std
@@ -769,20 +855,23 @@ __global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
     }
   }
 }
+__global__ void __launch_bounds__(256) latent1_bwd_kernel(Latent1BwdArgs a) {
+  pdl_wait();
+  latent1_bwd_body(blockIdx, gridDim, a);
+}
 int latent1_bwd(const Latent1BwdArgs& a, cudaStream_t st) {
   if (a.B * a.d == 0) return 0;
-  IWAE_REQUIRE(a.d <= 256, "latent1_bwd: latent size above 256 is not supported");
-  CUDA_TRY(launch_pdl(latent1_bwd_kernel, dim3(a.B), dim3(256), 0, st, a));
+  CUDA_TRY(launch_pdl(latent1_bwd_kernel, dim3(a.B, (a.d + 31) / 32), dim3(256), 0, st, a));
   LAUNCH_CHECK();
   return 0;
 }
 
 // Gradients reaching the parameters (pmu, pstd pre-activation) of a per-row Gaussian log p(z; pmu, pstd)
 // weighted by g[r] (IWAE2's lpz1z2, iwae2.py:120).
-__global__ void gauss_rows_bwd_kernel(const float* __restrict__ g, const float* __restrict__ z,
+__device__ __forceinline__ void gauss_rows_bwd_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ g, const float* __restrict__ z,
                                       const float* __restrict__ pmu, const float* __restrict__ pstd, int64_t R, int d,
                                       float* __restrict__ dpmu, float* __restrict__ dpa) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   const int64_t total = R * d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const float gg = g[i / d];
@@ -791,6 +880,10 @@ __global__ void gauss_rows_bwd_kernel(const float* __restrict__ g, const float* 
     dpmu[i] = gg * t;
     dpa[i] = gg * ((z[i] - pm) * t / ps - 1.f / ps) * (ps - 1e-6f);
   }
+}
+__global__ void __launch_bounds__(256) gauss_rows_bwd_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ pmu, const float* __restrict__ pstd, int64_t R, int d, float* __restrict__ dpmu, float* __restrict__ dpa) {
+  pdl_wait();
+  gauss_rows_bwd_body(blockIdx, gridDim, g, z, pmu, pstd, R, d, dpmu, dpa);
 }
 int gauss_rows_bwd(const float* g, const float* z, const float* pmu, const float* pstd, int64_t R, int d,
                    float* dpmu, float* dpa, cudaStream_t st) {
@@ -803,8 +896,8 @@ int gauss_rows_bwd(const float* g, const float* z, const float* pmu, const float
 }
 
 // Second stochastic layer of IWAE2 (all per row): z2 = mu2 + std2*eps2, lpz2 = N(0,1), -lq2 total.
-__global__ void latent2_bwd_kernel(Latent2BwdArgs a) {
-  pdl_wait();
+__device__ __forceinline__ void latent2_bwd_body(const uint3 vb_, const dim3 vg_, Latent2BwdArgs a) {
+  VBLOCK_SHADOW;
   const int64_t total = (int64_t)a.R * a.d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / a.d;
@@ -814,6 +907,10 @@ __global__ void latent2_bwd_kernel(Latent2BwdArgs a) {
     a.dmu[i] = dz;
     a.da[i] = (dz * a.eps[i] + g / sd) * (sd - 1e-6f);
   }
+}
+__global__ void __launch_bounds__(256) latent2_bwd_kernel(Latent2BwdArgs a) {
+  pdl_wait();
+  latent2_bwd_body(blockIdx, gridDim, a);
 }
 int latent2_bwd(const Latent2BwdArgs& a, cudaStream_t st) {
   const int64_t total = (int64_t)a.R * a.d;
@@ -865,10 +962,10 @@ int adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
 }
 
 // ---- split-K gradient partials: fixed-order reduction, optionally fused with the Keras-Adam update ----
-__global__ void grad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t n, float* __restrict__ g,
+__device__ __forceinline__ void grad_reduce_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ ws, int splits, int64_t n, float* __restrict__ g,
                                    float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float lr_t,
                                    float b1, float b2, float eps, const StepDyn* __restrict__ dyn) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   if (dyn) { lr_t = dyn->lr_t; b1 = dyn->b1; b2 = dyn->b2; eps = dyn->eps; }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -882,6 +979,10 @@ __global__ void grad_reduce_kernel(const float* __restrict__ ws, int splits, int
       p[i] = p[i] - lr_t * mm / (sqrtf(vv) + eps);
     }
   }
+}
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restrict__ ws, int splits, int64_t n, float* __restrict__ g, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float lr_t, float b1, float b2, float eps, const StepDyn* __restrict__ dyn) {
+  pdl_wait();
+  grad_reduce_body(blockIdx, gridDim, ws, splits, n, g, p, m, v, lr_t, b1, b2, eps, dyn);
 }
 int grad_reduce(const float* ws, int splits, int64_t n, float* grads, cudaStream_t st) {
   if (n == 0) return 0;
@@ -1015,9 +1116,9 @@ int sir_launch(const float* al, int L, const double* u, int n_u, int size, int64
 
 
 // ---- split-K forward epilogue ----
-__global__ void splitk_bias_act_kernel(const float* __restrict__ partial, int splits, int M, int N,
+__device__ __forceinline__ void splitk_bias_act_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ partial, int splits, int M, int N,
                                        const float* __restrict__ bias, int act, float* __restrict__ out) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   const int total = M * N;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -1028,6 +1129,10 @@ __global__ void splitk_bias_act_kernel(const float* __restrict__ partial, int sp
     out[i] = v;
   }
 }
+__global__ void __launch_bounds__(256) splitk_bias_act_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ bias, int act, float* __restrict__ out) {
+  pdl_wait();
+  splitk_bias_act_body(blockIdx, gridDim, partial, splits, M, N, bias, act, out);
+}
 int splitk_bias_act(const float* partial, int splits, int M, int N, const float* bias, int act, float* out, cudaStream_t st) {
   if (M * N == 0) return 0;
   CUDA_TRY(launch_pdl(splitk_bias_act_kernel, dim3((M * N + 255) / 256), dim3(256), 0, st, partial, splits, M, N, bias, act, out));
@@ -1035,9 +1140,9 @@ int splitk_bias_act(const float* partial, int splits, int M, int N, const float*
   return 0;
 }
 
-__global__ void splitk_mul_h_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ H,
+__device__ __forceinline__ void splitk_mul_h_body(const uint3 vb_, const dim3 vg_, const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ H,
                                     int64_t ld_h, int accumulate, float* __restrict__ dX, int64_t ld_dx) {
-  pdl_wait();
+  VBLOCK_SHADOW;
   const int total = M * N;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int m = i / N, n = i % N;
@@ -1047,6 +1152,10 @@ __global__ void splitk_mul_h_kernel(const float* __restrict__ partial, int split
     if (H) { const float h = H[(int64_t)m * ld_h + n]; v *= (1.f - h * h); }
     dX[(int64_t)m * ld_dx + n] = v;
   }
+}
+__global__ void __launch_bounds__(256) splitk_mul_h_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ H, int64_t ld_h, int accumulate, float* __restrict__ dX, int64_t ld_dx) {
+  pdl_wait();
+  splitk_mul_h_body(blockIdx, gridDim, partial, splits, M, N, H, ld_h, accumulate, dX, ld_dx);
 }
 int splitk_mul_h(const float* partial, int splits, int M, int N, const float* H, int64_t ld_h, int accumulate, float* dX,
                  int64_t ld_dx, cudaStream_t st) {
@@ -1333,5 +1442,358 @@ int transpose_jobs(const TransposeJobs& t, cudaStream_t st) {
   if (t.count == 0) return 0;
   CUDA_TRY(launch_pdl(transpose_jobs_kernel, dim3(24, t.count), dim3(256), 0, st, t));
   LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// Train-step megakernel.
+// A k=50 step is ~60 kernels of 1-6 us on a dependency chain ~31 kernels long; even replayed from a CUDA graph with
+// programmatic dependent launch the boundary between two dependent kernels (drain, launch, ramp-up) costs more than the
+// kernels do.  In record mode (mega_begin .. mega_flush) the launch wrappers of this file do not launch: they append
+// (kernel, grid, arguments) to a program, and each operation gets a LEVEL from the stream it was issued on and the
+// event edges between the streams (lane_dep) - exactly the dependency structure the multi-stream step already spells
+// out.  mega_flush uploads the program and launches ONE persistent cooperative kernel: for every level its CTAs share
+// out the virtual blocks of all operations of that level (each runs the unchanged *_body of its kernel), then meet at a
+// grid-wide barrier (one atomic + an acquire spin per CTA, ~1 us) instead of a kernel boundary.
+// Per-step scalars come from StepDyn as before, so the captured CUDA graph of a step is [inputs, step scalars, this
+// kernel, outputs] and the program is uploaded once, at capture.
+// Memory ordering: every buffer of a step is written at one level and read at later ones (the arena never reuses memory
+// within a step); writers fence before arriving at the barrier and readers first touch the data after their acquire.
+// =============================================================================================
+enum MegaType {
+  MT_GEMM_64_32 = 0, MT_GEMM_32_32, MT_GEMM_64_64, MT_CONCAT_ONEHOT, MT_SAMPLE_LATENT, MT_NLP_ROWS, MT_NLP_MULTI, MT_KL_ROWS,
+  MT_BERN_REDUCE, MT_LOGW, MT_SCAL_PART, MT_FINALIZE, MT_ROW_COEF, MT_DLOGITS, MT_LATENT1, MT_GAUSS_BWD, MT_LATENT2,
+  MT_GRAD_REDUCE, MT_SPLITK_BIAS, MT_SPLITK_MULH, MT_ZERO, MT_COUNT
+};
+struct MegaOp {
+  int type; unsigned gx, gy, gz;
+  unsigned vb_start, nblocks; unsigned pad[2];
+  alignas(16) unsigned char args[MEGA_ARG_BYTES];
+};
+struct MegaLevel { int op_begin, op_end; unsigned total, pad; };
+
+// zero n floats (the split-K gradient workspace): a level-0 operation of the megakernel, a memset outside it
+__device__ __forceinline__ void zero_f32_body(const uint3 vb_, const dim3 vg_, float* p, int64_t n) {
+  VBLOCK_SHADOW;
+  const int64_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+__global__ void __launch_bounds__(256) zero_f32_kernel(float* p, int64_t n) { pdl_wait(); zero_f32_body(blockIdx, gridDim, p, n); }
+
+template <class... KArgs, size_t... I>
+__device__ __forceinline__ void mega_apply(void (*body)(uint3, dim3, KArgs...), const void* raw, uint3 vb, dim3 vg,
+                                           std::index_sequence<I...>) {
+  const ArgPack<KArgs...>& p = *static_cast<const ArgPack<KArgs...>*>(raw);
+  body(vb, vg, pack_get<I>(p)...);
+}
+template <class... KArgs>
+__device__ __forceinline__ void mega_call(void (*body)(uint3, dim3, KArgs...), const void* raw, uint3 vb, dim3 vg) {
+  mega_apply(body, raw, vb, vg, std::index_sequence_for<KArgs...>{});
+}
+
+__device__ __forceinline__ void mega_grid_barrier(unsigned long long* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                                                   // this CTA's writes are visible device-wide ...
+    const unsigned long long t = atomicAdd(bar, 1ULL);                 // ... before its arrival is
+    const unsigned long long target = (t / gridDim.x + 1ULL) * gridDim.x;
+    unsigned long long seen;
+    do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory"); } while (seen < target);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long mega_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// trace (IWAE_MEGA_TRACE, diagnostics): CTA 0 stamps [2L] = its work of level L done, [2L+1] = barrier of level L passed
+__global__ void __launch_bounds__(256, 2) mega_kernel(const MegaLevel* __restrict__ levels, const MegaOp* __restrict__ ops,
+                                                      int nlevels, unsigned long long* bar, unsigned long long* trace) {
+  __shared__ __align__(16) unsigned char s_args[MEGA_ARG_BYTES];
+  int last_op = -1;
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[2 * nlevels] = mega_now();
+  for (int L = 0; L < nlevels; ++L) {
+    const int ob = levels[L].op_begin, oe = levels[L].op_end;
+    const unsigned total = levels[L].total;
+    for (unsigned v = blockIdx.x; v < total; v += gridDim.x) {
+      int o = ob;
+      while (o + 1 < oe && v >= ops[o + 1].vb_start) ++o;
+      __syncthreads();                     // the previous virtual block is done with s_args and the shared-memory pool
+      if (o != last_op) {
+        if (threadIdx.x < MEGA_ARG_BYTES / 16)
+          reinterpret_cast<uint4*>(s_args)[threadIdx.x] = reinterpret_cast<const uint4*>(ops[o].args)[threadIdx.x];
+        last_op = o;
+        __syncthreads();
+      }
+      const unsigned gx = ops[o].gx, gy = ops[o].gy, gz = ops[o].gz;
+      const unsigned local = v - ops[o].vb_start;
+      uint3 vb;
+      vb.x = local % gx; vb.y = (local / gx) % gy; vb.z = local / (gx * gy);
+      const dim3 vg(gx, gy, gz);
+      const void* raw = s_args;
+      switch (ops[o].type) {
+        case MT_GEMM_64_32: mega_call(gemm_f32_body<64, 32, 4, 2>, raw, vb, vg); break;
+        case MT_GEMM_32_32: mega_call(gemm_f32_body<32, 32, 2, 2>, raw, vb, vg); break;
+        case MT_GEMM_64_64: mega_call(gemm_f32_body<64, 64, 4, 4>, raw, vb, vg); break;
+        case MT_CONCAT_ONEHOT: mega_call(concat_onehot_body, raw, vb, vg); break;
+        case MT_SAMPLE_LATENT: mega_call(sample_latent_body, raw, vb, vg); break;
+        case MT_NLP_ROWS: mega_call(normal_logp_rows_body, raw, vb, vg); break;
+        case MT_NLP_MULTI: mega_call(normal_logp_rows_multi_body, raw, vb, vg); break;
+        case MT_KL_ROWS: mega_call(kl_rows_body, raw, vb, vg); break;
+        case MT_BERN_REDUCE: mega_call(bern_reduce_partials_body, raw, vb, vg); break;
+        case MT_LOGW: mega_call(logw_reduce_body, raw, vb, vg); break;
+        case MT_SCAL_PART: mega_call(scalars_partial_body, raw, vb, vg); break;
+        case MT_FINALIZE: mega_call(finalize_scalars_body, raw, vb, vg); break;
+        case MT_ROW_COEF: mega_call(row_coef_body, raw, vb, vg); break;
+        case MT_DLOGITS: mega_call(dlogits_body, raw, vb, vg); break;
+        case MT_LATENT1: mega_call(latent1_bwd_body, raw, vb, vg); break;
+        case MT_GAUSS_BWD: mega_call(gauss_rows_bwd_body, raw, vb, vg); break;
+        case MT_LATENT2: mega_call(latent2_bwd_body, raw, vb, vg); break;
+        case MT_GRAD_REDUCE: mega_call(grad_reduce_body, raw, vb, vg); break;
+        case MT_SPLITK_BIAS: mega_call(splitk_bias_act_body, raw, vb, vg); break;
+        case MT_SPLITK_MULH: mega_call(splitk_mul_h_body, raw, vb, vg); break;
+        case MT_ZERO: mega_call(zero_f32_body, raw, vb, vg); break;
+        default: break;
+      }
+    }
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[2 * L] = mega_now();
+    if (L + 1 < nlevels) mega_grid_barrier(bar);
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[2 * L + 1] = mega_now();
+  }
+}
+
+// ---- host side: recorder, program builder, launcher ----
+struct MegaOpHost { int type; int level; dim3 grid; size_t smem; int seq; unsigned char args[MEGA_ARG_BYTES]; };
+struct MegaBuf {
+  unsigned char* dev = nullptr; size_t cap = 0;
+  unsigned char* host = nullptr; size_t host_cap = 0;       // pinned staging
+  cudaEvent_t used = nullptr;                                 // the last upload from `host` / launch reading `dev`
+};
+struct MegaState {
+  bool recording = false, failed = false;
+  std::vector<MegaOpHost> ops;
+  std::vector<std::pair<cudaStream_t, int>> lvl;              // next free level of each stream seen while recording
+  MegaBuf buf[2];                                             // [0] eager launches, [1] the captured train-step graph
+  unsigned long long* bar = nullptr;
+  unsigned long long* trace = nullptr;
+  cudaStream_t upload = nullptr;
+  int grid = 0;
+  char why[160] = {0};
+};
+static thread_local MegaState* g_mega = nullptr;              // the recorder of the step this host thread is issuing
+
+bool mega_recording() { return g_mega != nullptr; }
+static int& mega_level_of(MegaState* m, cudaStream_t s) {
+  for (auto& e : m->lvl) if (e.first == s) return e.second;
+  m->lvl.emplace_back(s, 0);
+  return m->lvl.back().second;
+}
+void mega_dep(cudaStream_t from, cudaStream_t to) {
+  if (!g_mega || from == to) return;
+  const int lf = mega_level_of(g_mega, from);
+  int& lt = mega_level_of(g_mega, to);
+  lt = std::max(lt, lf);
+}
+static int mega_type_of(const void* kern) {
+  static const std::pair<const void*, int> table[] = {
+    {(const void*)gemm_f32_kernel<64, 32, 4, 2>, MT_GEMM_64_32}, {(const void*)gemm_f32_kernel<32, 32, 2, 2>, MT_GEMM_32_32},
+    {(const void*)gemm_f32_kernel<64, 64, 4, 4>, MT_GEMM_64_64}, {(const void*)concat_onehot_kernel, MT_CONCAT_ONEHOT},
+    {(const void*)sample_latent_kernel, MT_SAMPLE_LATENT}, {(const void*)normal_logp_rows_kernel, MT_NLP_ROWS},
+    {(const void*)normal_logp_rows_multi_kernel, MT_NLP_MULTI}, {(const void*)kl_rows_kernel, MT_KL_ROWS},
+    {(const void*)bern_reduce_partials_kernel, MT_BERN_REDUCE}, {(const void*)logw_reduce_kernel, MT_LOGW},
+    {(const void*)scalars_partial_kernel, MT_SCAL_PART}, {(const void*)finalize_scalars_kernel, MT_FINALIZE},
+    {(const void*)row_coef_kernel, MT_ROW_COEF}, {(const void*)dlogits_kernel, MT_DLOGITS},
+    {(const void*)latent1_bwd_kernel, MT_LATENT1}, {(const void*)gauss_rows_bwd_kernel, MT_GAUSS_BWD},
+    {(const void*)latent2_bwd_kernel, MT_LATENT2}, {(const void*)grad_reduce_kernel, MT_GRAD_REDUCE},
+    {(const void*)splitk_bias_act_kernel, MT_SPLITK_BIAS}, {(const void*)splitk_mul_h_kernel, MT_SPLITK_MULH},
+    {(const void*)zero_f32_kernel, MT_ZERO}};
+  for (const auto& e : table) if (e.first == kern) return e.second;
+  return -1;
+}
+bool mega_record(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const void* pack, size_t pack_bytes) {
+  MegaState* m = g_mega;
+  const int type = mega_type_of(kern);
+  if (type < 0 || block.x != 256 || block.y != 1 || block.z != 1 || pack_bytes > MEGA_ARG_BYTES || smem > MEGA_SMEM_BYTES) {
+    if (!m->failed) snprintf(m->why, sizeof(m->why), "operation not supported by the megakernel (type %d, block %ux%u, %zu bytes of shared memory)",
+                             type, block.x, block.y, smem);
+    m->failed = true;
+    return true;                 // keep recording; mega_flush reports
+  }
+  MegaOpHost op;
+  op.type = type; op.grid = grid; op.smem = smem; op.seq = (int)m->ops.size();
+  int& lv = mega_level_of(m, st);
+  op.level = lv; lv += 1;
+  memset(op.args, 0, sizeof(op.args));
+  memcpy(op.args, pack, pack_bytes);
+  m->ops.push_back(op);
+  return true;
+}
+
+int zero_f32(float* p, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (!mega_recording()) { CUDA_TRY(cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, st)); return 0; }
+  IWAE_REQUIRE(((uintptr_t)p & 15) == 0, "zero_f32: unaligned buffer");
+  const int blocks = (int)std::min<int64_t>((n / 4 + 2047) / 2048 + 1, 592);
+  CUDA_TRY(launch_pdl(zero_f32_kernel, dim3(blocks), dim3(256), 0, st, p, n));
+  return 0;
+}
+
+static int mega_state(iwae_ctx* ctx, MegaState** out) {
+  if (!ctx->mega) {
+    MegaState* m = new MegaState();
+    ctx->mega = m;
+    CUDA_TRY(cudaMalloc((void**)&m->bar, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(m->bar, 0, sizeof(unsigned long long)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->upload, cudaStreamNonBlocking));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel, 256, MEGA_SMEM_BYTES));
+    IWAE_REQUIRE(per_sm >= 1, "megakernel does not fit an SM");
+    m->grid = ctx->sm_count * std::min(per_sm, 2);
+  }
+  *out = ctx->mega;
+  return 0;
+}
+void mega_release(iwae_ctx* ctx) {
+  MegaState* m = ctx->mega;
+  if (!m) return;
+  for (MegaBuf& b : m->buf) {
+    if (b.dev) cudaFree(b.dev);
+    if (b.host) cudaFreeHost(b.host);
+    if (b.used) cudaEventDestroy(b.used);
+  }
+  if (m->bar) cudaFree(m->bar);
+  if (m->trace) cudaFree(m->trace);
+  if (m->upload) cudaStreamDestroy(m->upload);
+  delete m;
+  ctx->mega = nullptr;
+}
+
+int mega_begin(iwae_ctx* ctx, cudaStream_t st) {
+  MegaState* m;
+  IWAE_TRY(mega_state(ctx, &m));
+  IWAE_REQUIRE(!g_mega, "mega_begin: a recording is already open on this thread");
+  m->recording = true; m->failed = false; m->ops.clear(); m->lvl.clear(); m->why[0] = 0;
+  mega_level_of(m, st) = 0;
+  g_mega = m;
+  return 0;
+}
+void mega_abort(iwae_ctx* ctx) { if (ctx->mega && g_mega == ctx->mega) { g_mega = nullptr; ctx->mega->recording = false; } }
+
+// close the recording, build the level program, upload it and launch the megakernel on `st`
+int mega_flush(iwae_ctx* ctx, cudaStream_t st) {
+  MegaState* m = ctx->mega;
+  IWAE_REQUIRE(m && g_mega == m, "mega_flush: no open recording");
+  g_mega = nullptr; m->recording = false;
+  IWAE_REQUIRE(!m->failed, "train-step megakernel: %s", m->why);
+  if (m->ops.empty()) return 0;
+  // order: by level; inside a level the matrix products first (the longest virtual blocks start first), then issue order
+  std::vector<MegaOpHost*> ord;
+  for (auto& o : m->ops) ord.push_back(&o);
+  std::stable_sort(ord.begin(), ord.end(), [](const MegaOpHost* a, const MegaOpHost* b) {
+    if (a->level != b->level) return a->level < b->level;
+    const bool ga = a->type <= MT_GEMM_64_64, gb = b->type <= MT_GEMM_64_64;
+    if (ga != gb) return ga;
+    return a->seq < b->seq;
+  });
+  const int nlevels = ord.back()->level + 1;
+  const size_t lv_bytes = ((sizeof(MegaLevel) * (size_t)nlevels + 255) / 256) * 256;
+  const size_t bytes = lv_bytes + sizeof(MegaOp) * ord.size();
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  CUDA_TRY(cudaStreamIsCapturing(st, &cs));
+  const bool capturing = cs != cudaStreamCaptureStatusNone;
+  MegaBuf& b = m->buf[capturing ? 1 : 0];
+  if (b.cap < bytes || b.host_cap < bytes) {
+    IWAE_REQUIRE(!capturing, "train-step megakernel: program buffer too small during capture (%zu bytes)", bytes);
+    if (b.used) CUDA_TRY(cudaEventSynchronize(b.used));
+    if (b.dev) CUDA_TRY(cudaFree(b.dev));
+    if (b.host) CUDA_TRY(cudaFreeHost(b.host));
+    const size_t cap = bytes * 2;
+    CUDA_TRY(cudaMalloc((void**)&b.dev, cap)); b.cap = cap;
+    CUDA_TRY(cudaMallocHost((void**)&b.host, cap)); b.host_cap = cap;
+    // the captured graph's buffer is sized with the eager one (an eager step always precedes a capture)
+    MegaBuf& g = m->buf[1];
+    if (&g != &b && g.cap < cap) {
+      if (g.dev) CUDA_TRY(cudaFree(g.dev));
+      if (g.host) CUDA_TRY(cudaFreeHost(g.host));
+      CUDA_TRY(cudaMalloc((void**)&g.dev, cap)); g.cap = cap;
+      CUDA_TRY(cudaMallocHost((void**)&g.host, cap)); g.host_cap = cap;
+    }
+  }
+  if (!b.used) {
+    IWAE_REQUIRE(!capturing, "train-step megakernel: first use during capture");
+    CUDA_TRY(cudaEventCreateWithFlags(&b.used, cudaEventDisableTiming));
+    MegaBuf& g = m->buf[1];
+    if (!g.used) CUDA_TRY(cudaEventCreateWithFlags(&g.used, cudaEventDisableTiming));
+  } else if (!capturing) {
+    CUDA_TRY(cudaEventSynchronize(b.used));        // the previous upload has left the staging buffer
+  }
+  MegaLevel* lv = reinterpret_cast<MegaLevel*>(b.host);
+  MegaOp* ops = reinterpret_cast<MegaOp*>(b.host + lv_bytes);
+  memset(lv, 0, lv_bytes);
+  size_t smem = 0;
+  int cur = -1; unsigned vb = 0;
+  for (size_t i = 0; i < ord.size(); ++i) {
+    const MegaOpHost& h = *ord[i];
+    if (h.level != cur) {
+      // levels without operations cannot occur: a level is only created by an operation
+      cur = h.level; lv[cur].op_begin = (int)i; vb = 0;
+    }
+    MegaOp& o = ops[i];
+    o.type = h.type; o.gx = h.grid.x; o.gy = h.grid.y; o.gz = h.grid.z;
+    o.nblocks = h.grid.x * h.grid.y * h.grid.z; o.vb_start = vb; o.pad[0] = o.pad[1] = 0;
+    memcpy(o.args, h.args, MEGA_ARG_BYTES);
+    vb += o.nblocks;
+    lv[cur].op_end = (int)i + 1; lv[cur].total = vb;
+    smem = std::max(smem, h.smem);
+  }
+  for (int L = 0; L < nlevels; ++L) IWAE_REQUIRE(lv[L].op_end > lv[L].op_begin, "train-step megakernel: empty level %d", L);
+  if (capturing) {
+    // not a node of the graph: the program is constant for the life of the captured step
+    CUDA_TRY(cudaMemcpyAsync(b.dev, b.host, bytes, cudaMemcpyHostToDevice, m->upload));
+    CUDA_TRY(cudaStreamSynchronize(m->upload));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(b.dev, b.host, bytes, cudaMemcpyHostToDevice, st));
+  }
+  const MegaLevel* d_lv = reinterpret_cast<const MegaLevel*>(b.dev);
+  const MegaOp* d_ops = reinterpret_cast<const MegaOp*>(b.dev + lv_bytes);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(m->grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = MEGA_SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  static const char* trace_path = getenv("IWAE_MEGA_TRACE");
+  unsigned long long* trace = nullptr;
+  if (trace_path && !capturing) {
+    if (!m->trace) CUDA_TRY(cudaMalloc((void**)&m->trace, sizeof(unsigned long long) * 2 * 257));
+    IWAE_REQUIRE(nlevels <= 256, "trace: too many levels");
+    trace = m->trace;
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mega_kernel, d_lv, d_ops, nlevels, m->bar, trace));
+  LAUNCH_CHECK();
+  if (!capturing) CUDA_TRY(cudaEventRecord(b.used, st));
+  if (trace) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> t(2 * nlevels + 1);
+    CUDA_TRY(cudaMemcpy(t.data(), trace, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+    static const char* names[MT_COUNT] = {"gemm64x32", "gemm32x32", "gemm64x64", "concat_onehot", "sample_latent", "nlp_rows", "nlp_multi",
+      "kl_rows", "bern_reduce", "logw", "scal_part", "finalize", "row_coef", "dlogits", "latent1", "gauss_bwd", "latent2", "grad_reduce",
+      "splitk_bias", "splitk_mulh", "zero"};
+    FILE* fp = fopen(trace_path, "w");
+    if (fp) {
+      unsigned long long prev = t[2 * nlevels];
+      fprintf(fp, "# level  work_us(CTA 0)  barrier_us  ops (type:virtual blocks)   grid=%d CTAs\n", m->grid);
+      for (int L = 0; L < nlevels; ++L) {
+        fprintf(fp, "%3d  %7.2f  %7.2f ", L, (t[2 * L] - prev) * 1e-3, (t[2 * L + 1] - t[2 * L]) * 1e-3);
+        for (int i = lv[L].op_begin; i < lv[L].op_end; ++i) fprintf(fp, " %s:%u", names[ops[i].type], ops[i].nblocks);
+        fprintf(fp, "\n");
+        prev = t[2 * L + 1];
+      }
+      fprintf(fp, "# total %.2f us\n", (t[2 * nlevels - 1] - t[2 * nlevels]) * 1e-3);
+      fclose(fp);
+    }
+  }
   return 0;
 }
