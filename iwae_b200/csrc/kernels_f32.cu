@@ -804,54 +804,59 @@ __device__ __forceinline__ void latent1_bwd_body(const uint3 vb_, const dim3 vg_
       const float g = a.g[r];
       const float z = a.z[r * a.d + j], e = a.eps[r * a.d + j];
       float dz = a.dz_dec[r * a.ld_dz + j];
-      if (a.dz_q2) dz += a.dz_q2[r * a.d + j];
+      if (a.dz_q2) dz = __fadd_rn(dz, a.dz_q2[r * a.d + j]);
+      // (explicit roundings / fmaf below: the body is compiled into two kernels - its own and the train-step megakernel -
+      //  and the compiler's choice of which a*b+c to contract must not differ between them)
       if (dreg) {
         // task02.py:60-76: encoder signal = al * (decoder-path dz) - (al^2/B) * d(lpz - lq_stopped)/dz
         const float al = a.al[r];
-        const float sd2 = sd + 1e-6f;
-        dz = al * dz - (al * al / (float)a.B_norm) * (-z + (z - mu) / (sd2 * sd2));
-        acc_mu += dz;
-        acc_sd += dz * e;
+        const float sd2 = __fadd_rn(sd, 1e-6f);
+        const float inner = __fadd_rn(-z, __fdiv_rn(__fsub_rn(z, mu), __fmul_rn(sd2, sd2)));
+        dz = __fsub_rn(__fmul_rn(al, dz), __fmul_rn(__fdiv_rn(__fmul_rn(al, al), (float)a.B_norm), inner));
+        acc_mu = __fadd_rn(acc_mu, dz);
+        acc_sd = fmaf(dz, e, acc_sd);
         continue;
       }
       if (!klobj) {
         if (a.prior_rows == 0) {
-          dz += g * a.beta * (-z);
+          dz = fmaf(__fmul_rn(g, a.beta), -z, dz);
         } else {
           const int64_t pr = (a.prior_rows == 1) ? (int64_t)b * a.d + j : r * a.d + j;
           const float pm = a.pmu[pr], ps = a.pstd[pr];
-          const float bt = (a.prior_rows == 1) ? a.beta : 1.f;    // iwae2 ignores beta (iwae2.py:128)
-          const float t = (z - pm) / (ps * ps);
-          dz += g * bt * (-t);
-          const float dpm = g * bt * t;
-          const float dps = g * bt * ((z - pm) * t / ps - 1.f / ps);
-          if (a.prior_rows == 1) { acc_pmu += dpm; acc_psd += dps; }
-          else if (a.dpmu) { a.dpmu[pr] = dpm; a.dpa[pr] = dps * (ps - 1e-6f); }
+          const float gbt = (a.prior_rows == 1) ? __fmul_rn(g, a.beta) : g;    // iwae2 ignores beta (iwae2.py:128)
+          const float zc = __fsub_rn(z, pm);
+          const float t = __fdiv_rn(zc, __fmul_rn(ps, ps));
+          dz = fmaf(gbt, -t, dz);
+          const float dpm = __fmul_rn(gbt, t);
+          const float dps = __fmul_rn(gbt, __fsub_rn(__fdiv_rn(__fmul_rn(zc, t), ps), __fdiv_rn(1.f, ps)));
+          if (a.prior_rows == 1) { acc_pmu = __fadd_rn(acc_pmu, dpm); acc_psd = __fadd_rn(acc_psd, dps); }
+          else if (a.dpmu) { a.dpmu[pr] = dpm; a.dpa[pr] = __fmul_rn(dps, __fsub_rn(ps, 1e-6f)); }
         }
-        const float bt = (a.prior_rows == 2) ? 1.f : a.beta;
-        acc_sd += g * bt / sd;                                     // -beta * d lq/d std (total) = +beta/std
+        const float gb = (a.prior_rows == 2) ? g : __fmul_rn(g, a.beta);
+        acc_sd = __fadd_rn(acc_sd, __fdiv_rn(gb, sd));                 // -beta * d lq/d std (total) = +beta/std
       }
-      acc_mu += dz;
-      acc_sd += dz * e;
+      acc_mu = __fadd_rn(acc_mu, dz);
+      acc_sd = fmaf(dz, e, acc_sd);
     }
   }
   red[0][threadIdx.x] = acc_mu; red[1][threadIdx.x] = acc_sd; red[2][threadIdx.x] = acc_pmu; red[3][threadIdx.x] = acc_psd;
   __syncthreads();
   if (active && ks == 0) {
     for (int q = 1; q < KS; ++q) {
-      acc_mu += red[0][q * 32 + jl]; acc_sd += red[1][q * 32 + jl];
-      acc_pmu += red[2][q * 32 + jl]; acc_psd += red[3][q * 32 + jl];
+      acc_mu = __fadd_rn(acc_mu, red[0][q * 32 + jl]); acc_sd = __fadd_rn(acc_sd, red[1][q * 32 + jl]);
+      acc_pmu = __fadd_rn(acc_pmu, red[2][q * 32 + jl]); acc_psd = __fadd_rn(acc_psd, red[3][q * 32 + jl]);
     }
     if (klobj) {
       // loss = -mean lpxz + beta * mean_b kl ; d kl/d mu = mu, d kl/d std = std - 1/std
-      acc_mu += a.beta / (float)a.B_norm * mu;
-      acc_sd += a.beta / (float)a.B_norm * (sd - 1.f / sd);
+      const float bn = __fdiv_rn(a.beta, (float)a.B_norm);
+      acc_mu = fmaf(bn, mu, acc_mu);
+      acc_sd = fmaf(bn, __fsub_rn(sd, __fdiv_rn(1.f, sd)), acc_sd);
     }
     a.dmu[idx] = acc_mu;
-    a.da[idx] = acc_sd * (sd - 1e-6f);      // std = exp(a) + 1e-6
+    a.da[idx] = __fmul_rn(acc_sd, __fsub_rn(sd, 1e-6f));      // std = exp(a) + 1e-6
     if (a.prior_rows == 1 && a.dpmu) {
       a.dpmu[idx] = acc_pmu;
-      a.dpa[idx] = acc_psd * (a.pstd[idx] - 1e-6f);
+      a.dpa[idx] = __fmul_rn(acc_psd, __fsub_rn(a.pstd[idx], 1e-6f));
     }
   }
 }
