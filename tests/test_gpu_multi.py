@@ -70,5 +70,8 @@ def test_two_rank_dp_train_and_sharded_eval(tmp_path):
     rep = json.load(open(out))
     print(rep)
     # same noise (Philox keyed on the global image index), same arithmetic up to the summation order of the gradient
-    assert rep["iwae2"] < 1e-6 and rep["dreg"] < 1e-6, rep
+    # (per-rank partial sums over 10 images each vs one sum over 20).  Keras-Adam with epsilon = 1e-4 turns an absolute
+    # rounding difference dg of a near-zero gradient element into lr * dg / 1e-4 = 10 dg per step: measured 1.1e-6 (IWAE2)
+    # and 4.7e-7 (DReG) max |dp| after 5 steps, i.e. ~1e-3 of one learning-rate step.  Bound: 3e-6.
+    assert rep["iwae2"] < 3e-6 and rep["dreg"] < 3e-6, rep
     assert rep["eval_bit_exact"] and rep["eval_mean_err"] < 1e-9 * 450
