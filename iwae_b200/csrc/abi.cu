@@ -186,12 +186,15 @@ struct Fwd {
   float *lpxz = nullptr, *lpz = nullptr, *lq1 = nullptr, *lq2 = nullptr, *lp12 = nullptr, *lqst = nullptr;
   float *log_w = nullptr, *al = nullptr, *iwae = nullptr, *vae = nullptr, *eq14 = nullptr, *kl = nullptr,
         *dreg = nullptr, *snis1 = nullptr, *snis2 = nullptr;
+  float* g = nullptr;       // row coefficient of the backward pass, written by logw_reduce in gradient calls
 };
 
 struct FwdOpts {
   bool keep_for_bwd = false;   // materialise logits, eps, al
   bool want_dreg = false;
   bool lanes = false;          // train step: run independent branches on the context's side streams
+  int objective = -1;          // >= 0 (gradient calls): logw_reduce also writes the backward's row coefficient g
+  int B_norm = 0;
 };
 
 // `to` waits for everything issued so far on `from` (an event from the context's pool; re-recording an event after the
@@ -433,6 +436,12 @@ static int forward_internal(iwae_ctx* ctx, const float* P, const float* x, const
   if (f.lqst) IWAE_TRY(pick(ar, o->dreg, (size_t)B, &f.dreg));
   la.log_w = f.log_w; la.al = f.al; la.iwae = f.iwae; la.vae = f.vae; la.eq14 = f.eq14; la.dreg = f.dreg;
   la.snis1 = f.snis1; la.snis2 = f.snis2;
+  if (opt.objective >= 0) {
+    // DReG's decoder part is the IWAE-ELBO gradient (task02.py:96)
+    IWAE_TRY(ar.get(&f.g, (size_t)R));
+    la.g_out = f.g; la.B_norm = opt.B_norm;
+    la.g_vae = (opt.objective == IWAE_OBJ_VAE_ELBO || opt.objective == IWAE_OBJ_VAE_ELBO_KL) ? 1 : 0;
+  }
   IWAE_TRY(logw_reduce(la, st));
   if (o->scalars) {
     ScalarArgs sa;
@@ -818,9 +827,11 @@ static int backward_internal(iwae_ctx* ctx, const float* P, const Fwd& f, float 
     w_dec = ctx->lane[1]; w_lat = ctx->lane[2];
     if (m.two_layer()) s_dec = ctx->lane[0];
   }
-  float *g, *dl, *da2, *da1, *dzin;
-  IWAE_TRY(ar.get(&g, (size_t)R));
-  IWAE_TRY(row_coef(f.al, B, k, dec_obj, B_norm, g, st));
+  float *g = f.g, *dl, *da2, *da1, *dzin;
+  if (!g) {                                        // (a forward that did not write the coefficient)
+    IWAE_TRY(ar.get(&g, (size_t)R));
+    IWAE_TRY(row_coef(f.al, B, k, dec_obj, B_norm, g, st));
+  }
   IWAE_TRY(lane_dep(ctx, st, s_dec));
   IWAE_TRY(ar.get(&dl, (size_t)R * nx));
   IWAE_TRY(dlogits_f32(f.logits, f.x, g, (int)R, B, nx, dl, s_dec));
@@ -904,6 +915,7 @@ static int grads_internal(iwae_ctx* ctx, const float* params, const float* x, co
   opt.want_dreg = (objective == IWAE_OBJ_DREG);
   static const bool no_lanes = getenv("IWAE_NO_LANES") != nullptr;
   opt.lanes = !no_lanes;
+  opt.objective = objective; opt.B_norm = B_norm;
   // Training shapes: forward + backward + update as ONE persistent kernel (kernels_f32.cu, "train-step megakernel"): the
   // launches below are recorded with their stream / event structure and run level by level behind grid barriers.
   static const bool mega_on = getenv("IWAE_MEGA") != nullptr;

@@ -188,6 +188,9 @@ struct LogwArgs {
   float *log_w = nullptr, *al = nullptr, *iwae = nullptr, *vae = nullptr, *eq14 = nullptr, *dreg = nullptr;
   float *snis1 = nullptr, *snis2 = nullptr;
   int al_in_smem = 0;                       // set by logw_reduce
+  // train step: the backward's per-row coefficient g[r] = d(-objective)/d(log_w[r]) (A.4) written here instead of by a
+  // kernel of its own: -al/B_norm for the importance-weighted objectives, -1/(k B_norm) for the VAE ones (g_vae)
+  float* g_out = nullptr; int g_vae = 0; int B_norm = 0;
 };
 int logw_reduce(const LogwArgs& a, cudaStream_t st);
 struct ScalarArgs {

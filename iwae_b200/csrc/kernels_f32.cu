@@ -544,6 +544,7 @@ __device__ __forceinline__ void logw_reduce_body(const uint3 vb_, const dim3 vg_
     if (a.two_layer) lw = a.lpxz[r] + a.lp12[r] + a.lpz[r] - a.lq1[r] - a.lq2[r];     // iwae2.py:126
     else lw = a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);                              // iwae1.py:113
     if (a.log_w) a.log_w[r] = lw;
+    if (a.g_out && a.g_vae) a.g_out[r] = -1.f / ((float)k * (float)a.B_norm);
     mx = fmaxf(mx, lw);
     sm += lw;
   }
@@ -562,7 +563,7 @@ __device__ __forceinline__ void logw_reduce_body(const uint3 vb_, const dim3 vg_
     if (a.iwae) a.iwae[b] = logf(se / (float)k) + mx;       // utils.logmeanexp (utils.py:6-8)
     if (a.vae) a.vae[b] = sm / (float)k;
   }
-  const bool need_al = a.al || a.eq14 || a.dreg || a.snis1 || a.snis2;
+  const bool need_al = a.al || a.eq14 || a.dreg || a.snis1 || a.snis2 || (a.g_out && !a.g_vae);
   if (!need_al) return;
   // pass 3: normalised weights, eq14, DReG
   float e14 = 0.f, dr = 0.f;
@@ -572,6 +573,7 @@ __device__ __forceinline__ void logw_reduce_body(const uint3 vb_, const dim3 vg_
                            : a.lpxz[r] + a.beta * (a.lpz[r] - a.lq1[r]);
     const float w = expf(lw - mx) / se;
     if (a.al) a.al[r] = w;
+    if (a.g_out && !a.g_vae) a.g_out[r] = -w / (float)a.B_norm;
     if (a.al_in_smem) s_al[s] = w;
     e14 += w * lw;
     if (a.dreg) dr += w * w * (a.lpz[r] + a.lpxz[r] - a.lq_stopped[r]);                // task02.py:70-73
