@@ -1414,11 +1414,8 @@ int dense_chain(const ChainArgs& a_in, cudaStream_t st) {
   const size_t smem = chain_plan(a);
   IWAE_REQUIRE(smem > 0 && smem <= CHAIN_SMEM_MAX, "dense_chain: the chain does not fit shared memory (%zu bytes)", smem);
   if (a.M <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
-    attr_set = true;
-  }
+  // (per device and cheap: set on every launch rather than remembered in a process-wide flag)
+  CUDA_TRY(cudaFuncSetAttribute(dense_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
   CUDA_TRY(launch_pdl(dense_chain_kernel, dim3((a.M + CHAIN_TM - 1) / CHAIN_TM), dim3(256), smem, st, a));
   LAUNCH_CHECK();
   return 0;
