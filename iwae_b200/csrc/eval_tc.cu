@@ -176,11 +176,17 @@ struct Layer {
                                //    and the later chunks go to the START of the activation buffer, which follows the z1 buffer in
                                //    shared memory: the output is then ONE contiguous K-major operand that begins at the z1 buffer
   int src_split;               // 1: this layer reads that contiguous operand (src == 0, k_pad > KZ_MAX)
+  // Early hand-off between two dependent layers: the epilogue warps of a TANH layer signal `act_early` as soon as the first
+  // SLAB_K output columns of every row are in shared memory (early_sig), and the MMA issuer of the next layer starts
+  // with the K steps of its first weight slab then, waiting for `act_ready` (all columns) only before the second slab
+  // (wait_split).  Hides ~half of the issue + tensor latency of the dependent chain of small layers.
+  int early_sig, wait_split;
 };
 struct Program {
   int nlayers, two_layer, cond, learned_prior;
   int d1, d2, nc, nx, kz_pad;  // kz_pad: K of the layers that read z1
   int z1_lo;                   // 1: room for the fp16 "lo" halves of z1 (hi + lo = 22 bits) next to the operands, see stage 0
+  int stage0_early;            // 1: stage 0 signals act_early once the first SLAB_K columns of z1 are written (Layer::early_sig)
   Layer L[MAX_LAYERS];
 };
 
@@ -240,7 +246,7 @@ struct __align__(16) SmemLayout {
   uint8_t ring[NSTAGES][SLAB_BYTES];
   // full / empty: weight ring.  acc_full[b]: accumulator buffer b complete (commit, multicast).  acc_empty[b],
   // act_ready: arrived on by the epilogue warps of BOTH CTAs, in the leader's shared memory (the MMA issuer waits there)
-  uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready;
+  uint64_t full[NSTAGES], empty[NSTAGES], acc_full[2], acc_empty[2], act_ready, act_early;
   uint32_t tmem_base;
 };
 
@@ -403,6 +409,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], NUM_EPI_WARPS * PAIR); }
     mbar_init(&S.act_ready, NUM_EPI_WARPS * PAIR);
+    mbar_init(&S.act_early, NUM_EPI_WARPS * PAIR);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_cg(&S.tmem_base, TMEM_COLS); tmem_relinquish_cg(); }
@@ -473,7 +480,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
     if (elect_one_sync()) {
     const uint32_t issue = 1u;
     uint32_t stage = 0, phase = 0, cc = 0;
-    uint32_t act_phase = 0;
+    uint32_t act_phase = 0, early_phase = 0;
     uint32_t empty_bits = 0;     // phase bit of acc_empty[buf] at bit buf (a register, not a dynamically indexed array)
     const uint32_t ring0 = smem_u32(S.ring[0]);
     const uint32_t z0 = smem_u32(S.sub.bufZ), p0 = smem_u32(S.sub.bufP);
@@ -481,7 +488,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
 
     for (uint32_t mt = mt_begin; mt < mt_end; ++mt, ++tl) {
       for (int l = 0; l < P.nlayers; ++l) {
-        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act;
+        const int nchunks = P.L[l].nchunks, k_pad = P.L[l].k_pad, wait_act = P.L[l].wait_act, wait_split = P.L[l].wait_split;
         const uint32_t a_base0 = P.L[l].src ? p0 : z0;
         trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 0);
         for (int c = 0; c < nchunks; ++c) {
@@ -489,7 +496,8 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           const uint32_t n = (uint32_t)P.L[l].chunk_n[c];
           const uint32_t idesc = make_idesc_cg(n);
           if (wait_act && c == 0) {
-            mbar_wait_pair(&S.act_ready, act_phase, 200); act_phase ^= 1;
+            if (wait_split) { mbar_wait_pair(&S.act_early, early_phase, 203); early_phase ^= 1; }     // first slab's columns only
+            else { mbar_wait_pair(&S.act_ready, act_phase, 200); act_phase ^= 1; }
             trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 1);
           }
           // Every epilogue warp signals act_ready only AFTER it has drained (and signalled acc_empty for) all chunks of
@@ -505,6 +513,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           // descriptors: only the 14-bit start-address field (16-byte units) changes between MMAs
           uint64_t ad = make_smem_desc(a_base0, TILE_M * 16, 128);
           for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
+            if (wait_split && c == 0 && k0 == SLAB_K) { mbar_wait_pair(&S.act_ready, act_phase, 204); act_phase ^= 1; }
             mbar_wait_pair(&S.full[stage], phase, 202);
             tc_fence_after();
             uint64_t bd = make_smem_desc(ring0 + stage * SLAB_BYTES, n_share * 16u, 128);
@@ -546,8 +555,10 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
     // the barriers the MMA issuer waits on live in the leader CTA
 #if IWAE_PAIR
     const uint32_t act_ready_l = map_to_rank(smem_u32(&S.act_ready), 0), acc_empty_l = map_to_rank(smem_u32(&S.acc_empty[0]), 0);
+    const uint32_t act_early_l = map_to_rank(smem_u32(&S.act_early), 0);
 #else
     const uint32_t act_ready_l = smem_u32(&S.act_ready), acc_empty_l = smem_u32(&S.acc_empty[0]);
+    const uint32_t act_early_l = smem_u32(&S.act_early);
 #endif
     const int d1 = P.d1, nx = P.nx;
     const int nx_pad = (nx + 15) & ~15;
@@ -682,6 +693,14 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           put_lo(k0, v);
           put_z(args.z1_out, d1, k0, v);
         };
+        // early hand-off to the first layer: after this warp's last 8-dim group below SLAB_K
+        auto maybe_early = [&](int kgrp) {
+          if (P.stage0_early && kgrp < SLAB_K && kgrp + 16 >= SLAB_K) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(act_early_l);
+          }
+        };
         int k0 = 8 * half;
         if (FAST) {
           // two groups per iteration: two independent Philox / Box-Muller chains in flight per thread (the
@@ -692,6 +711,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             noise8(1u, (uint32_t)(k0 >> 3) + 2u, d1, eb);
             full_group(k0, ea, va);
             full_group(k0 + 16, eb, vb);
+            maybe_early(k0 + 16);
           }
         }
         for (; k0 < P.kz_pad; k0 += 16) {
@@ -700,6 +720,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             float ea[8];
             noise8(1u, (uint32_t)(k0 >> 3), d1, ea);
             full_group(k0, ea, v);
+            maybe_early(k0);
             continue;
           } else {
             float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -740,6 +761,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           store8(T.bufZ, row, k0, v);
           if (k0 < d1) put_lo(k0, v);
           put_z(args.z1_out, d1, k0, v);
+          maybe_early(k0);
         }
         if (FAST) { acc.template add<T_LQ1>(-0.5f * e1sum); acc.template add<T_PRIOR>(-0.5f * z1sum); }     // constants are added once per row at the end
       }
@@ -755,6 +777,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
         // layer constants once per layer (the asm statements' memory clobbers otherwise force re-reads per chunk)
         const int kind = Ly.kind, nchunks = Ly.nchunks;
         const bool wait_all = Ly.inplace && nchunks > 1, split_dst = Ly.split_dst != 0, signal_act = Ly.signal_act != 0;
+        const bool early_sig = Ly.early_sig != 0;
         uint8_t* dst = Ly.dst ? T.bufP : T.bufZ;
         if (wait_all) {
           // all chunks' MMAs must have retired before the input buffer is overwritten
@@ -787,6 +810,12 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
               store16(dstc, row, off + g, v);
+              // this warp's last group below SLAB_K of chunk 0: the first weight slab's K columns are complete for its rows
+              if (early_sig && c == 0 && g < SLAB_K && g + 32 >= SLAB_K) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(act_early_l);
+              }
             });
           } else if (kind == EPI_GSAMPLE) {
             // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8]
@@ -1266,6 +1295,23 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P, bool fast)
       D1.split_dst = 1; D1.inplace = 0;
       BL.src_split = 1; BL.src = 0;
     }
+  }
+  // early hand-off (see Layer::early_sig): TANH producer whose chunk 0 covers the consumer's whole first slab, written
+  // to where the consumer reads it (not the split destination), consumer with more than one slab
+  static const bool no_early = getenv("IWAE_TC_NO_EARLY") != nullptr;
+  for (int l = 0; l + 1 < nl && !no_early; ++l) {
+    Layer& A = pr.L[l]; Layer& B = pr.L[l + 1];
+    // (single-chunk producers only: the consumer's first chunk then accumulates into the OTHER TMEM buffer, which every
+    //  epilogue warp has drained before it reached this layer; a two-chunk producer would still be reading it)
+    if (A.kind == EPI_TANH && A.nchunks == 1 && A.signal_act && !A.split_dst && A.chunk_n[0] >= SLAB_K && A.chunk_off[0] == 0 &&
+        B.wait_act && B.src == A.dst && !B.src_split && B.k_pad > SLAB_K) {
+      A.early_sig = 1; B.wait_split = 1;
+    }
+  }
+  // ... and the sampling stage hands the first slab of z1 to the first layer the same way (needs every dim below SLAB_K to
+  // be a latent dim written by complete 8-dim groups)
+  if (!no_early && pr.L[0].wait_act && pr.L[0].src == 0 && pr.L[0].k_pad > SLAB_K && (c.d1 & ~7) >= SLAB_K) {
+    pr.stage0_early = 1; pr.L[0].wait_split = 1;
   }
   // packed offsets
   int64_t off = 0;
