@@ -105,6 +105,24 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_wait_pair(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns = 32) {
   mbar_wait(bar, parity, tag, sleep_ns);
 }
+// IWAE_MMA_CONVERGED = 1: the MMA role runs with all 32 lanes converged (only the tcgen05 instructions are predicated on the
+// elected lane) and its barrier waits keep the control flow warp-UNIFORM (the loop condition is a vote), so that the
+// compiler can keep the descriptor arithmetic in uniform registers - the operand form UTCHMMA reads - instead of moving
+// seven vector registers to uniform ones (R2UR) in front of every MMA.
+#ifndef IWAE_MMA_CONVERGED
+#define IWAE_MMA_CONVERGED 1
+#endif
+__device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t parity, int tag) {
+#if IWAE_MMA_CONVERGED
+  uint32_t polls = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    __nanosleep(32);
+    if (++polls > (1u << 26)) { if ((threadIdx.x & 31) == 0) printf("iwae_b200: mbarrier timeout tag=%d block=%d\n", tag, blockIdx.x); __trap(); }
+  }
+#else
+  mbar_wait(bar, parity, tag, 32);
+#endif
+}
 __device__ __forceinline__ void tmem_alloc_cg(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc." IWAE_CG ".sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
 }
@@ -214,7 +232,7 @@ struct EvalArgs {
   long long* trace;            // debug timeline (IWAE_TC_TRACE=<file>): [cta<4][role<3][512] (tag, clock64) pairs, else null
 };
 
-#define TRACE_SLOTS 512
+#define TRACE_SLOTS 1024
 // tag = tile_local*10000 + layer*100 + chunk*10 + phase
 template <bool TRACE>
 __device__ __forceinline__ void trace_ev(const EvalArgs& a, int role, int& n, int tag) {
@@ -260,6 +278,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 
 template <bool FAST>
 __device__ __forceinline__ float act_tanh(float v) {
+#ifdef IWAE_DIAG_NOTANH
+  return v * 0.25f;                            // timing diagnostic only (wrong results): the layer without its MUFU.TANH
+#endif
   if (FAST) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
   return tanhf(v);
 }
@@ -317,7 +338,19 @@ __device__ __forceinline__ float ex2_poly_neg(float x) {
 template <bool FAST>
 __device__ __forceinline__ void normal8(uint64_t seed, uint32_t stream_id, uint32_t img, uint32_t s, uint32_t g, float (&o)[8]) {
   if (!FAST) { philox_normal8(seed, stream_id, img, s, g, o); return; }
+#ifdef IWAE_DIAG_NONOISE
+  {                                            // timing diagnostic only (wrong results): no generator at all
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.125f * (float)((int)((s + g + i) & 15u) - 8);
+    return;
+  }
+#endif
+#ifdef IWAE_DIAG_NOPHILOX
+  // timing diagnostic only (wrong results): Box-Muller kept, the Philox rounds replaced by one multiply per word
+  const uint4 r = make_uint4(s * 2654435761u + g, g * 40503u + img, (s ^ img) * 2246822519u, (s + stream_id) * 3266489917u);
+#else
   const uint4 r = philox4x32_10(make_uint4(s, g, img, stream_id), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+#endif
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
@@ -389,7 +422,9 @@ __cluster_dims__(2, 1, 1)
 __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_constant__ EvalArgs args, const __grid_constant__ Program P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (the warp index through a shuffle: the compiler then knows it is warp-uniform, so the role branches below are uniform
+  //  branches and the code inside them may use the uniform datapath - what CUTLASS calls canonical_warp_idx_sync)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t rank = IWAE_PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs), 1 = peer
   // Work unit of a CTA group: PAIR consecutive tiles (one per CTA).  Each group owns a CONTIGUOUS range of units:
   // consecutive tiles then belong to the same image (k/128 tiles per image), so the per-image constants (x, mu, std:
@@ -477,8 +512,13 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
     // instructions themselves are predicated on the elected lane.  (Round 1 ran the role inside one elected thread:
     // every MMA then cost ~20 instructions of a dependent chain incl. 4 R2UR moves, ~130 cycles per MMA against the
     // 56 the tensor pipe needs; with an elect / reconverge per slab it was ~200, scripts/umma_bench3.py.)
+#if IWAE_MMA_CONVERGED
+    {
+    const uint32_t issue = elect_one_sync();
+#else
     if (elect_one_sync()) {
     const uint32_t issue = 1u;
+#endif
     uint32_t stage = 0, phase = 0, cc = 0;
     uint32_t act_phase = 0, early_phase = 0;
     uint32_t empty_bits = 0;     // phase bit of acc_empty[buf] at bit buf (a register, not a dynamically indexed array)
@@ -496,15 +536,15 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           const uint32_t n = (uint32_t)P.L[l].chunk_n[c];
           const uint32_t idesc = make_idesc_cg(n);
           if (wait_act && c == 0) {
-            if (wait_split) { mbar_wait_pair(&S.act_early, early_phase, 203); early_phase ^= 1; }     // first slab's columns only
-            else { mbar_wait_pair(&S.act_ready, act_phase, 200); act_phase ^= 1; }
+            if (wait_split) { mma_wait(&S.act_early, early_phase, 203); early_phase ^= 1; }     // first slab's columns only
+            else { mma_wait(&S.act_ready, act_phase, 200); act_phase ^= 1; }
             trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + 1);
           }
           // Every epilogue warp signals act_ready only AFTER it has drained (and signalled acc_empty for) all chunks of
           // the layer before: once act_ready has completed, both accumulator buffers are known to be free, so the first
           // two chunks of such a layer skip the acc_empty wait (a try_wait on a completed barrier still costs ~100
           // cycles of the issuing warp's dependent chain); the phase bookkeeping advances either way.
-          if (!(wait_act && c < 2)) mbar_wait_pair(&S.acc_empty[buf], ((empty_bits >> buf) & 1u) ^ 1u, 201);
+          if (!(wait_act && c < 2)) mma_wait(&S.acc_empty[buf], ((empty_bits >> buf) & 1u) ^ 1u, 201);
           empty_bits ^= 1u << buf;
           tc_fence_after();
           trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
@@ -513,8 +553,8 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           // descriptors: only the 14-bit start-address field (16-byte units) changes between MMAs
           uint64_t ad = make_smem_desc(a_base0, TILE_M * 16, 128);
           for (int k0 = 0; k0 < k_pad; k0 += SLAB_K) {
-            if (wait_split && c == 0 && k0 == SLAB_K) { mbar_wait_pair(&S.act_ready, act_phase, 204); act_phase ^= 1; }
-            mbar_wait_pair(&S.full[stage], phase, 202);
+            if (wait_split && c == 0 && k0 == SLAB_K) { mma_wait(&S.act_ready, act_phase, 204); act_phase ^= 1; }
+            mma_wait(&S.full[stage], phase, 202);
             tc_fence_after();
             uint64_t bd = make_smem_desc(ring0 + stage * SLAB_BYTES, n_share * 16u, 128);
             const int ksteps = min(SLAB_K, k_pad - k0) >> 4;
@@ -816,6 +856,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(act_early_l);
               }
+              trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 8);
             });
           } else if (kind == EPI_GSAMPLE) {
             // Gaussian-head column layout: 16 columns per 8 latent dims, [mu x8 | log-std pre-activation x8]
@@ -982,11 +1023,20 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                 const float4* sg4 = reinterpret_cast<const float4*>(&T.sgn[off + g]);
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
+#ifndef IWAE_DIAG_NOSIGN
                   const float4 sg = sg4[i4];
+#endif
                   const float l0 = __uint_as_float(r[4 * i4]), l1 = __uint_as_float(r[4 * i4 + 1]);
                   const float l2 = __uint_as_float(r[4 * i4 + 2]), l3 = __uint_as_float(r[4 * i4 + 3]);
+#ifndef IWAE_DIAG_NOSIGN
                   s0 = fmaf(sg.x, l0, s0); s1 = fmaf(sg.y, l1, s1); s0 = fmaf(sg.z, l2, s0); s1 = fmaf(sg.w, l3, s1);
+#endif
                   a0 += fabsf(l0); a1 += fabsf(l1); a0 += fabsf(l2); a1 += fabsf(l3);
+#ifdef IWAE_DIAG_NOEX2
+                  if (true) {                  // timing diagnostic only (wrong results): the pixel without its MUFU.EX2
+                    p0 = fmaf(p0, -fabsf(l0), p0); p1 = fmaf(p1, -fabsf(l1), p1); p2 = fmaf(p2, -fabsf(l2), p2); p3 = fmaf(p3, -fabsf(l3), p3);
+                  } else
+#endif
                   if (i4 < 4 - IWAE_EX2_POLY) {
                     p0 = fmaf(p0, ex2_approx(-fabsf(l0)), p0); p1 = fmaf(p1, ex2_approx(-fabsf(l1)), p1);
                     p2 = fmaf(p2, ex2_approx(-fabsf(l2)), p2); p3 = fmaf(p3, ex2_approx(-fabsf(l3)), p3);
@@ -995,6 +1045,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
                     p2 = fmaf(p2, ex2_poly_neg(-fabsf(l2)), p2); p3 = fmaf(p3, ex2_poly_neg(-fabsf(l3)), p3);
                   }
                 }
+                trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 8);
               });
               bern_s += s0 + s1; bern_a += a0 + a1;
               bern_lg += lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
