@@ -23,6 +23,11 @@ int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, int
  * first issue to completion.  Used to size the fused kernel's MMA width (scripts/umma_bench.py). */
 int iwae_umma_bench(int32_t N, int32_t reps, int32_t nctas, int64_t* out_cycles, void* stream);
 
+/* TMEM-read micro-benchmark (diagnostic): cycles of `reps` 16-column accumulator groups per warp for the epilogue's
+ * load patterns (mode 0/1: tcgen05.ld .x16 serial / double-buffered, 2/3: .x32, 4/6: with the tanh MUFU work, 5: MUFU
+ * only), `nwarps` warps per CTA (nwarps/4 per TMEM lane quarter).  out_cycles [nctas*nwarps].  scripts/ldtm_bench.py. */
+int iwae_ldtm_bench(int32_t mode, int32_t nwarps, int32_t reps, int32_t nctas, int64_t* out_cycles, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,8 @@ def diag_lib():
         d.iwae_umma_selftest.argtypes = [vp, vp, i32, i32, i32, vp, vp]
         d.iwae_umma_bench.restype = C.c_int
         d.iwae_umma_bench.argtypes = [i32, i32, i32, vp, vp]
+        d.iwae_ldtm_bench.restype = C.c_int
+        d.iwae_ldtm_bench.argtypes = [i32, i32, i32, i32, vp, vp, vp]
         _diag = d
     return _diag
 

@@ -154,6 +154,9 @@ __device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
 // elected lane (issue != 0) executes the tcgen05 instruction.
 __device__ __forceinline__ void umma_f16_cg_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
                                                  uint32_t issue) {
+#ifdef IWAE_DIAG_NOMMA
+  return;                                      // timing diagnostic only (wrong results): the schedule without tensor work
+#endif
   asm volatile(
       "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma." IWAE_CG
       ".kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
@@ -199,6 +202,9 @@ struct Layer {
   // with the K steps of its first weight slab then, waiting for `act_ready` (all columns) only before the second slab
   // (wait_split).  Hides ~half of the issue + tensor latency of the dependent chain of small layers.
   int early_sig, wait_split;
+  int early_two;               // wait_split consumer of a TWO-chunk producer: its first chunk accumulates into the TMEM buffer of the
+                               // producer's chunk 0, so the issuer waits for that buffer's acc_empty explicitly (after a one-chunk
+                               // producer the consumer's first chunk gets the other buffer, drained a layer earlier)
 };
 struct Program {
   int nlayers, two_layer, cond, learned_prior;
@@ -389,6 +395,71 @@ __device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int
   }
 }
 
+// IWAE_LDX32 = 1: the two warps of a lane quarter split a chunk into alternating 32-column groups and read each with ONE
+// tcgen05.ld .x32 (a trailing 16-column group with .x16), double-buffered: 32 columns of arithmetic cover the latency of
+// the next load instead of 16 (the timeline shows ~400 cycles per 16-column group whatever the arithmetic - tanh or
+// Bernoulli - i.e. the group period is the load's latency, not the XU pipe's 128 cycles).
+#ifndef IWAE_LDX32
+#define IWAE_LDX32 0
+#endif
+constexpr int LD_COLS = IWAE_LDX32 ? 32 : 16;      // columns per epilogue load group
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// the 16 low registers of a 32-register group as their own array (constant indices after inlining: stays in registers)
+__device__ __forceinline__ void tmem_ld16_lo(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// f(r16, g) for every 16-column group of this warp's 32-column groups g_first, g_first + 64, ...
+template <class F>
+__device__ __forceinline__ void for_each_32cols(uint32_t taddr, int g_first, int ncols, F&& f) {
+  if (g_first >= ncols) return;
+  uint32_t ra[32], rb[32];
+  auto ld = [&](int g, uint32_t (&r)[32]) { if (g + 32 <= ncols) tmem_ld32(taddr + g, r); else tmem_ld16_lo(taddr + g, r); };
+  auto proc = [&](int g, const uint32_t (&r)[32]) {
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo[i] = r[i]; hi[i] = r[16 + i]; }
+    f(lo, g);
+    if (g + 32 <= ncols) f(hi, g + 16);
+  };
+  ld(g_first, ra);
+  tmem_ld_wait();
+  for (int g = g_first; g < ncols; g += 128) {
+    const bool has_b = g + 64 < ncols;
+    if (has_b) ld(g + 64, rb);
+    proc(g, ra);
+    if (has_b) {
+      tmem_ld_wait();
+      const bool has_a = g + 128 < ncols;
+      if (has_a) ld(g + 128, ra);
+      proc(g + 64, rb);
+      if (has_a) tmem_ld_wait();
+    }
+  }
+}
+template <class F>
+__device__ __forceinline__ void for_each_cols(uint32_t taddr, int g_first, int ncols, F&& f) {
+#if IWAE_LDX32
+  for_each_32cols(taddr, g_first, ncols, f);
+#else
+  for_each_16cols(taddr, g_first, ncols, f);
+#endif
+}
+
 // TRACE: the timeline instrumentation (IWAE_TC_TRACE) is compiled into a separate instantiation
 // The five log-density terms of a row (sums over columns).  The evaluation needs only their signed sum (one register);
 // TERMS mode keeps them apart (five registers) and writes them per row.
@@ -544,7 +615,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           // the layer before: once act_ready has completed, both accumulator buffers are known to be free, so the first
           // two chunks of such a layer skip the acc_empty wait (a try_wait on a completed barrier still costs ~100
           // cycles of the issuing warp's dependent chain); the phase bookkeeping advances either way.
-          if (!(wait_act && c < 2)) mma_wait(&S.acc_empty[buf], ((empty_bits >> buf) & 1u) ^ 1u, 201);
+          if (!(wait_act && c < 2) || (c == 0 && P.L[l].early_two)) mma_wait(&S.acc_empty[buf], ((empty_bits >> buf) & 1u) ^ 1u, 201);
           empty_bits ^= 1u << buf;
           tc_fence_after();
           trace_ev<TRACE>(args, 1, tn, tl * 10000 + l * 100 + c * 10 + 2);
@@ -837,7 +908,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 5);
           const uint32_t tbase = tmem_base + lane_addr + buf * 128u;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
-          const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
+          const int g_first = LD_COLS * ((half + c) & 1);     // this warp's first column group of the chunk
 
           if (kind == EPI_TANH) {
             // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
@@ -845,13 +916,14 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             // split destination: unit j of the layer lands at K column j of the contiguous operand that starts at the z1
             // buffer (the activation buffer follows it in shared memory; bufZ holds exactly KZ_MAX columns)
             uint8_t* dstc = split_dst ? T.bufZ : dst;
-            for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
+            for_each_cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
               store16(dstc, row, off + g, v);
               // this warp's last group below SLAB_K of chunk 0: the first weight slab's K columns are complete for its rows
-              if (early_sig && c == 0 && g < SLAB_K && g + 32 >= SLAB_K) {
+              const int next_g = IWAE_LDX32 ? (((g - g_first) & 16) ? g + 48 : g + 16) : g + 32;     // this warp's next 16-column group
+              if (early_sig && c == 0 && g < SLAB_K && next_g >= SLAB_K) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(act_early_l);
@@ -1019,7 +1091,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             // are batched: one lg2 per <= 32 factors (1 + 2^-|l'|) in (1, 2].
             if (FAST) {
               float p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
-              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
+              for_each_cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
                 const float4* sg4 = reinterpret_cast<const float4*>(&T.sgn[off + g]);
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
@@ -1051,7 +1123,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
               bern_lg += lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
             } else {
               float bsum = 0.f;
-              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
+              for_each_cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float lgt = __uint_as_float(r[i]);
@@ -1070,9 +1142,9 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           ++cc;
         }
         if (signal_act) {
-#ifndef IWAE_EXP_NOFENCE
+          // (issuing this proxy fence BEFORE the acc_empty arrive of the last chunk, so that its MEMBAR does not wait for the
+          //  remote arrive, measured 0.5 % slower: the accumulator is handed back later)
           fence_proxy_async();
-#endif
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(act_ready_l);
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + 7);
@@ -1354,9 +1426,15 @@ static int build_program(const ModelP& m, TcPack& tp, const float* P, bool fast)
     Layer& A = pr.L[l]; Layer& B = pr.L[l + 1];
     // (single-chunk producers only: the consumer's first chunk then accumulates into the OTHER TMEM buffer, which every
     //  epilogue warp has drained before it reached this layer; a two-chunk producer would still be reading it)
-    if (A.kind == EPI_TANH && A.nchunks == 1 && A.signal_act && !A.split_dst && A.chunk_n[0] >= SLAB_K && A.chunk_off[0] == 0 &&
-        B.wait_act && B.src == A.dst && !B.src_split && B.k_pad > SLAB_K) {
-      A.early_sig = 1; B.wait_split = 1;
+    // A two-chunk producer qualifies too (IWAE_TC_EARLY2=0 turns it off): the first slab's columns all come from its chunk 0,
+    // whose TMEM buffer is the one the consumer's first chunk accumulates into - the issuer then waits for that buffer's
+    // acc_empty (Layer::early_two).  The producer's chunk 0 must land where the consumer's operand begins: the same buffer,
+    // or the z1 buffer for the split pair (second decoder layer -> logit layer).
+    static const bool early2 = !(getenv("IWAE_TC_EARLY2") && atoi(getenv("IWAE_TC_EARLY2")) == 0);
+    const bool same_base = (A.split_dst && B.src_split) || (!A.split_dst && !B.src_split && B.src == A.dst);
+    if (A.kind == EPI_TANH && (A.nchunks == 1 || (A.nchunks == 2 && early2 && !A.inplace)) && A.signal_act && A.chunk_n[0] >= SLAB_K &&
+        A.chunk_off[0] == 0 && B.wait_act && same_base && B.k_pad > SLAB_K && (A.nchunks == 2 || !A.split_dst)) {
+      A.early_sig = 1; B.wait_split = 1; B.early_two = (A.nchunks == 2) ? 1 : 0;
     }
   }
   // ... and the sampling stage hands the first slab of z1 to the first layer the same way (needs every dim below SLAB_K to
