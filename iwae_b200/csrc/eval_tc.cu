@@ -395,71 +395,6 @@ __device__ __forceinline__ void for_each_16cols(uint32_t taddr, int g_first, int
   }
 }
 
-// IWAE_LDX32 = 1: the two warps of a lane quarter split a chunk into alternating 32-column groups and read each with ONE
-// tcgen05.ld .x32 (a trailing 16-column group with .x16), double-buffered: 32 columns of arithmetic cover the latency of
-// the next load instead of 16 (the timeline shows ~400 cycles per 16-column group whatever the arithmetic - tanh or
-// Bernoulli - i.e. the group period is the load's latency, not the XU pipe's 128 cycles).
-#ifndef IWAE_LDX32
-#define IWAE_LDX32 0
-#endif
-constexpr int LD_COLS = IWAE_LDX32 ? 32 : 16;      // columns per epilogue load group
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-      "%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-        "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-// the 16 low registers of a 32-register group as their own array (constant indices after inlining: stays in registers)
-__device__ __forceinline__ void tmem_ld16_lo(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-// f(r16, g) for every 16-column group of this warp's 32-column groups g_first, g_first + 64, ...
-template <class F>
-__device__ __forceinline__ void for_each_32cols(uint32_t taddr, int g_first, int ncols, F&& f) {
-  if (g_first >= ncols) return;
-  uint32_t ra[32], rb[32];
-  auto ld = [&](int g, uint32_t (&r)[32]) { if (g + 32 <= ncols) tmem_ld32(taddr + g, r); else tmem_ld16_lo(taddr + g, r); };
-  auto proc = [&](int g, const uint32_t (&r)[32]) {
-    uint32_t lo[16], hi[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { lo[i] = r[i]; hi[i] = r[16 + i]; }
-    f(lo, g);
-    if (g + 32 <= ncols) f(hi, g + 16);
-  };
-  ld(g_first, ra);
-  tmem_ld_wait();
-  for (int g = g_first; g < ncols; g += 128) {
-    const bool has_b = g + 64 < ncols;
-    if (has_b) ld(g + 64, rb);
-    proc(g, ra);
-    if (has_b) {
-      tmem_ld_wait();
-      const bool has_a = g + 128 < ncols;
-      if (has_a) ld(g + 128, ra);
-      proc(g + 64, rb);
-      if (has_a) tmem_ld_wait();
-    }
-  }
-}
-template <class F>
-__device__ __forceinline__ void for_each_cols(uint32_t taddr, int g_first, int ncols, F&& f) {
-#if IWAE_LDX32
-  for_each_32cols(taddr, g_first, ncols, f);
-#else
-  for_each_16cols(taddr, g_first, ncols, f);
-#endif
-}
-
 // TRACE: the timeline instrumentation (IWAE_TC_TRACE) is compiled into a separate instantiation
 // The five log-density terms of a row (sums over columns).  The evaluation needs only their signed sum (one register);
 // TERMS mode keeps them apart (five registers) and writes them per row.
@@ -908,7 +843,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
           trace_ev<TRACE>(args, trole, tn, tl * 10000 + l * 100 + c * 10 + 5);
           const uint32_t tbase = tmem_base + lane_addr + buf * 128u;
           const int cnt = Ly.chunk_cnt[c], off = Ly.chunk_off[c], cn = Ly.chunk_n[c];
-          const int g_first = LD_COLS * ((half + c) & 1);     // this warp's first column group of the chunk
+          const int g_first = 16 * ((half + c) & 1);     // this warp's first 16-column group of the chunk
 
           if (kind == EPI_TANH) {
             // padded units have zero weights (tanh(0) = 0) and the constant-1 unit has weight 0 and
@@ -916,14 +851,13 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             // split destination: unit j of the layer lands at K column j of the contiguous operand that starts at the z1
             // buffer (the activation buffer follows it in shared memory; bufZ holds exactly KZ_MAX columns)
             uint8_t* dstc = split_dst ? T.bufZ : dst;
-            for_each_cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
+            for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = act_tanh<FAST>(__uint_as_float(r[i]));
               store16(dstc, row, off + g, v);
               // this warp's last group below SLAB_K of chunk 0: the first weight slab's K columns are complete for its rows
-              const int next_g = IWAE_LDX32 ? (((g - g_first) & 16) ? g + 48 : g + 16) : g + 32;     // this warp's next 16-column group
-              if (early_sig && c == 0 && g < SLAB_K && next_g >= SLAB_K) {
+              if (early_sig && c == 0 && g < SLAB_K && g + 32 >= SLAB_K) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(act_early_l);
@@ -1091,7 +1025,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
             // are batched: one lg2 per <= 32 factors (1 + 2^-|l'|) in (1, 2].
             if (FAST) {
               float p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
-              for_each_cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
+              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
                 const float4* sg4 = reinterpret_cast<const float4*>(&T.sgn[off + g]);
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
@@ -1123,7 +1057,7 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
               bern_lg += lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
             } else {
               float bsum = 0.f;
-              for_each_cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
+              for_each_16cols(tbase, g_first, cn, [&](const uint32_t (&r)[16], int g) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float lgt = __uint_as_float(r[i]);
