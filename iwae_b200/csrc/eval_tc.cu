@@ -11,7 +11,8 @@
 // Roles (320 threads): warp 0 = weight producer (cp.async.bulk half-slabs through an mbarrier ring; weights are fp16,
 // pre-packed in the exact smem image, ~0.31 MB per tile and CTA from L2), warp 1 = MMA issuer in the leader (tcgen05.mma,
 // kind::f16, fp32 accumulators in TMEM, two 128-column accumulator buffers; completion multicast to both CTAs' mbarriers)
-// and slab-arrival relay in the peer (both of these roles run inside ONE elected thread each), warps 2-9 = epilogue
+// and slab-arrival relay in the peer (the issuer runs with all 32 lanes converged and warp-uniform control flow, so its
+// descriptors live in uniform registers; producer and relay run inside one elected thread each), warps 2-9 = epilogue
 // (tcgen05.ld -> the bias is already folded into the GEMM through a constant-1 column -> tanh / exp / softplus -> fp16
 // back to smem for the next layer; warps e and e+4 share a TMEM lane quarter and split the accumulator columns;
 // log-density terms accumulate per row in registers; they arrive on the LEADER's mbarriers).  Two CTAs (of two
@@ -515,9 +516,10 @@ __launch_bounds__(NUM_THREADS, CTAS_PER_SM) iwae_eval_tc_kernel(const __grid_con
     // ===================== MMA issuer (leader CTA) =====================
     // The whole warp runs the role CONVERGED: control flow, barrier waits and descriptor arithmetic are warp-uniform,
     // so the compiler keeps them in uniform registers (the operand form tcgen05.mma reads); only the tcgen05
-    // instructions themselves are predicated on the elected lane.  (Round 1 ran the role inside one elected thread:
-    // every MMA then cost ~20 instructions of a dependent chain incl. 4 R2UR moves, ~130 cycles per MMA against the
-    // 56 the tensor pipe needs; with an elect / reconverge per slab it was ~200, scripts/umma_bench3.py.)
+    // instructions themselves are predicated on the elected lane.  This needs the role branch itself to be a UNIFORM
+    // branch (the warp index comes from a shuffle, see the top of the kernel): inside a branch on `tid >> 5` the
+    // compiler must assume divergence and moves every operand with R2UR / VOTEU in front of each MMA.
+    // (-DIWAE_MMA_CONVERGED=0: the role inside one elected thread, 7 R2UR per MMA, 2 % slower.)
 #if IWAE_MMA_CONVERGED
     {
     const uint32_t issue = elect_one_sync();
