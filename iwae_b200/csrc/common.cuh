@@ -145,6 +145,9 @@ struct GemmArgs {
   const float* mul_h = nullptr; int64_t ld_h = 0;         // v *= (1 - H(m,n)^2)   (tanh backward)
   const float* bern_x = nullptr; int bern_B = 0;          // fused Bernoulli log-lik: x[(m % B), n]
   float* bern_partial = nullptr;                          // [M, n_tiles_n] partial row sums
+  const float* dl_x = nullptr; const float* dl_g = nullptr; int dl_B = 0;
+                                                          // backward recompute of the output layer: the stored value is
+                                                          // d(objective)/d logit = g[m] * (x[(m % B), n] - sigmoid(v))
   int small_tile = 0;                                     // 32x32 tiles (more CTAs for skinny outputs)
   int split_k = 1;                                        // >1: gridDim.z partial products, C + z*split_stride (plain products only)
   int64_t split_stride = 0;

@@ -192,6 +192,11 @@ __device__ __forceinline__ void gemm_f32_body(const uint3 vb_, const dim3 vg_, G
           const float h = __ldg(a.mul_h + (int64_t)gm * a.ld_h + gn);
           v *= (1.f - h * h);
         }
+        if (a.dl_x) {
+          // recomputed logit -> its gradient (the arithmetic of dlogits_body on the stored logit, bit for bit)
+          const float sg = 1.f / (1.f + expf(-v));
+          v = __ldg(a.dl_g + gm) * (__ldg(a.dl_x + (int64_t)(gm % a.dl_B) * a.N + gn) - sg);
+        }
         if (Cout) Cout[(int64_t)gm * a.ldc + gn] = v;
         if (a.bern_x) {
           // tfd.Bernoulli(logits).log_prob(x) = -(1-x) softplus(l) - x softplus(-l)   (A.3)
@@ -226,6 +231,8 @@ int gemm_f32(const GemmArgs& a, cudaStream_t st) {
                "gemm_f32: split-K supports plain products only");
   IWAE_REQUIRE(!a.ones_row || (!a.bias && a.act == ACT_NONE && !a.accumulate && !a.mul_h && !a.bern_x),
                "gemm_f32: ones_row supports plain products only");
+  IWAE_REQUIRE(!a.dl_x || (z == 1 && !a.ones_row && !a.bern_x && !a.mul_h && !a.accumulate && a.dl_g && a.dl_B > 0 && a.C),
+               "gemm_f32: the logit-gradient epilogue needs a plain product with g, B and an output");
   const int m_rows = a.M + (a.ones_row ? 1 : 0);
   if (a.small_tile && m_rows >= 256 && a.K >= 512 && z == 1) {
     // tall, narrow outputs (rows = k*B = 1,000 by <= 200 units): 4x2 register tiles halve the shared-memory loads

@@ -44,7 +44,7 @@ print("RESULT " + json.dumps({"elbos": elbos, "sum": float(p.astype(np.float64).
 
 def run_child(kind, **env):
     e = dict(os.environ)
-    for k in ("IWAE_MEGA", "IWAE_CHAIN"):
+    for k in ("IWAE_MEGA", "IWAE_CHAIN", "IWAE_RECOMPUTE"):
         e.pop(k, None)
     e.update(env)
     out = subprocess.run([sys.executable, "-c", CHILD, kind], env=e, capture_output=True, text=True, timeout=300)
@@ -59,6 +59,21 @@ def test_megakernel_step_is_bit_identical(kind):
     got = run_child(kind, IWAE_MEGA="1")
     assert got["elbos"] == ref["elbos"]
     assert got["sum"] == ref["sum"] and got["params"] == ref["params"]
+
+
+@pytest.mark.parametrize("kind", ["iwae2", "iwae1", "ciwae", "dreg"])
+def test_recompute_backward_is_bit_identical(kind):
+    """IWAE_RECOMPUTE=1: the forward of the train step does not write the [k*B, 784] logits and the backward runs the
+    output layer's GEMM again with the gradient in its epilogue (abi.cu, backward_internal; north_star "recomputes decoder
+    activations instead of storing them").  Same tiles, same order: parameters after six steps equal those from stored
+    logits (IWAE_RECOMPUTE=0) bit for bit - also inside the megakernel."""
+    ref = run_child(kind, IWAE_RECOMPUTE="0")
+    got = run_child(kind, IWAE_RECOMPUTE="1")
+    assert got["elbos"] == ref["elbos"]
+    assert got["sum"] == ref["sum"] and got["params"] == ref["params"]
+    if kind == "iwae2":
+        mega = run_child(kind, IWAE_RECOMPUTE="1", IWAE_MEGA="1")
+        assert mega["sum"] == ref["sum"] and mega["params"] == ref["params"]
 
 
 def test_chain_kernel_step_matches():
