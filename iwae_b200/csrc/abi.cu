@@ -118,6 +118,7 @@ extern "C" int iwae_destroy(iwae_ctx* ctx) {
   if (!ctx) return 0;
   cudaDeviceSynchronize();
   tc_release(ctx);
+  tc_encoder_release(ctx);
   ctx->arena.release();
   if (ctx->per_buf) cudaFree(ctx->per_buf);
   if (ctx->stage_x) cudaFree(ctx->stage_x);

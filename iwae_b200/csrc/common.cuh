@@ -108,6 +108,7 @@ struct iwae_ctx {
   int device = 0;
   int sm_count = 148;
   TcPack* tc = nullptr;
+  struct EncPack* enc = nullptr;    // packed hi/lo weights of the tensor-core encoder pre-pass (encoder_tc.cu)
   DpComm* dp = nullptr;
   uint64_t params_version = 0;     // iwae_set_params_version: content version of the caller's parameter buffer (0 = unknown)
   // persistent device staging for iwae_llh_eval / iwae_llh_eval_host (outlives arena resets)
@@ -294,6 +295,11 @@ struct TcTerms { float *lpxz, *prior, *lq1, *lq2, *lp12, *z1, *z2, *q_mu, *q_std
 int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float* y, int64_t N, int k,
                 uint64_t seed, int64_t img_offset, int fast, float* out_per_example, float* out_vae, cudaStream_t st,
                 const float* eps1 = nullptr, const float* eps2 = nullptr, const TcTerms* terms = nullptr);
+// encoder_tc.cu: the BasicBlock q(z1|x) on tcgen05 (fp16 hi+lo operands, fp32-accurate); 0 = done, -1 = shape not supported /
+// switched off (run block_fwd_f32 instead), > 0 = error
+int tc_encoder_fwd(iwae_ctx* ctx, const float* params, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* mu, float* sd,
+                   cudaStream_t st);
+void tc_encoder_release(iwae_ctx* ctx);
 int block_fwd_f32(const float* P, const BlockP& blk, const float* X, int64_t ldx, int64_t M, float* h1, float* h2,
                   float* mu, float* sd, cudaStream_t st, float* l1_scratch = nullptr, iwae_ctx* lane_ctx = nullptr,
                   cudaStream_t lane = nullptr);

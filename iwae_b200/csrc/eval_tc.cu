@@ -1431,7 +1431,7 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   TcPack& tp = *ctx->tc;
   Arena& ar = ctx->arena;
 
-  // encoder pre-pass q(z1|x) (per image, k-independent): fp32 FFMA, ~1% of the FLOPs
+  // encoder pre-pass q(z1|x) (per image, k-independent, ~1% of the FLOPs)
   float *h1, *h2, *mu1, *std1, *pmu = nullptr, *pstd = nullptr;
   const float* xin = x; int64_t ldx = c.n_x;
   const int nc = m.cond() ? c.n_cond : 0;
@@ -1443,7 +1443,12 @@ int tc_llh_eval(iwae_ctx* ctx, const float* params, const float* x, const float*
   IWAE_TRY(ar.get(&h1, (size_t)N * c.h1)); IWAE_TRY(ar.get(&h2, (size_t)N * c.h1));
   if (terms) { mu1 = terms->q_mu; std1 = terms->q_std; IWAE_REQUIRE(mu1 && std1, "tensor-core path: terms mode needs q_mu / q_std buffers"); }
   else { IWAE_TRY(ar.get(&mu1, (size_t)N * c.d1)); IWAE_TRY(ar.get(&std1, (size_t)N * c.d1)); }
-  IWAE_TRY(block_fwd_f32(params, m.enc1, xin, ldx, N, h1, h2, mu1, std1, st));
+  {
+    // tensor cores (encoder_tc.cu) when the block fits, else the fp32 kernels
+    const int rc = tc_encoder_fwd(ctx, params, m.enc1, xin, ldx, N, mu1, std1, st);
+    if (rc > 0) return rc;
+    if (rc < 0) IWAE_TRY(block_fwd_f32(params, m.enc1, xin, ldx, N, h1, h2, mu1, std1, st));
+  }
   if (m.learned_prior()) {
     float* yoh;
     IWAE_TRY(ar.get(&yoh, (size_t)N * nc));

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // returns early whenever any mbarrier of the CTA changes, so a free-running poll loop of the producer
 // warp alone executed 42 % of all instructions of the kernel and took issue slots from the epilogue
 // warps of its SM sub-partition - whose rows then finish every layer last.
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns) {
   uint64_t t0 = 0;
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
