@@ -110,6 +110,9 @@ __device__ __forceinline__ void mbar_wait_pair(uint64_t* bar, uint32_t parity, i
 // elected lane) and its barrier waits keep the control flow warp-UNIFORM (the loop condition is a vote), so that the
 // compiler can keep the descriptor arithmetic in uniform registers - the operand form UTCHMMA reads - instead of moving
 // seven vector registers to uniform ones (R2UR) in front of every MMA.
+#ifndef IWAE_MMA_SLEEP
+#define IWAE_MMA_SLEEP 32
+#endif
 #ifndef IWAE_MMA_CONVERGED
 #define IWAE_MMA_CONVERGED 1
 #endif
@@ -117,7 +120,9 @@ __device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t parity, int tag
 #if IWAE_MMA_CONVERGED
   uint32_t polls = 0;
   while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-    __nanosleep(32);
+#if IWAE_MMA_SLEEP
+    __nanosleep(IWAE_MMA_SLEEP);
+#endif
     if (++polls > (1u << 26)) { if ((threadIdx.x & 31) == 0) printf("iwae_b200: mbarrier timeout tag=%d block=%d\n", tag, blockIdx.x); __trap(); }
   }
 #else
