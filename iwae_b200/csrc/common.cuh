@@ -288,7 +288,7 @@ struct TransposeJobs { TransposeJob job[16]; int count = 0; };
 int transpose_jobs(const TransposeJobs& t, cudaStream_t st);
 
 // ---- fused tcgen05 evaluation (eval_tc.cu) ----
-int tc_pack_weights(iwae_ctx* ctx, const float* params, bool fast, cudaStream_t st);
+int tc_pack_weights(iwae_ctx* ctx, const float* params, bool fast, bool side_ok, cudaStream_t st);
 // TERMS mode of the fused kernel: per-row log-density terms [k,N], latent samples [k,N,d] and the per-image q(z1|x)
 // parameters [N,d1] (q_mu / q_std must be given; every other pointer may be null)
 struct TcTerms { float *lpxz, *prior, *lq1, *lq2, *lp12, *z1, *z2, *q_mu, *q_std; };
