@@ -26,6 +26,20 @@ def test_library_exports_every_header_symbol():
     assert _abi.lib.iwae_version() >= 100
 
 
+def test_diagnostics_library_exports_every_header_symbol():
+    """libiwae_b200_diag.so (tensor-core unit test hook and the micro-benchmarks behind profiles/r02_microbench_*.txt) is a
+    separate library: every function of include/iwae_b200_diag.h must be exported, none of them by the product library."""
+    from iwae_b200 import _abi
+    src = open(os.path.join(ROOT, "include", "iwae_b200_diag.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(iwae_[a-z0-9_]+)\s*\(", src)))
+    assert {"iwae_umma_selftest", "iwae_umma_bench", "iwae_ldtm_bench", "iwae_diag_last_error"} <= set(names)
+    d = _abi.diag_lib()
+    for n in names:
+        assert hasattr(d, n), f"libiwae_b200_diag.so does not export {n}"
+        assert not hasattr(_abi.lib, n), f"{n} belongs to the diagnostics library, not to libiwae_b200.so"
+
+
 @pytest.mark.parametrize("kind,cfg,okind,h,d", [
     (1, (784, 0, 200, 0, 100, 0), "iwae1", 200, 100),
     (1, (784, 0, 200, 0, 50, 0), "iwae1", 200, 50),
