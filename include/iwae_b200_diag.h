@@ -14,7 +14,7 @@ const char* iwae_diag_last_error(void);
  * the fused evaluation kernel stages them (no-swizzle K-major core matrices, one tcgen05.mma chain).
  * A, B fp32 on the device (rounded to fp16 inside).  variant 0 = the descriptor convention the fused
  * kernel uses (LBO = K-direction core-matrix stride, SBO = M/N-direction); 1 = the two swapped
- * (diagnostic only).  Used by tests/test_gpu_eval.py::test_umma_selftest_matches_fp16_gemm. */
+ * (diagnostic only).  Used by tests/test_gpu_eval.py::test_umma_descriptor_selftest. */
 int iwae_umma_selftest(const float* A, const float* B, int32_t N, int32_t K, int32_t variant, float* D,
                        void* stream);
 

@@ -305,7 +305,7 @@ def test_val_step_full_test_set_shape(oracle):
     m.set_weights(params)
     eps1 = rs.randn(k, B, 100).astype(np.float32)
     eps2 = rs.randn(k, B, 50).astype(np.float32)
-    res = m.val_step(X, k, 1.0) if False else m(X, k, 1.0, eps=eps1, eps2=eps2)
+    res = m(X, k, 1.0, eps=eps1, eps2=eps2)          # injected noise, fp32 kernels: comparable with the oracle value by value
     p = oracle.to_torch(params)
     ref = oracle.iwae2_call(p, torch.tensor(X, dtype=torch.float64), k, 1.0, torch.tensor(eps1, dtype=torch.float64),
                             torch.tensor(eps2, dtype=torch.float64))
