@@ -82,3 +82,45 @@ def test_chain_kernel_step_matches():
     a, b = np.array(ref["params"]), np.array(got["params"])
     assert np.max(np.abs(a - b)) <= 1e-5 * max(1.0, float(np.max(np.abs(a))))
     assert np.allclose(ref["elbos"], got["elbos"], rtol=1e-5)
+
+
+EVAL_CHILD = r"""
+import json, sys, numpy as np, torch
+sys.path.insert(0, %r)
+import iwae_b200 as ib
+P, X, Y = ib.data.synthetic_binarised(64, seed=5)
+m = ib.IWAE2([200, 100], [100, 50], out_bias=ib.data.get_bias(P.mean(0)), seed=11)
+per, tot = m.llh(torch.from_numpy(X[:37]).cuda(), 700, precision="tc_f16_fast", seed=123)
+torch.cuda.synchronize()
+print("RESULT " + json.dumps({"per": per.cpu().numpy().astype(np.float64).tolist(), "sum": float(tot)}))
+""" % ROOT
+
+
+def run_eval_child(**env):
+    e = dict(os.environ)
+    for k in ("IWAE_TC_SIDE", "IWAE_TC_NO_EARLY", "IWAE_TC_EARLY2", "IWAE_TC_ENCODER"):
+        e.pop(k, None)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", EVAL_CHILD], env=e, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[len("RESULT "):])
+
+
+def test_fused_kernel_schedule_options_are_bit_identical():
+    """The schedule options of the fused evaluation kernel change WHEN a layer's MMAs are issued, never what is computed:
+    the side layer (IWAE_TC_SIDE=1: second chunk of the first decoder layer inside the hand-off gap of q(z2|z1), other
+    layer order, other packed-weight order) and the early hand-offs (IWAE_TC_NO_EARLY=1, IWAE_TC_EARLY2=0) must give the
+    per-example LLH of the default schedule bit for bit (37 images x k=700: several tiles per image, a ragged last pair)."""
+    ref = run_eval_child()
+    for env in ({"IWAE_TC_SIDE": "1"}, {"IWAE_TC_NO_EARLY": "1"}, {"IWAE_TC_EARLY2": "0"}, {"IWAE_TC_SIDE": "1", "IWAE_TC_NO_EARLY": "1"}):
+        got = run_eval_child(**env)
+        assert got["per"] == ref["per"] and got["sum"] == ref["sum"], env
+    # The tensor-core encoder pre-pass against the fp32 kernels: mu / std differ by ~2e-6 of their scale, but z1 = mu + std*eps
+    # is rounded to fp16 for the first GEMMs, so a last-bit change of mu flips some of those roundings: the two LLHs differ
+    # at the fused kernel's own noise floor (both are within TC_RTOL = 1e-4 of the oracle), not at 1e-6.
+    f32 = run_eval_child(IWAE_TC_ENCODER="0")
+    a, b = np.array(ref["per"]), np.array(f32["per"])
+    err = float(np.max(np.abs(a - b) / np.abs(b)))
+    print(f"\n[encoder on tensor cores vs fp32 kernels] max relative LLH difference {err:.2e}, mean LLH {a.mean():.5f} vs {b.mean():.5f}")
+    assert err < 1e-4 and abs(a.mean() - b.mean()) < 2e-3
