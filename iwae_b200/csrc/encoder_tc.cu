@@ -6,11 +6,12 @@
 // epilogue, activations handed from layer to layer through shared memory - nothing but mu and std reaches HBM.
 //
 // Precision: the outputs feed every sample's z1 = mu + std*eps, so they must be fp32-accurate.  Every operand is an fp16
-// hi + lo PAIR (hi = rn(v), lo = rn(v - hi): ~21 bits) and a product is three MMAs, hi*hi + lo*hi + hi*lo (the lo*lo term
-// is 2^-22 relative), accumulated in fp32.  The first layer's input is the binarised image (or image | one-hot label):
-// exactly representable, so its lo half is zero and the layer needs two MMAs per K step.  Measured against the fp64 oracle
-// (tests/test_gpu_eval.py::test_tensor_core_encoder_matches_fp32_kernels): mu and std within 0.4 - 2.3e-6 of their scale,
-// where the fp32 FFMA kernels are at 0.2 - 0.7e-6 (the lo halves of small weights are fp16 subnormals: ~20 bits).
+// hi + lo PAIR, hi = rn(v) and lo = rn((v - hi) * 2048): the factor 2^11 keeps the lo halves of small weights out of the
+// fp16 subnormals (22 bits in all).  A product is three MMAs into TWO fp32 accumulators in TMEM, D1 += hi*hi and
+// D2 += lo*hi + hi*lo (the lo*lo term is 2^-22 relative), and the epilogue adds them as D1 + D2 / 2048.  The first layer's
+// input is the binarised image (or image | one-hot label): exactly representable, so it needs two MMAs per K step.
+// Measured against the fp64 oracle (tests/test_gpu_eval.py::test_tensor_core_encoder_matches_fp32_kernels): mu and std as
+// close as the fp32 FFMA kernels' (both 0.2 - 0.7e-6 of the tensor's scale).
 //
 // Data movement: the first layer streams K (784 pixels) in slabs of 32: all 128 threads convert their image row's 32
 // pixels to fp16 into a double-buffered A slab while one thread fetches the matching hi/lo weight slab with cp.async.bulk
@@ -30,6 +31,8 @@ constexpr int ENC_NMAX = 208;       // widest layer (padded to 16)
 constexpr int ENC_ABYTES = ENC_M * ENC_SK * 2;                 // 8192: one A slab (fp16)
 constexpr int ENC_WBYTES = 2 * ENC_SK * ENC_NMAX * 2;          // 26624: one weight slab, hi block then lo block
 constexpr int ENC_HBYTES = ENC_M * ENC_NMAX * 2;               // 53248: activations, one of (hi, lo)
+constexpr int ENC_TMEM_COLS = 512;                             // D1 at columns 0.., D2 at columns 256.. (one CTA per SM)
+constexpr float ENC_LO_SCALE = 2048.f;                         // lo halves are stored times 2^11
 
 struct EncLayer {
   int k_real, k_pad, n_real, n_pad;     // k_pad, n_pad: multiples of 16
@@ -62,13 +65,13 @@ __host__ __device__ inline int enc_slab_rows(const EncLayer& L, int s) { return 
 __global__ void __launch_bounds__(128, 1) encoder_tc_kernel(const __grid_constant__ EncArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.mma_done[i], 1); }
     mbar_init(&S.acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(&S.tmem_base, 256); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(&S.tmem_base, ENC_TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,17 +129,18 @@ __global__ void __launch_bounds__(128, 1) encoder_tc_kernel(const __grid_constan
           const uint64_t bhi = make_smem_desc(wb + ks * 2 * lbo_w, lbo_w, 128);
           const uint64_t blo = make_smem_desc(wb + lo_ofs + ks * 2 * lbo_w, lbo_w, 128);
           const uint32_t first = (s == 0 && ks == 0) ? 0u : 1u;
+          const uint32_t d1 = tmem_base, d2 = tmem_base + 256u;        // hi*hi | the two cross terms (times 2^11)
           if (l == 0) {
             const uint64_t ad = make_smem_desc(smem_u32(S.a[buf]) + ks * 2 * (ENC_M * 16), ENC_M * 16, 128);
-            umma_f16(tmem_base, ad, bhi, idesc, first);
-            umma_f16(tmem_base, ad, blo, idesc, 1u);
+            umma_f16(d1, ad, bhi, idesc, first);
+            umma_f16(d2, ad, blo, idesc, first);
           } else {
             const uint32_t kofs = (uint32_t)(s * ENC_SK / 8 + ks * 2) * (ENC_M * 16);
             const uint64_t ahi = make_smem_desc(smem_u32(S.h_hi) + kofs, ENC_M * 16, 128);
             const uint64_t alo = make_smem_desc(smem_u32(S.h_lo) + kofs, ENC_M * 16, 128);
-            umma_f16(tmem_base, ahi, bhi, idesc, first);
-            umma_f16(tmem_base, alo, bhi, idesc, 1u);
-            umma_f16(tmem_base, ahi, blo, idesc, 1u);
+            umma_f16(d1, ahi, bhi, idesc, first);
+            umma_f16(d2, alo, bhi, idesc, first);
+            umma_f16(d2, ahi, blo, idesc, 1u);
           }
         }
         umma_commit(&S.mma_done[buf]);
@@ -147,9 +151,12 @@ __global__ void __launch_bounds__(128, 1) encoder_tc_kernel(const __grid_constan
     mbar_wait(&S.acc_full, (uint32_t)l & 1u, 702);
     tc_fence_after();
     for (int g = 0; g < L.n_pad; g += 16) {
-      uint32_t r[16];
+      uint32_t r[16], r2[16];
       tmem_ld16(taddr + g, r);
+      tmem_ld16(taddr + 256u + g, r2);
       tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(fmaf(__uint_as_float(r2[i]), 1.f / ENC_LO_SCALE, __uint_as_float(r[i])));
       if (l < 2) {
         float hi[16], lo[16];
 #pragma unroll
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(128, 1) encoder_tc_kernel(const __grid_constan
           const int c = g + i;
           const float v = (c < L.n_real) ? tanhf(__uint_as_float(r[i]) + __ldg(L.bias + c)) : 0.f;
           const float h = __half2float(__float2half_rn(v));
-          hi[i] = h; lo[i] = v - h;
+          hi[i] = h; lo[i] = (v - h) * ENC_LO_SCALE;
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -184,8 +191,7 @@ __global__ void __launch_bounds__(128, 1) encoder_tc_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
   }
-  (void)lane;
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, ENC_TMEM_COLS);
 }
 
 // Weights of one layer -> hi / lo fp16 slabs in the shared-memory image: slab s = [hi block | lo block], each
@@ -203,7 +209,7 @@ __global__ void encoder_pack_kernel(const float* __restrict__ W, int ldw, int n1
     const int64_t slab_base = (int64_t)s * 2 * ENC_SK * L.n_pad;                  // halves; full slabs precede
     const int64_t pos = ((int64_t)(kin >> 3) * L.n_pad + n) * 8 + (kin & 7);
     out[slab_base + pos] = __float2half_rn(hi);
-    out[slab_base + (int64_t)rows * L.n_pad + pos] = __float2half_rn(v - hi);
+    out[slab_base + (int64_t)rows * L.n_pad + pos] = __float2half_rn((v - hi) * ENC_LO_SCALE);
   }
 }
 
