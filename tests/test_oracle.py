@@ -204,3 +204,47 @@ def test_philox_bernoulli_restatement(oracle):
     u = (words >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
     probe = np.full(8, 0.5, dtype=np.float32)                   # elements 4..7 use Philox call q = 1
     assert np.array_equal(oracle.philox_bernoulli(probe, 9, 7)[4:], (u < 0.5).astype(np.float32))
+
+
+def test_two_layer_call_against_numpy_scipy(oracle):
+    """A third, torch-free statement of iwae2.IWAE.call (iwae2.py:109-167): plain NumPy matmuls with SciPy's
+    norm.logpdf / expit / logsumexp (another library lineage than torch.distributions) must reproduce every per-row
+    term, log_w, the importance weights and the three ELBOs of the oracle."""
+    from scipy.special import expit, logsumexp
+    from scipy.stats import norm
+    c = make_case(oracle, "iwae2", [200, 100], [100, 50], 4, 6, seed=9, scale=0.7)
+    k = 6
+    P = {n: np.asarray(v, dtype=np.float64) for n, v in c["params"].items()}
+    x = c["x"].astype(np.float64)
+    e1, e2 = c["eps1"].astype(np.float64), c["eps2"].astype(np.float64)
+
+    def block(prefix, inp):
+        h = np.tanh(inp @ P[prefix + ".l1.kernel"] + P[prefix + ".l1.bias"])
+        h = np.tanh(h @ P[prefix + ".l2.kernel"] + P[prefix + ".l2.bias"])
+        return h @ P[prefix + ".lmu.kernel"] + P[prefix + ".lmu.bias"], np.exp(h @ P[prefix + ".lstd.kernel"] + P[prefix + ".lstd.bias"]) + 1e-6
+
+    mu1, sd1 = block("encoder.encode_x_to_z1", x)
+    z1 = mu1 + sd1 * e1
+    mu2, sd2 = block("encoder.encode_z1_to_z2", z1)
+    z2 = mu2 + sd2 * e2
+    pmu, psd = block("decoder.decode_z2_to_z1", z2)
+    h = z1
+    for i, act in enumerate((np.tanh, np.tanh, lambda t: t)):
+        h = act(h @ P[f"decoder.decode_z1_to_x.dense{i}.kernel"] + P[f"decoder.decode_z1_to_x.dense{i}.bias"])
+    pr = expit(h)
+    terms = {
+        "lpxz1": (x * np.log(pr) + (1.0 - x) * np.log1p(-pr)).sum(-1),
+        "lpz1z2": norm.logpdf(z1, pmu, psd).sum(-1),
+        "lpz2": norm.logpdf(z2).sum(-1),
+        "lqz1x": norm.logpdf(z1, mu1, sd1).sum(-1),
+        "lqz2z1": norm.logpdf(z2, mu2, sd2).sum(-1),
+    }
+    log_w = terms["lpxz1"] + terms["lpz1z2"] + terms["lpz2"] - terms["lqz1x"] - terms["lqz2z1"]
+    p64 = oracle.to_torch(c["params"], torch.float64)
+    res = oracle.iwae2_call(p64, torch.tensor(x), k, 1.0, torch.tensor(e1), torch.tensor(e2))
+    for name, v in terms.items():
+        assert np.allclose(res[name].numpy(), v, rtol=1e-9, atol=1e-8), name
+    assert np.allclose(res["log_w"].numpy(), log_w, rtol=1e-10, atol=1e-8)
+    assert np.allclose(res["al"].numpy(), np.exp(log_w - logsumexp(log_w, axis=0)), rtol=1e-9, atol=1e-12)
+    assert abs(float(res["iwae_elbo"]) - float((logsumexp(log_w, axis=0) - np.log(k)).mean())) < 1e-9
+    assert abs(float(res["vae_elbo"]) - float(log_w.mean())) < 1e-9
