@@ -117,7 +117,10 @@ int iwae_forward(iwae_ctx* ctx, const float* params, const float* x, const float
 /* The same call with the fused tensor-core kernel as the engine (model.val_step on the whole test set at k = n_samples,
  * main.py:152; generate_and_save_posteriors' call(Xtest, 10), src/iwae1.py:207): every output of iwae_forward except
  * `logits` and `dreg` - per-row terms, log_w, al, per-example ELBOs, SNIS means, z1 / z2, q_mu / q_std, scalars - with
- * no [k,B,784] tensor ever materialised.  Philox noise only.  precision: IWAE_PREC_TC_F16 or IWAE_PREC_TC_F16_FAST. */
+ * no [k,B,784] tensor ever materialised.  Philox noise only.  precision: IWAE_PREC_TC_F16 or IWAE_PREC_TC_F16_FAST.
+ * The tensor-core precisions (here and in iwae_llh_eval / iwae_monitor_eval / iwae_llh_eval_eps) REQUIRE binarised images,
+ * x in {0,1} exactly, as the reference feeds them (utils.bernoullisample, main.py:117-120): the Bernoulli term is evaluated
+ * as -softplus((1-2x) l) and the encoder's first GEMM takes x as an exact fp16 operand.  Real-valued x: IWAE_PREC_FP32. */
 int iwae_forward_tc(iwae_ctx* ctx, const float* params, const float* x, const float* y, int32_t B, int32_t k,
                     float beta, uint64_t seed, int64_t img_offset, int32_t precision, const iwae_outputs* outs,
                     void* stream);

@@ -674,7 +674,9 @@ class IWAE:
         return bool(ok)
 
     def _precision(self, precision):
-        """None / "auto": the fused tensor-core kernel when the architecture fits it, else the fp32 CUDA kernels."""
+        """None / "auto": the fused tensor-core kernel when the architecture fits it, else the fp32 CUDA kernels.
+        The tensor-core precisions assume BINARISED images (x in {0,1} exactly, as main.py feeds them): pass
+        precision="fp32" for real-valued x."""
         if precision in (None, "auto"):
             return "tc_f16_fast" if self.tc_supported() else "fp32"
         return precision
